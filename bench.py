@@ -1,0 +1,476 @@
+#!/usr/bin/env python
+"""bench.py -- signals clustered / s (+ coverage bins / s) of the TIDDIT hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload wgs30x|config2|tumor60x]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+A step = one pass of the clustering hot path (all (chrA,chrB) pairs: key packing, both radix sorts, both
+eps-range-query/run-labelling kernels, id assignment, scatter) over the synthetic 30X-WGS-shaped signal set of
+BASELINE.json configs[2] (20 M signals, 300 pairs, eps=500, m=3).  With N > 1 the pairs are sharded over the
+ranks (LPT by signal count, no data-path collective) and the labels are all-gathered once per step
+(BASELINE.json configs[3]; total work fixed => "scaling": "strong").  Rank 0 prints ONE JSON line.
+
+value        device-resident inputs, CUDA events, max over ranks
+e2e          the same through the host front end: pinned host arrays -> H2D -> kernels -> D2H labels, every step
+roofline     the eps-range-query kernel (window_runs<X>): 8 B/signal / its event-timed duration
+cpu_baseline the REAL reference (oracle/_ref, compiled from the upstream sources) or the C port, 1 core,
+             on a bounded sample of whole pairs of the same workload
+coverage     the coverage kernel on 30X-shaped reads (reads/s, bins/s, its own roofline and CPU baseline)
+
+--impl reference times the reference's own CPU path (all host cores, a bounded sample per step).
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    "wgs30x": dict(gen="wgs30x_signals", n=20_000_000, eps=500, m=3,
+                   desc="30X-WGS-shaped synthetic set: 20M signals over 300 chrom-pairs (BASELINE configs[2])"),
+    "config2": dict(gen="config2_signals", n=1_000_000, eps=500, m=3,
+                    desc="1M synthetic signals, single chrom-pair (BASELINE configs[1])"),
+    "tumor60x": dict(gen="tumor60x_signals", n=50_000_000, eps=1000, m=5,
+                     desc="60X tumor-like synthetic set: 50M signals (BASELINE configs[4])"),
+}
+METRIC = "signals_clustered_per_sec"
+UNIT = "signals/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks during the timed region (NVML, sampled from a thread)
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x1: "gpu_idle", 0x2: "applications_clocks_setting", 0x4: "sw_power_cap", 0x8: "hw_slowdown",
+               0x10: "sync_boost", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown",
+               0x80: "hw_power_brake_slowdown", 0x100: "display_clock_setting"}
+
+    def __init__(self, index):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit and name != "gpu_idle":
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def __enter__(self):
+        if self.nv is not None:
+            self._thread = threading.Thread(target=self._run, daemon=True)
+            self._thread.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thread is not None:
+            self._thread.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["nvml unavailable"]}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# sharding (host logic, also exercised by tests/test_dist.py on gloo)
+# ---------------------------------------------------------------------------------------------------
+def lpt_assign(sizes, n_ranks):
+    """Longest-processing-time greedy: pair -> rank, balancing the signal counts."""
+    load = [0] * n_ranks
+    owner = np.zeros(len(sizes), dtype=np.int64)
+    for p in np.argsort(-np.asarray(sizes), kind="stable"):
+        r = int(np.argmin(load))
+        owner[p] = r
+        load[r] += int(sizes[p])
+    return owner
+
+
+def shard_workload(posA, posB, seg_off, owner, rank):
+    """The signals of the pairs `rank` owns, pair order kept -> posA, posB, seg_off of the shard."""
+    mine = np.flatnonzero(owner == rank)
+    sizes = np.diff(seg_off)[mine]
+    idx = np.concatenate([np.arange(seg_off[p], seg_off[p + 1]) for p in mine]) if len(mine) else np.zeros(0, np.int64)
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    return posA[idx], posB[idx], off, idx
+
+
+# ---------------------------------------------------------------------------------------------------
+# the reference on the host cores
+# ---------------------------------------------------------------------------------------------------
+def _ref_modules():
+    from oracle import ref
+    return ref.load()
+
+
+def _ref_pair_seconds(job):
+    """One (chrA,chrB) list through the reference: sorted(key=posA) + DBSCAN.main (tiddit_cluster.pyx:152-154)."""
+    a, b, eps, m, use_ref = job
+    rows = [[int(x), int(y), i] for i, (x, y) in enumerate(zip(a, b))]
+    t0 = time.perf_counter()
+    if use_ref:
+        R = _ref_modules()
+        arr = np.array(sorted(rows, key=lambda l: l[0]))
+        R.DBSCAN.main(arr, eps, m)
+    else:
+        from oracle import oracle
+        arr = np.array(sorted(rows, key=lambda l: l[0]))
+        oracle.main(arr, eps, m)
+    return time.perf_counter() - t0
+
+
+def sample_jobs(posA, posB, seg_off, n_crops, crop=50_000, sparse_share=0.3):
+    """A bounded, workload-shaped sample for the CPU reference: `n_crops` posA-window crops of ~`crop` signals
+    cut out of the largest pairs (local density and clusters intact -- the dense, expensive 70 % of the
+    workload) plus whole small pairs adding `sparse_share` of the signals (the sparse inter-chromosomal 30 %).
+    Whole large pairs cost the reference minutes to hours each (O(#clusters * n) y-pass), so per signal this
+    sample is CHEAPER for the CPU than the full workload."""
+    sizes = np.diff(seg_off)
+    big = np.argsort(-sizes, kind="stable")
+    jobs, total = [], 0
+    for i in range(n_crops):
+        p = int(big[i % min(len(big), 24)])
+        lo, hi = int(seg_off[p]), int(seg_off[p + 1])
+        k = min(crop, hi - lo)
+        order = np.argsort(posA[lo:hi], kind="stable")
+        s0 = ((i // 24) * 7 + 1) * k % max(1, (hi - lo) - k + 1)
+        pick = np.sort(order[s0:s0 + k])                      # insertion order kept
+        jobs.append((posA[lo:hi][pick], posB[lo:hi][pick]))
+        total += k
+    want_sparse = int(total * sparse_share / (1 - sparse_share)) if len(sizes) > 1 else 0
+    got = 0
+    for p in np.argsort(sizes, kind="stable"):
+        if got >= want_sparse:
+            break
+        if sizes[p] < 1000 or sizes[p] > crop:
+            continue
+        jobs.append((posA[seg_off[p]:seg_off[p + 1]], posB[seg_off[p]:seg_off[p + 1]]))
+        got += int(sizes[p])
+    return jobs, total + got
+
+
+def cpu_cluster_baseline(posA, posB, seg_off, eps, m, n_crops=4):
+    use_ref = _ref_modules() is not None
+    jobs, total = sample_jobs(posA, posB, seg_off, n_crops)
+    secs = sum(_ref_pair_seconds((a, b, eps, m, use_ref)) for a, b in jobs)
+    return {"value": total / secs, "unit": UNIT, "cores": 1, "kind": "reference" if use_ref else "port",
+            "sample": "%d signals: %d posA-window crops of 50k signals from the largest pairs + whole small pairs "
+                      "for the sparse 30%%; sorted(key=posA) + DBSCAN.main each (tiddit_cluster.pyx:152-154), "
+                      "%.1f s on 1 core; whole large pairs are far slower per signal (O(#clusters*n) y-pass), so "
+                      "this flatters the CPU" % (total, n_crops, secs)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU clustering on all host cores, bounded sample per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from concurrent.futures import ProcessPoolExecutor
+    from tiddit_b200 import synth
+    w = WORKLOADS[args.workload]
+    posA, posB, seg_off, _ = getattr(synth, w["gen"])(args.signals or w["n"])
+    use_ref = _ref_modules() is not None
+    cores = os.cpu_count() or 1
+    jobs, total = sample_jobs(posA, posB, seg_off, cores * args.ref_crops_per_core)
+    jobs = [(a, b, w["eps"], w["m"], use_ref) for a, b in jobs]
+    times = []
+    with ProcessPoolExecutor(max_workers=cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            list(pool.map(_ref_pair_seconds, jobs, chunksize=1))
+            dt = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(dt)
+    sec = float(np.mean(times))
+    value = total / sec
+    sample = ("%d signals per step: %d posA-window crops of 50k signals from the largest pairs + whole small pairs, "
+              "over a %d-process pool (one pair per task, as the reference clusters a pair serially)"
+              % (total, cores * args.ref_crops_per_core, cores))
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": w["desc"], "eps": w["eps"], "min_pts": w["m"]},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference" if use_ref else "port",
+                             "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ---------------------------------------------------------------------------------------------------
+# coverage leg (N = 1)
+# ---------------------------------------------------------------------------------------------------
+def coverage_leg(torch, args, hbm_peak, flush):
+    from tiddit_b200 import device_ops, synth, _lib
+    lens = np.array([ln for _, ln in synth.GRCH38], dtype=np.int64)
+    z = 500
+    n_reads = args.cov_reads
+    per = np.floor(n_reads * lens / lens.sum()).astype(np.int64)
+    per[0] += n_reads - per.sum()
+    g = torch.Generator(device="cuda")
+    g.manual_seed(7)
+    starts, ends = [], []
+    for ln, k in zip(lens, per):                       # coordinate-sorted per contig, like a BAM
+        s = torch.sort((torch.rand(int(k), device="cuda", generator=g, dtype=torch.float64) * int(ln)).to(torch.int32)).values
+        starts.append(s)
+        ends.append(torch.clamp(s + 150, max=int(ln)))
+    start, end = torch.cat(starts), torch.cat(ends)
+    del starts, ends
+    nb = np.ceil(lens / float(z)).astype(np.int64)
+    read_off = torch.from_numpy(np.concatenate([[0], np.cumsum(per)]).astype(np.int64)).cuda()
+    bin_off_h = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+    bin_off = torch.from_numpy(bin_off_h).cuda()
+    ebs = torch.from_numpy((lens - (nb - 1) * z).astype(np.int32)).cuda()
+    n_bins = int(bin_off_h[-1])
+    bins = torch.zeros(n_bins, dtype=torch.float64, device="cuda")
+    bad = device_ops.new_first_bad(torch)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    times = []
+    for it in range(args.warmup + args.steps):
+        bins.zero_()
+        flush()
+        ev[0].record()
+        device_ops.coverage_accumulate_contigs_device(start, end, read_off, bin_off, ebs, z, bins, bad)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            times.append(ev[0].elapsed_time(ev[1]))
+    ms = float(np.mean(times))
+    mean_cov = float(bins.mean().item())
+    alg_bytes = 8.0 * n_reads + 8.0 * n_bins
+    out = {"reads": n_reads, "bins": n_bins, "bin_size": z, "ms_per_step": ms, "reads_per_sec": n_reads / ms * 1e3,
+           "bins_per_sec": n_bins / ms * 1e3, "mean_coverage": mean_cov,
+           "roofline": {"bound": "hbm", "achieved": alg_bytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg_bytes / ms / 1e6 / hbm_peak, "traffic": None, "kernel": "coverage_kernel",
+                        "algorithmic_bytes": "8 B/read + 8 B/bin"}}
+    if args.no_cpu:
+        return out
+    # CPU: the reference's update_coverage per read (1 core), bounded sample
+    k = min(n_reads, 2_000_000)
+    hs, he = start[:k].cpu().numpy(), end[:k].cpu().numpy()
+    R = _ref_modules()
+    ln0 = int(lens[0])
+    t0 = time.perf_counter()
+    if R is not None:
+        cov, e0 = R.tiddit_coverage.create_coverage({"SQ": [{"SN": "chr1", "LN": ln0}]}, z, "chr1")
+        upd = R.tiddit_coverage.update_coverage
+        for a, b in zip(hs.tolist(), he.tolist()):
+            upd(a, b, z, cov, e0)
+        kind = "reference"
+    else:
+        from oracle import oracle
+        cov, e0 = oracle.create_coverage({"SQ": [{"SN": "chr1", "LN": ln0}]}, z, "chr1")
+        oracle.update_coverage_batch(hs, he, z, cov, e0)
+        kind = "port"
+    dt = time.perf_counter() - t0
+    out["cpu_baseline"] = {"value": k / dt, "unit": "reads/s", "cores": 1, "kind": kind,
+                           "sample": "first %d reads of chr1, one update_coverage call per read, %.1f s" % (k, dt)}
+    # parity spot check on the same sample (test infrastructure as checker)
+    from oracle import oracle
+    chk = np.zeros(int(nb[0]))
+    oracle.update_coverage_batch(hs, he, z, chk, int(lens[0] - (nb[0] - 1) * z))
+    dchk = torch.zeros(int(nb[0]), dtype=torch.float64, device="cuda")
+    device_ops.coverage_accumulate_device(start[:k], end[:k], z, int(lens[0] - (nb[0] - 1) * z), dchk,
+                                          device_ops.new_first_bad(torch))
+    out["verified"] = bool(np.array_equal(dchk.cpu().numpy().view(np.uint64), chk.view(np.uint64)))
+    del start, end, bins
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# main (our arm)
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="wgs30x", choices=sorted(WORKLOADS))
+    ap.add_argument("--signals", type=int, default=0, help="override the workload's signal count")
+    ap.add_argument("--cov-reads", type=int, default=617_653_966, help="reads for the coverage leg (30X = 617653966)")
+    ap.add_argument("--no-coverage", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
+    ap.add_argument("--ref-crops-per-core", type=int, default=1, help="--impl reference: 50k-signal crops per core per step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from tiddit_b200 import build
+    build.build()
+    from tiddit_b200 import device_ops, synth, _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    hbm_peak, peak_src = peaks()
+    w = WORKLOADS[args.workload]
+    eps, m = w["eps"], w["m"]
+    posA, posB, seg_off, L = getattr(synth, w["gen"])(args.signals or w["n"])
+    n_total = len(posA)
+    P_total = len(seg_off) - 1
+
+    owner = lpt_assign(np.diff(seg_off), world)
+    a_h, b_h, off_h, idx_h = shard_workload(posA, posB, seg_off, owner, rank) if world > 1 else \
+        (posA, posB, seg_off, None)
+    n_mine, P_mine = len(a_h), len(off_h) - 1
+    shard_sizes = [int(np.diff(seg_off)[owner == r].sum()) for r in range(world)]
+    pad = max(shard_sizes)
+
+    a_pin = torch.from_numpy(a_h).pin_memory()
+    b_pin = torch.from_numpy(b_h).pin_memory()
+    off_pin = torch.from_numpy(off_h).pin_memory()
+    a_d, b_d, off_d = a_pin.cuda(), b_pin.cuda(), off_pin.cuda()
+    labels_d = torch.empty(pad, dtype=torch.int32, device="cuda")
+    gathered = torch.empty(world * pad, dtype=torch.int32, device="cuda") if world > 1 else None
+    out_pin = torch.empty(world * pad if world > 1 else n_total, dtype=torch.int32).pin_memory()
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+
+    def flush():
+        flush_buf.add_(1)          # 256 MB read+write > the 126 MB L2
+
+    def step_device():
+        device_ops.cluster_labels_device(a_d, b_d, off_d, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, labels_d)
+
+    def step_e2e(a_dev, b_dev, off_dev):
+        a_dev.copy_(a_pin, non_blocking=True)
+        b_dev.copy_(b_pin, non_blocking=True)
+        off_dev.copy_(off_pin, non_blocking=True)
+        device_ops.cluster_labels_device(a_dev, b_dev, off_dev, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, labels_d)
+            if rank == 0:
+                out_pin.copy_(gathered, non_blocking=True)
+        else:
+            out_pin.copy_(labels_d[:n_total], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        barrier()
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for s, e in ev:
+            flush()
+            if world > 1:
+                dist.barrier()
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        ms = sum(s.elapsed_time(e) for s, e in ev)
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()) / steps
+
+    launches0 = _lib.launch_count()
+    with ClockSampler(local) as clk:
+        ms_step = timed(step_device, args.steps, args.warmup)
+        launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup)
+        a2, b2, off2 = torch.empty_like(a_d), torch.empty_like(b_d), torch.empty_like(off_d)
+        ms_e2e = timed(lambda: step_e2e(a2, b2, off2), max(3, args.steps // 2), 2)
+    clocks = clk.summary()
+
+    # per-stage device times of one more (untimed) pass -> roofline of the eps-range-query kernel
+    stage_ms = {}
+    reps = 5
+    for _ in range(reps):
+        flush()
+        torch.cuda.synchronize()
+        _lib.profile_begin()
+        device_ops.cluster_labels_device(a_d, b_d, off_d, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
+        for name, ms in _lib.profile_end():
+            stage_ms[name] = stage_ms.get(name, 0.0) + ms / reps
+    tot_stage = sum(stage_ms.values()) or 1.0
+    k_ms = stage_ms.get("window_runs_x", float("nan"))
+    alg = 8.0 * n_mine
+    roofline = {"bound": "hbm", "kernel": "window_runs_kernel<X_PAIRS> (eps-range query + run labelling, posA axis)",
+                "achieved": alg / k_ms / 1e6, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
+                "frac": alg / k_ms / 1e6 / hbm_peak, "traffic": None,
+                "algorithmic_bytes_per_launch": alg, "ms_per_launch": k_ms,
+                "share_of_step": k_ms / tot_stage,
+                "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+                "pipeline": {"algorithmic_bytes": 12.0 * n_mine, "achieved": 12.0 * n_mine / ms_step / 1e6,
+                             "frac": 12.0 * n_mine / ms_step / 1e6 / hbm_peak}}
+
+    line = {"metric": METRIC, "value": n_total / ms_step * 1e3, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": w["desc"], "signals": n_total, "pairs": P_total, "eps": eps, "min_pts": m,
+                       "sharding": "pairs LPT over %d ranks, one all-gather of int32 labels" % world if world > 1
+                       else "single GPU", "l2": "256 MB flush between timed steps (and inputs > L2 at N=1)"},
+            "e2e": {"value": n_total / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + off_h.nbytes),
+                    "d2h_bytes_per_step": int(out_pin.numel() * 4) if rank == 0 else 0},
+            "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
+            "clocks": clocks, "roofline": roofline}
+
+    if world == 1 and rank == 0:
+        if not args.no_cpu:
+            line["cpu_baseline"] = cpu_cluster_baseline(posA, posB, seg_off, eps, m)
+        if not args.no_coverage:
+            del a2, b2, off2
+            torch.cuda.empty_cache()
+            try:
+                line["coverage"] = coverage_leg(torch, args, hbm_peak, flush)
+            except torch.cuda.OutOfMemoryError as exc:
+                line["coverage"] = {"error": "out of memory: %s" % exc}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

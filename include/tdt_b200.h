@@ -1,0 +1,132 @@
+/*
+ * tdt_b200.h -- C ABI of libtdt_b200.so, the B200 (sm_100a) implementation of TIDDIT's
+ * signal-clustering / coverage / GC hot path.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _h (host);
+ *   - the caller owns every buffer; the library allocates nothing persistent: scratch comes from
+ *     the caller-provided workspace `ws` (size it with the matching *_workspace_bytes call);
+ *   - work is enqueued on `stream` (a cudaStream_t passed as void*); functions documented as
+ *     "synchronises" block on that stream once, everything else returns as soon as it is enqueued;
+ *   - return value: 0 = ok, < 0 = error (TDT_E_*), text via tdt_last_error() (thread-local);
+ *   - no exceptions cross the boundary; distinct streams may be driven from distinct threads.
+ *
+ * Each entry point cites the reference interface it replaces (paths relative to the upstream
+ * TIDDIT tree, v3.9.5).
+ */
+#ifndef TDT_B200_H
+#define TDT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define TDT_API __attribute__((visibility("default")))
+#else
+#define TDT_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TDT_OK 0
+#define TDT_E_ARG (-1)       /* invalid argument (min_pts < 2, bin_size <= 0, negative sizes ...)   */
+#define TDT_E_WORKSPACE (-2) /* workspace missing or too small                                      */
+#define TDT_E_CUDA (-3)      /* a CUDA runtime call failed                                          */
+#define TDT_E_RANGE (-4)     /* a coordinate is outside the range the call was told to expect       */
+
+TDT_API int tdt_version(void);
+TDT_API const char *tdt_last_error(void);
+
+/* --------------------------------------------------------------------------------------------
+ * Clustering.  Replaces tiddit/tiddit_cluster.pyx:140-160 (per (chrA,chrB): stable sort by posA,
+ * DBSCAN.main, labels back in insertion order) for ALL pairs in one call, and therefore
+ * tiddit/DBSCAN.py:125-129 (main), :33-64 (x_coordinate_clustering), :66-123
+ * (y_coordinate_clustering).
+ *
+ * Signals: posA[i], posB[i] >= 0 (int32), i in [0, n).  Pairs are given either
+ *   (a) segmented: seg_off[P+1] (device, int64), signals of pair p are [seg_off[p], seg_off[p+1])
+ *       in insertion order (= the order of the reference's global signal index), or
+ *   (b) keyed: pair_id[i] in [0, P) per signal, signals in any interleaving; the relative order of
+ *       the signals of one pair is their insertion order.
+ * labels_out[i] (int32, input order): the reference's own ids -- x-pass ids 0..nx-1 in order of run
+ * start, y-pass sub-clusters nx, nx+1, ... in visiting order, -1 = noise -- per pair, so they are
+ * bit-identical to int(DBSCAN.main(...)[i]) (ids are < the pair's signal count).
+ * max_pos: an upper bound on every posA/posB (e.g. the longest contig); 0 = unknown (31 bits assumed).
+ *          It only sizes the radix-sort keys; a coordinate above it returns TDT_E_RANGE.
+ * Synchronises `stream` once (the y-pass sort is sized from the x-pass result).
+ * ------------------------------------------------------------------------------------------ */
+TDT_API size_t tdt_cluster_workspace_bytes(int64_t n, int32_t P);
+
+TDT_API int tdt_cluster_labels(const int32_t *posA, const int32_t *posB, const int64_t *seg_off, int64_t n, int32_t P,
+                       int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out, void *ws,
+                       size_t ws_bytes, void *stream);
+
+TDT_API int tdt_cluster_labels_keyed(const int32_t *posA, const int32_t *posB, const int32_t *pair_id, int64_t n, int32_t P,
+                             int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out, void *ws,
+                             size_t ws_bytes, void *stream);
+
+/* DBSCAN.py:125-129 on ONE array in the caller's order (the reference does not sort inside
+ * DBSCAN.main; its caller does): x-pass over x[] as given -- window max of |x[j]-x[i]|, so unsorted
+ * input behaves like the reference -- then the y-pass.  Same workspace as tdt_cluster_labels(n, 1).
+ * Synchronises once. */
+TDT_API int tdt_dbscan_main(const int32_t *x, const int32_t *y, int64_t n, int32_t eps, int32_t min_pts, int32_t max_pos,
+                    int32_t *labels_out, void *ws, size_t ws_bytes, void *stream);
+
+/* DBSCAN.py:33-64 (x_coordinate_clustering; second caller tiddit_contig_analysis.pyx:176):
+ * labels_out[i] = run id or -1; *last_id_out (device int32) = the returned cluster_id (-1 = none).
+ * Does not synchronise. */
+TDT_API int tdt_xpass_labels(const int32_t *x, int64_t n, int32_t eps, int32_t min_pts, int32_t *labels_out,
+                     int32_t *last_id_out, void *ws, size_t ws_bytes, void *stream);
+
+/* DBSCAN.py:66-123 (y_coordinate_clustering) as a stand-alone call: labels_io holds the x-pass ids
+ * (ids in [0, cluster_id], -1 = noise) and is rewritten in place; *cluster_id_io (device int32) is
+ * advanced by the number of extra sub-clusters like the reference's return value.
+ * Synchronises once. */
+TDT_API int tdt_ypass_labels(const int32_t *y, int64_t n, int32_t eps, int32_t min_pts, int32_t max_pos,
+                     int32_t *labels_io, int32_t *cluster_id_io, void *ws, size_t ws_bytes, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * Coverage.  Replaces tiddit/tiddit_coverage.pyx:48-74 (update_coverage) applied to a batch of
+ * reads: bins[] (float64) is accumulated IN PLACE (the reference's `+=`).  Every addend is the
+ * float32 quotient the reference computes, all partial sums are exact in float64, so the result is
+ * bit-identical for any summation order.
+ *   single contig : reads (start[i], end[i]) against bins[0..n_bins) with the contig's end_bin_size;
+ *   all contigs   : reads grouped by contig, read_off[C+1] / bin_off[C+1] (device int64) delimit the
+ *                   reads / the bins of contig c inside start/end / bins, end_bin_size[C] (device).
+ * A read the reference would reject (IndexError: a touched bin outside [0, n_bins)) is skipped and
+ * its index is min-reduced into *first_bad (device int64, caller initialises to -1 semantics:
+ * INT64_MAX = none); negative bin indices (Python wrap-around in the reference) are rejected too.
+ * Does not synchronise.
+ * ------------------------------------------------------------------------------------------ */
+TDT_API int tdt_coverage_accumulate(const int32_t *start, const int32_t *end, int64_t n_reads, int32_t bin_size,
+                            int32_t end_bin_size, double *bins, int64_t n_bins, int64_t *first_bad, void *stream);
+
+TDT_API int tdt_coverage_accumulate_contigs(const int32_t *start, const int32_t *end, int64_t n_reads,
+                                    const int64_t *read_off, const int64_t *bin_off, const int32_t *end_bin_size,
+                                    int32_t C, int32_t bin_size, double *bins, int64_t n_bins_total,
+                                    int64_t *first_bad, void *stream);
+
+/* --------------------------------------------------------------------------------------------
+ * GC bins.  Replaces tiddit/tiddit_gc.pyx:6-33 (binned_gc) on a contig sequence resident in HBM
+ * (one byte per base, as pysam.FastaFile.fetch returns it): out[b] (int8) = -1 if
+ * #N/bin_size > n_cutoff else rint(100 * #GC / #chars), ceil(len / bin_size) bins.
+ * Does not synchronise.
+ * ------------------------------------------------------------------------------------------ */
+TDT_API int tdt_gc_bins(const uint8_t *seq, int64_t len, int32_t bin_size, double n_cutoff, int8_t *out, void *stream);
+
+/* Per-stage device timing for bench.py's roofline line: between tdt_profile_begin() and tdt_profile_end()
+ * every stage of every call is bracketed by CUDA events on the caller's stream; tdt_profile_end synchronises
+ * on them and writes "stage=milliseconds\n" lines into out (returns the byte count).  Not thread-safe. */
+TDT_API void tdt_profile_begin(void);
+TDT_API int tdt_profile_end(char *out, size_t cap);
+
+/* Launch counter: number of kernels this library has launched in the calling process (all threads),
+ * for bench.py's "gpu_launches" line. */
+TDT_API int64_t tdt_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TDT_B200_H */

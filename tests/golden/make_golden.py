@@ -1,0 +1,225 @@
+#!/usr/bin/env python
+"""Generate the golden vectors under tests/golden/ by running the REAL reference (compiled from
+/root/reference into oracle/_ref/ by oracle/build_ref.py).  Run in the build container only; the
+outputs are committed so that the tests need neither /root/reference nor oracle/_ref.
+
+    python tests/golden/make_golden.py
+"""
+import json
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import build_ref, ref  # noqa: E402
+
+build_ref.build()
+R = ref.load()
+assert R is not None, "the reference could not be compiled"
+
+
+def dbscan_cases():
+    """App. A.4 known-answer vectors + random small cases, labels from the real DBSCAN.py."""
+    cases = []
+    kats = [
+        ([0, 1, 5, 9, 12, 14, 14], [0] * 7, 10, 3),
+        ([1, 1, 1, 10], [2, 2, 2, 11], 0.1, 2),
+        ([0, 1, 2, 3, 100, 101, 102, 103], [0] * 8, 10, 3),
+        (list(range(8)), [0, 0, 0, 0, 1000, 1000, 1000, 1000], 10, 3),
+        (list(range(8)), [0, 1000] * 4, 10, 3),
+        (list(range(9)), [0, 0, 0, 500, 500, 500, 900, 900, 900], 10, 3),
+        ([5, 5, 5], [7, 7, 7], 10, 3),
+        ([5, 5, 5, 5], [7, 7, 7, 7], 10, 3),
+    ]
+    rng = np.random.default_rng(20261017)
+    for t in range(400):
+        n = int(rng.integers(0, 70))
+        m = int(rng.integers(2, 7))
+        eps = int(rng.integers(1, 40))
+        span = int(rng.integers(5, 300))
+        x = np.sort(rng.integers(0, span, n)).tolist()
+        if t % 5 == 0 and n:   # unsorted x: DBSCAN.main does not sort, window max of |dx|
+            x = rng.integers(0, span, n).tolist()
+        y = rng.integers(0, span, n).tolist()
+        kats.append((x, y, eps, m))
+    for x, y, eps, m in kats:
+        data = np.array([[a, b, i] for i, (a, b) in enumerate(zip(x, y))], dtype=np.int64).reshape(len(x), 3)
+        if len(x) == 0:
+            xl, cid, fl = [], -1, []
+        else:
+            xl, cid = R.DBSCAN.x_coordinate_clustering(data, eps, m)
+            fl = R.DBSCAN.main(data, eps, m)
+            xl, fl = [int(v) for v in xl], [int(v) for v in fl]
+        cases.append({"x": x, "y": y, "eps": eps, "m": m, "x_labels": xl, "x_last_id": int(cid), "labels": fl})
+    with open(os.path.join(HERE, "dbscan_small.json"), "w") as f:
+        json.dump(cases, f, separators=(",", ":"))
+    # medium cases in the regimes that matter (sparse / at-threshold / dense / hotspot), stored as npz
+    med = {}
+    for k, (n, span, eps, m) in enumerate([(6000, 4_000_000, 500, 3), (6000, 1_000_000, 500, 3),
+                                            (6000, 300_000, 500, 3), (5000, 2_000_000, 1000, 5),
+                                            (4000, 50_000, 50, 2)]):
+        r = np.random.default_rng(100 + k)
+        nc = n // 20
+        sizes = 2 + r.geometric(1 / 8, nc)
+        cx, cy = r.integers(0, span, nc), r.integers(0, span, nc)
+        ax = np.repeat(cx, sizes) + np.rint(r.normal(0, 120, sizes.sum())).astype(np.int64)
+        ay = np.repeat(cy, sizes) + np.rint(r.normal(0, 120, sizes.sum())).astype(np.int64)
+        hot = r.integers(0, span - 3000)
+        ax = np.concatenate([ax, r.integers(0, span, n // 2), hot + r.integers(0, 2000, n // 8)])
+        ay = np.concatenate([ay, r.integers(0, span, n // 2), hot + r.integers(0, 2000, n // 8)])
+        ax, ay = np.clip(ax, 0, span), np.clip(ay, 0, span)
+        perm = r.permutation(len(ax))
+        ax, ay = ax[perm], ay[perm]
+        order = np.argsort(ax, kind="stable")
+        data = np.stack([ax[order], ay[order], np.arange(len(ax))], 1).astype(np.int64)
+        lab = R.DBSCAN.main(data, eps, m)
+        out = np.empty(len(ax), dtype=np.int32)
+        out[order] = lab.astype(np.int32)
+        med["posA_%d" % k], med["posB_%d" % k], med["labels_%d" % k] = ax.astype(np.int32), ay.astype(np.int32), out
+        med["param_%d" % k] = np.array([eps, m])
+    np.savez_compressed(os.path.join(HERE, "dbscan_medium.npz"), **med)
+
+
+def coverage_cases():
+    cov = R.tiddit_coverage
+    out = []
+    # App. B known-answer vector
+    specs = [("c1", 1234, 500, [(0, 150), (400, 550), (990, 1234), (1100, 1234), (499, 501), (0, 1234)])]
+    rng = np.random.default_rng(7)
+    for t in range(40):
+        z = int(rng.choice([1, 7, 37, 50, 100, 500, 1000, 4096]))
+        ln = int(rng.integers(1, 30000 if z >= 37 else 1500))
+        k = int(rng.integers(0, 400))
+        s = np.sort(rng.integers(0, ln, k))
+        length = rng.integers(1, 400, k) if t % 3 else rng.integers(1, 6000, k)
+        e = np.minimum(s + length, ln)
+        specs.append(("ctg%d" % t, ln, z, [(int(a), int(b)) for a, b in zip(s, e)]))
+    for name, ln, z, reads in specs:
+        header = {"SQ": [{"SN": name, "LN": ln}]}
+        data, ebs = cov.create_coverage(header, z, name)
+        for a, b in reads:
+            data = cov.update_coverage(a, b, z, data, ebs)
+        out.append({"name": name, "LN": ln, "bin": z, "reads": reads, "end_bin_size": int(ebs),
+                    "bins_hex": [float(v).hex() for v in data]})
+    with open(os.path.join(HERE, "coverage_cases.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+    # text output of print_coverage (bed + wig) for a 3-contig header
+    header = {"SQ": [{"SN": "c1", "LN": 1234}, {"SN": "c2", "LN": 500}, {"SN": "c3", "LN": 2001}]}
+    data, ebs = cov.create_coverage(header, 500)
+    r = np.random.default_rng(11)
+    reads = {}
+    for c in header["SQ"]:
+        s = np.sort(r.integers(0, c["LN"], 60))
+        e = np.minimum(s + r.integers(1, 300, 60), c["LN"])
+        reads[c["SN"]] = [(int(a), int(b)) for a, b in zip(s, e)]
+        for a, b in reads[c["SN"]]:
+            cov.update_coverage(a, b, 500, data[c["SN"]], ebs[c["SN"]])
+    cov.print_coverage(data, header, 500, "bed", os.path.join(HERE, "print_coverage.bed"))
+    cov.print_coverage(data, header, 500, "wig", os.path.join(HERE, "print_coverage.wig"))
+    with open(os.path.join(HERE, "print_coverage_input.json"), "w") as f:
+        json.dump({"header": header, "bin": 500, "reads": reads}, f, separators=(",", ":"))
+
+
+def gc_cases():
+    out = []
+    seqs = [("ACGTACGTACNNNNNNacgtNNNNNGGGGGATTTACAT", 10, 0.5), ("GGGATTTT", 50, 0.5)]
+    rng = np.random.default_rng(9)
+    alphabet = np.frombuffer(b"ACGTacgtNnRYKM", dtype=np.uint8)
+    for t in range(30):
+        ln = int(rng.integers(1, 4000))
+        z = int(rng.choice([1, 3, 10, 16, 50, 64, 100, 191, 192, 193, 500, 1000]))
+        p = np.array([6, 6, 6, 6, 3, 3, 3, 3, 4, 1, .2, .2, .2, .2])
+        s = rng.choice(alphabet, ln, p=p / p.sum())
+        k = int(rng.integers(0, ln))
+        s[k:k + int(rng.integers(0, 300))] = ord("N")
+        seqs.append((bytes(s).decode(), z, float(rng.choice([0.5, 0.0, 0.2, 1.0]))))
+    tmp = os.path.join(HERE, "_tmp.fa")
+    for k, (s, z, cut) in enumerate(seqs):
+        with open(tmp, "w") as f:
+            f.write(">ctg\n")
+            for i in range(0, len(s), 60):
+                f.write(s[i:i + 60] + "\n")
+        import pysam  # the stand-in next to the compiled reference
+        pysam.FastaFile._cache.clear()
+        name, bins = R.tiddit_gc.binned_gc(tmp, "ctg", z, cut)
+        out.append({"seq": s, "bin": z, "n_cutoff": cut, "gc": [int(v) for v in bins]})
+    os.remove(tmp)
+    with open(os.path.join(HERE, "gc_cases.json"), "w") as f:
+        json.dump(out, f, separators=(",", ":"))
+
+
+def _jsonable(o):
+    if isinstance(o, dict):
+        return {str(k): _jsonable(v) for k, v in o.items()}
+    if isinstance(o, (set, frozenset)):
+        return {"__set__": sorted(_jsonable(v) for v in o)}
+    if isinstance(o, (list, tuple)):
+        return [_jsonable(v) for v in o]
+    if isinstance(o, (np.integer,)):
+        return int(o)
+    return o
+
+
+def cluster_cases():
+    """Synthetic <prefix>_tiddit/*.tab files (App. D formats) + the reference's candidates dict."""
+    contigs = {"chr1": 60000, "chr2": 45000, "chr10": 30000, "tiny": 900}
+    names = list(contigs)
+    rng = np.random.default_rng(5)
+
+    def tf():
+        return "True" if rng.random() < 0.5 else "False"
+
+    for case, (samples, is_mp, skip_assembly, eps, m, min_reads) in enumerate(
+            [(["S1"], False, False, 300, 3, 3), (["S1", "S2"], True, False, 200, 2, 2), (["S1"], False, True, 300, 4, 5)]):
+        prefix = os.path.join(HERE, "cluster_case%d" % case)
+        os.makedirs(prefix + "_tiddit", exist_ok=True)
+        centres = [(names[a], names[b], int(rng.integers(100, contigs[names[a]])), int(rng.integers(100, contigs[names[b]])))
+                   for a, b in [(0, 0), (0, 0), (0, 1), (1, 1), (0, 2), (2, 2), (0, 0), (1, 2), (0, 3)]]
+        for sample in samples:
+            with open("%s_tiddit/discordants_%s.tab" % (prefix, sample), "w") as f:
+                for k in range(260):
+                    ca, cb, xa, xb = centres[int(rng.integers(0, len(centres)))]
+                    if rng.random() < 0.25:
+                        xa, xb = int(rng.integers(1, contigs[ca])), int(rng.integers(1, contigs[cb]))
+                    sa = xa + int(rng.normal(0, 80)); sb = xb + int(rng.normal(0, 80))
+                    sa, sb = max(1, sa), max(1, sb)
+                    if rng.random() < 0.03:
+                        sa = contigs[ca] + 50   # beyond the contig end: exercises the clamp
+                    f.write("\t".join(["read%d_%s" % (k // 2, sample), ca, cb, str(sa), str(sa + 100), tf(),
+                                       str(sb), str(sb + 100), tf()]) + "\n")
+            with open("%s_tiddit/splits_%s.tab" % (prefix, sample), "w") as f:
+                for k in range(140):
+                    ca, cb, xa, xb = centres[int(rng.integers(0, len(centres)))]
+                    pa = max(1, xa + int(rng.integers(-3, 4))); pb = max(1, xb + int(rng.integers(-3, 4)))
+                    if rng.random() < 0.03:
+                        pb = contigs[cb] + 7
+                    f.write("\t".join(["split%d_%s" % (k, sample), ca, cb, str(pa), tf(), str(pb), tf(),
+                                       str(pa - 40), str(pa), str(pb), str(pb + 40)]) + "\n")
+            with open("%s_tiddit/contigs_%s.tab" % (prefix, sample), "w") as f:
+                for k in range(40):
+                    ca, cb, xa, xb = centres[int(rng.integers(0, len(centres)))]
+                    if rng.random() < 0.5:
+                        cb = ca
+                        xa = int(rng.integers(1, contigs[ca] - 500)); xb = xa + int(rng.integers(10, 900))
+                    f.write("\t".join(["ctg%d_%s" % (k, sample), ca, cb, str(xa), tf(), str(xb), tf(),
+                                       str(xa - 200), str(xa), str(xb), str(xb + 200)]) + "\n")
+        chromosomes = ["chr1", "chr2", "chr10", "tiny"]
+        args = dict(samples=samples, is_mp=is_mp, epsilon=eps, m=m, max_ins_len=400, min_contig=1000,
+                    skip_assembly=skip_assembly, min_reads=min_reads, chromosomes=chromosomes, contig_length=contigs)
+        cand = R.tiddit_cluster.main(prefix, chromosomes, contigs, samples, is_mp, eps, m, 400, 1000, skip_assembly,
+                                     min_reads)
+        order = {a: {b: [int(c) for c in cand[a][b]] for b in cand[a]} for a in cand}
+        with open(prefix + "_expected.json", "w") as f:
+            json.dump({"args": args, "candidates": _jsonable(cand), "order": order}, f, separators=(",", ":"))
+
+
+if __name__ == "__main__":
+    dbscan_cases()
+    coverage_cases()
+    gc_cases()
+    cluster_cases()
+    print("golden vectors written to", HERE)

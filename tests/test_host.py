@@ -1,0 +1,107 @@
+"""CPU: host-side logic of the drop-in modules (parsing, folding, text output, generators).
+Where a test needs cluster labels without a GPU it injects the ORACLE's labels (test-only stand-in)."""
+import filecmp
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, load_json, unjson
+
+
+def _same_candidates(got, want_json, order):
+    want = unjson(want_json)
+    assert list(got) == list(want)
+    for a in want:
+        assert list(got[a]) == list(want[a])
+        for b in want[a]:
+            assert [int(k) for k in got[a][b]] == order[a][b]          # dict insertion order drives SV numbering
+            for cid, cand in got[a][b].items():
+                assert cand == want[a][b][str(cid)], (a, b, cid)
+
+
+@pytest.mark.parametrize("case", [0, 1, 2])
+def test_cluster_main_fold_matches_reference(case, oracle, monkeypatch):
+    from tiddit_b200 import tiddit_cluster, device_ops
+    exp = load_json("cluster_case%d_expected.json" % case)
+    a = exp["args"]
+    monkeypatch.setattr(device_ops, "cluster_labels",
+                        lambda posA, posB, seg_off, eps, m, max_pos=0: oracle.cluster_segments(posA, posB, seg_off, eps, m))
+    got = tiddit_cluster.main(os.path.join(GOLDEN, "cluster_case%d" % case), a["chromosomes"], a["contig_length"],
+                              a["samples"], a["is_mp"], a["epsilon"], a["m"], a["max_ins_len"], a["min_contig"],
+                              a["skip_assembly"], a["min_reads"])
+    _same_candidates(got, exp["candidates"], exp["order"])
+
+
+def test_find_discordant_pos_table(ref):
+    from tiddit_b200 import tiddit_cluster
+    frag = ["r", "c1", "c2", "s3", "e4", None, "s6", "e7", None]
+    expected = {  # tiddit_cluster.pyx:8-35
+        (True, "False", "True"): ("s3", "e7"), (True, "False", "False"): ("s3", "s6"),
+        (True, "True", "True"): ("e4", "e7"), (True, "True", "False"): ("e4", "s6"),
+        (False, "False", "True"): ("e4", "s6"), (False, "False", "False"): ("e4", "e7"),
+        (False, "True", "True"): ("s3", "s6"), (False, "True", "False"): ("s3", "e7")}
+    for (mp, ra, rb), want in expected.items():
+        frag[5], frag[8] = ra, rb
+        assert tiddit_cluster.find_discordant_pos(frag, mp) == want
+        if ref is not None:
+            assert ref.tiddit_cluster.find_discordant_pos(frag, mp) == want
+
+
+def test_create_coverage_shapes():
+    from tiddit_b200 import tiddit_coverage as cov
+    header = {"SQ": [{"SN": "c1", "LN": 1234}, {"SN": "c2", "LN": 1000}]}
+    data, ebs = cov.create_coverage(header, 500)
+    assert list(data) == ["c1", "c2"] and len(data["c1"]) == 3 and len(data["c2"]) == 2
+    assert ebs == {"c1": 234, "c2": 500} and data["c1"].dtype == np.float64
+    one, e1 = cov.create_coverage(header, 500, "c2")
+    assert isinstance(one, np.ndarray) and len(one) == 2 and e1 == 500
+    assert cov.create_coverage(header, 500, "nope") == ({}, {})
+
+
+def test_print_coverage_bytes(oracle, tmp_path):
+    from tiddit_b200 import tiddit_coverage as cov
+    inp = load_json("print_coverage_input.json")
+    header, z = inp["header"], inp["bin"]
+    data, ebs = cov.create_coverage(header, z)
+    for name, reads in inp["reads"].items():     # bins from the oracle: this test is about the text
+        oracle.update_coverage_batch([r[0] for r in reads], [r[1] for r in reads], z, data[name], ebs[name])
+    for kind in ("bed", "wig"):
+        out = str(tmp_path / ("o." + kind))
+        cov.print_coverage(data, header, z, kind, out)
+        assert filecmp.cmp(out, os.path.join(GOLDEN, "print_coverage." + kind), shallow=False)
+
+
+def test_print_coverage_number_format(ref, tmp_path):
+    if ref is None:
+        pytest.skip("oracle/_ref not built")
+    from tiddit_b200 import tiddit_coverage as cov
+    header = {"SQ": [{"SN": "c", "LN": 12 * 50 - 3}]}
+    vals = np.array([0.0, 1.0, 2.0 ** -32, 1e-5, 123456.789, 1e16, 1 / 3, 0.30000001192092896, 29.98, 1e-4, 5e-324, 7.0])
+    for kind in ("bed", "wig"):
+        a, b = str(tmp_path / ("a." + kind)), str(tmp_path / ("b." + kind))
+        cov.print_coverage({"c": vals}, header, 50, kind, a)
+        ref.tiddit_coverage.print_coverage({"c": vals}, header, 50, kind, b)
+        assert filecmp.cmp(a, b, shallow=False)
+
+
+def test_synth_shapes():
+    from tiddit_b200 import synth
+    a, b, off, L = synth.wgs30x_signals(200_000)
+    assert len(a) == len(b) == 200_000 == off[-1] and len(off) == 301
+    assert a.dtype == np.int32 and a.min() >= 1 and max(a.max(), b.max()) <= L
+    a2, _, _, _ = synth.wgs30x_signals(200_000)
+    assert np.array_equal(a, a2)
+    s, e, roff, lens = synth.coverage_reads(100_000)
+    assert len(s) == 100_000 and np.all(e > s) and np.all(np.diff(s[roff[0]:roff[1]]) >= 0)
+    seq = synth.fasta_sequence(100_000)
+    assert seq.dtype == np.uint8 and (seq == ord("N")).sum() > 1000
+
+
+def test_fasta_reader(tmp_path):
+    from tiddit_b200 import fasta
+    p = tmp_path / "x.fa"
+    p.write_text(">c1 desc\nACGT\nNNgg\n>c2\nTT\r\nA\n")
+    fa = fasta.NumpyFasta(str(p))
+    assert fa.references == ["c1", "c2"]
+    assert fa.get_reference_length("c1") == 8 and fa.fetch("c1", 2, 6) == "GTNN" and fa.fetch("c2") == "TTA"

@@ -1,0 +1,176 @@
+"""Thin, typed wrappers over the C ABI working on torch CUDA tensors (inputs already in HBM) and
+host-array front ends that add the host<->device copies.  No arithmetic happens in this file.
+"""
+import math
+
+import numpy as np
+
+from . import _lib
+
+INT32_MAX = 2 ** 31 - 1
+FIRST_BAD_NONE = 2 ** 63 - 1
+
+
+def eps_to_int(epsilon):
+    """Integer coordinates: d < epsilon  <=>  d < ceil(epsilon) (DBSCAN.py:51,99 compare ints to epsilon)."""
+    e = math.ceil(epsilon)
+    return int(min(max(e, 0), INT32_MAX))
+
+
+def check_min_pts(m, n):
+    if int(m) != m:
+        raise TypeError("'%s' object cannot be interpreted as an integer" % type(m).__name__)
+    if n > 0 and m < 2:
+        # DBSCAN.py:51 / :99: max() over an empty window
+        raise ValueError("max() arg is an empty sequence")
+
+
+# ---------------------------------------------------------------------------------------------
+# clustering
+# ---------------------------------------------------------------------------------------------
+def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_out=None, pair_id=None):
+    """All (chrA,chrB) segments in one call; int32 CUDA tensors in, int32 CUDA labels (insertion order) out.
+
+    Replaces tiddit_cluster.pyx:140-160 + DBSCAN.py:125-129.  Exactly one of seg_off (int64, P+1) and
+    pair_id (int32, n) is given."""
+    torch = _lib.torch_cuda()
+    L = _lib.lib()
+    n = int(posA.numel())
+    check_min_pts(m, n)
+    if labels_out is None:
+        labels_out = torch.empty(n, dtype=torch.int32, device=posA.device)
+    if n == 0:
+        return labels_out
+    need = L.tdt_cluster_workspace_bytes(n, int(P))
+    ws = _lib.workspace(torch, need)
+    st = _lib.stream_ptr(torch)
+    if pair_id is None:
+        rc = L.tdt_cluster_labels(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(seg_off), n, int(P), eps_to_int(epsilon),
+                                  int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws), ws.numel(), st)
+    else:
+        rc = L.tdt_cluster_labels_keyed(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(pair_id), n, int(P),
+                                        eps_to_int(epsilon), int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws),
+                                        ws.numel(), st)
+    _lib.check(rc)
+    return labels_out
+
+
+def cluster_labels(posA, posB, seg_off, epsilon, m, max_pos=0):
+    """Host front end: numpy int32 posA/posB + int64 seg_off -> numpy int32 labels (H2D, kernels, D2H)."""
+    torch = _lib.torch_cuda()
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+    a = _lib.to_device(torch, posA, np.int32)
+    b = _lib.to_device(torch, posB, np.int32)
+    s = _lib.to_device(torch, seg_off, np.int64)
+    out = cluster_labels_device(a, b, s, len(seg_off) - 1, epsilon, m, max_pos)
+    return out.cpu().numpy()
+
+
+def dbscan_main_device(x, y, epsilon, m, max_pos=0):
+    """DBSCAN.py:125-129 on one array in the caller's order (no sort); int32 CUDA tensors."""
+    torch = _lib.torch_cuda()
+    L = _lib.lib()
+    n = int(x.numel())
+    check_min_pts(m, n)
+    labels = torch.empty(n, dtype=torch.int32, device=x.device)
+    if n == 0:
+        return labels
+    ws = _lib.workspace(torch, L.tdt_cluster_workspace_bytes(n, 1))
+    rc = L.tdt_dbscan_main(_lib.ptr(x), _lib.ptr(y), n, eps_to_int(epsilon), int(m), int(max_pos), _lib.ptr(labels),
+                           _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return labels
+
+
+def xpass_device(x, epsilon, m):
+    """DBSCAN.py:33-64 -> (int32 CUDA labels, int32 CUDA scalar last id)."""
+    torch = _lib.torch_cuda()
+    L = _lib.lib()
+    n = int(x.numel())
+    check_min_pts(m, n)
+    labels = torch.empty(n, dtype=torch.int32, device=x.device)
+    last = torch.full((1,), -1, dtype=torch.int32, device=x.device)
+    if n == 0:
+        return labels, last
+    ws = _lib.workspace(torch, L.tdt_cluster_workspace_bytes(n, 1))
+    rc = L.tdt_xpass_labels(_lib.ptr(x), n, eps_to_int(epsilon), int(m), _lib.ptr(labels), _lib.ptr(last),
+                            _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return labels, last
+
+
+def ypass_device(y, epsilon, m, labels_io, cluster_id_io, max_pos=0):
+    """DBSCAN.py:66-123 in place on int32 CUDA labels / a one-element int32 CUDA cluster id."""
+    torch = _lib.torch_cuda()
+    L = _lib.lib()
+    n = int(y.numel())
+    check_min_pts(m, n)
+    if n == 0:
+        return labels_io, cluster_id_io
+    ws = _lib.workspace(torch, L.tdt_cluster_workspace_bytes(n, 1))
+    rc = L.tdt_ypass_labels(_lib.ptr(y), n, eps_to_int(epsilon), int(m), int(max_pos), _lib.ptr(labels_io),
+                            _lib.ptr(cluster_id_io), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return labels_io, cluster_id_io
+
+
+# ---------------------------------------------------------------------------------------------
+# coverage
+# ---------------------------------------------------------------------------------------------
+def new_first_bad(torch):
+    return torch.full((1,), FIRST_BAD_NONE, dtype=torch.int64, device="cuda")
+
+
+def coverage_accumulate_device(start, end, bin_size, end_bin_size, bins, first_bad):
+    """tiddit_coverage.pyx:48-74 for a batch of reads of ONE contig; bins (float64 CUDA) updated in place."""
+    torch = _lib.torch_cuda()
+    if bin_size == 0:
+        raise ZeroDivisionError("integer division or modulo by zero")
+    rc = _lib.lib().tdt_coverage_accumulate(_lib.ptr(start), _lib.ptr(end), int(start.numel()), int(bin_size),
+                                            int(end_bin_size), _lib.ptr(bins), int(bins.numel()), _lib.ptr(first_bad),
+                                            _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return bins
+
+
+def coverage_accumulate_contigs_device(start, end, read_off, bin_off, end_bin_size, bin_size, bins, first_bad):
+    """The same for reads grouped by contig (read_off / bin_off int64 CUDA, end_bin_size int32 CUDA)."""
+    torch = _lib.torch_cuda()
+    if bin_size == 0:
+        raise ZeroDivisionError("integer division or modulo by zero")
+    rc = _lib.lib().tdt_coverage_accumulate_contigs(
+        _lib.ptr(start), _lib.ptr(end), int(start.numel()), _lib.ptr(read_off), _lib.ptr(bin_off),
+        _lib.ptr(end_bin_size), int(end_bin_size.numel()), int(bin_size), _lib.ptr(bins), int(bins.numel()),
+        _lib.ptr(first_bad), _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return bins
+
+
+# ---------------------------------------------------------------------------------------------
+# GC
+# ---------------------------------------------------------------------------------------------
+def padded_sequence_device(seq_bytes):
+    """uint8 host sequence -> CUDA tensor padded to a multiple of 16 bytes (the kernel's bulk copies read whole
+    16-byte granules); returns (tensor, true length)."""
+    torch = _lib.torch_cuda()
+    arr = np.frombuffer(seq_bytes, dtype=np.uint8) if isinstance(seq_bytes, (bytes, bytearray, memoryview)) \
+        else np.ascontiguousarray(seq_bytes, dtype=np.uint8)
+    n = len(arr)
+    dev = torch.zeros((n + 15) // 16 * 16 + 16, dtype=torch.uint8, device="cuda")
+    if n:
+        dev[:n].copy_(torch.from_numpy(arr), non_blocking=False)
+    return dev, n
+
+
+def gc_bins_device(seq, length, bin_size, n_cutoff, out=None):
+    """tiddit_gc.pyx:6-33 on a CUDA uint8 sequence (16-byte aligned, padded) -> int8 CUDA bins."""
+    torch = _lib.torch_cuda()
+    if bin_size == 0:
+        raise ZeroDivisionError("division by zero")
+    n_bins = int(math.ceil(length / bin_size))
+    if out is None:
+        out = torch.zeros(n_bins, dtype=torch.int8, device="cuda")
+    rc = _lib.lib().tdt_gc_bins(_lib.ptr(seq), int(length), int(bin_size), float(n_cutoff), _lib.ptr(out),
+                                _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return out

@@ -1,0 +1,142 @@
+"""Synthetic workloads shaped like TIDDIT's inputs (SURVEY.md App. E / BASELINE.json configs).
+
+Pure numpy generators, deterministic per seed; used by bench.py and the tests.  Signals come out
+grouped by (chrA,chrB) pair -- seg_off delimits the pairs -- and shuffled inside each pair, which is
+the insertion order the cluster driver sees."""
+import numpy as np
+
+GRCH38 = [("chr1", 248956422), ("chr2", 242193529), ("chr3", 198295559), ("chr4", 190214555),
+          ("chr5", 181538259), ("chr6", 170805979), ("chr7", 159345973), ("chr8", 145138636),
+          ("chr9", 138394717), ("chr10", 133797422), ("chr11", 135086622), ("chr12", 133275309),
+          ("chr13", 114364328), ("chr14", 107043718), ("chr15", 101991189), ("chr16", 90338345),
+          ("chr17", 83257441), ("chr18", 80373285), ("chr19", 58617616), ("chr20", 64444167),
+          ("chr21", 46709983), ("chr22", 50818468), ("chrX", 156040895), ("chrY", 57227415)]
+
+
+def config2_signals(n=1_000_000, seed=42, length=250_000_000, n_clusters=20_000, mean_size=15, sigma=120):
+    """BASELINE config 2: one pair, planted clusters of size 2+Geom(1/mean_size) + uniform noise up to n."""
+    rng = np.random.default_rng(seed)
+    sizes = 2 + rng.geometric(1.0 / mean_size, n_clusters)
+    keep = np.cumsum(sizes) <= n
+    sizes = sizes[keep]
+    cx = rng.integers(1, length, len(sizes))
+    cy = rng.integers(1, length, len(sizes))
+    ax = np.repeat(cx, sizes) + np.rint(rng.normal(0, sigma, sizes.sum())).astype(np.int64)
+    ay = np.repeat(cy, sizes) + np.rint(rng.normal(0, sigma, sizes.sum())).astype(np.int64)
+    k = n - len(ax)
+    ax = np.concatenate([ax, rng.integers(1, length, k)])
+    ay = np.concatenate([ay, rng.integers(1, length, k)])
+    perm = rng.permutation(n)
+    posA = np.clip(ax[perm], 1, length).astype(np.int32)
+    posB = np.clip(ay[perm], 1, length).astype(np.int32)
+    return posA, posB, np.array([0, n], dtype=np.int64), length
+
+
+def populated_pairs(contigs=GRCH38):
+    """(ia, ib) with nameA <= nameB in string order, as tiddit_signal.pyx:214-219 orders inter-chromosomal pairs;
+    listed in the cluster driver's visiting order (header order of chrA, then chrB)."""
+    out = []
+    for ia, (na, _) in enumerate(contigs):
+        for ib, (nb, _) in enumerate(contigs):
+            if na <= nb:
+                out.append((ia, ib))
+    return out
+
+
+def _wgs_signals(n, seed, bg, cl, hs, cluster_mean, sigma, n_hot, hot_lo, hot_hi, contigs):
+    rng = np.random.default_rng(seed)
+    lens = np.array([ln for _, ln in contigs], dtype=np.float64)
+    pairs = populated_pairs(contigs)
+    intra = np.array([ia == ib for ia, ib in pairs])
+    w = np.where(intra, 0.7 * np.array([lens[ia] for ia, _ in pairs]) / lens.sum(), 0.0)
+    wi = np.array([lens[ia] * lens[ib] for ia, ib in pairs]) * (~intra)
+    w = w + 0.3 * wi / wi.sum()
+    w /= w.sum()
+    n_hs = int(n * hs)
+    n_pair = rng.multinomial(n - n_hs, w)
+    hot_sizes = rng.integers(hot_lo, hot_hi, n_hot).astype(np.float64)
+    hot_sizes = np.maximum(1, np.floor(hot_sizes * n_hs / hot_sizes.sum())).astype(np.int64)
+    hot_sizes[0] += n_hs - hot_sizes.sum()
+    hot_pair = rng.choice(len(pairs), n_hot, p=w)
+    A, B, off = [], [], [0]
+    for k, (ia, ib) in enumerate(pairs):
+        la, lb = int(lens[ia]), int(lens[ib])
+        nk = int(n_pair[k])
+        n_bg = int(round(nk * bg / (bg + cl)))
+        n_cl = nk - n_bg
+        xa = [rng.integers(1, la + 1, n_bg)]
+        if ia == ib:
+            xb = [np.minimum(xa[0] + np.floor(rng.lognormal(9, 2, n_bg)).astype(np.int64), lb)]
+        else:
+            xb = [rng.integers(1, lb + 1, n_bg)]
+        if n_cl > 0:
+            sizes = 2 + rng.geometric(1.0 / cluster_mean, max(1, n_cl // (cluster_mean + 1) + 8))
+            sizes = sizes[np.cumsum(sizes) <= n_cl]
+            rest = n_cl - int(sizes.sum())
+            if rest > 0:
+                sizes = np.append(sizes, rest)
+            cx = rng.integers(1, la + 1, len(sizes))
+            cy = rng.integers(1, lb + 1, len(sizes))
+            xa.append(np.repeat(cx, sizes) + np.rint(rng.normal(0, sigma, n_cl)).astype(np.int64))
+            xb.append(np.repeat(cy, sizes) + np.rint(rng.normal(0, sigma, n_cl)).astype(np.int64))
+        for h in np.flatnonzero(hot_pair == k):
+            hx, hy = rng.integers(1, la + 1), rng.integers(1, lb + 1)
+            xa.append(hx + rng.integers(0, 2000, hot_sizes[h]))
+            xb.append(hy + rng.integers(0, 2000, hot_sizes[h]))
+        a = np.clip(np.concatenate(xa), 1, la)
+        b = np.clip(np.concatenate(xb), 1, lb)
+        perm = rng.permutation(len(a))
+        A.append(a[perm].astype(np.int32))
+        B.append(b[perm].astype(np.int32))
+        off.append(off[-1] + len(a))
+    return np.concatenate(A), np.concatenate(B), np.array(off, dtype=np.int64), int(lens.max())
+
+
+def wgs30x_signals(n=20_000_000, seed=3, contigs=GRCH38):
+    """BASELINE config 3: 30X-WGS-shaped signals over the 300 populated chromosome pairs (eps=500, m=3)."""
+    return _wgs_signals(n, seed, 0.55, 0.40, 0.05, 12, 120, 50, 5_000, 50_000, contigs)
+
+
+def tumor60x_signals(n=50_000_000, seed=5, contigs=GRCH38):
+    """BASELINE config 5: 60X tumour-like signals, dense clusters + 100 hotspots (eps=1000, m=5)."""
+    return _wgs_signals(n, seed, 0.25, 0.70, 0.05, 60, 250, 100, 10_000, 100_000, contigs)
+
+
+def coverage_reads(n_reads, seed=7, contigs=GRCH38, read_len=150):
+    """Coordinate-sorted reads per contig (BAM order): starts uniform, end = min(start + read_len, LN).
+    -> start, end (int32), read_off, bin-independent contig lengths."""
+    rng = np.random.default_rng(seed)
+    lens = np.array([ln for _, ln in contigs], dtype=np.int64)
+    per = np.floor(n_reads * lens / lens.sum()).astype(np.int64)
+    per[0] += n_reads - per.sum()
+    starts, ends, off = [], [], [0]
+    for ln, k in zip(lens, per):
+        s = np.sort(rng.integers(0, ln, int(k)))
+        starts.append(s.astype(np.int32))
+        ends.append(np.minimum(s + read_len, ln).astype(np.int32))
+        off.append(off[-1] + int(k))
+    return np.concatenate(starts), np.concatenate(ends), np.array(off, dtype=np.int64), lens
+
+
+def fasta_sequence(length, seed=9, gc=0.41):
+    """uint8 bases: i.i.d. with `gc` GC content, half soft-masked in blocks of 300-3000 bp, one N block in the
+    middle (3 % of the contig, <= 3 Mbp) and 10 kb (<= 1 %) N telomeres."""
+    rng = np.random.default_rng(seed)
+    r = rng.random(length)
+    seq = np.where(r < gc / 2, ord("C"), np.where(r < gc, ord("G"), np.where(r < gc + (1 - gc) / 2, ord("A"), ord("T"))))
+    seq = seq.astype(np.uint8)
+    pos = 0
+    lower = rng.random() < 0.5
+    while pos < length:
+        blk = int(rng.integers(300, 3001))
+        if lower:
+            seq[pos:pos + blk] |= 0x20
+        lower = not lower
+        pos += blk
+    tel = min(10_000, max(1, length // 100))
+    seq[:tel] = ord("N")
+    seq[length - tel:] = ord("N")
+    cen = min(3_000_000, max(1, length * 3 // 100))
+    mid = length // 2
+    seq[mid:mid + cen] = ord("N")
+    return seq
