@@ -107,29 +107,6 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
-# sharding (host logic, also exercised by tests/test_dist.py on gloo)
-# ---------------------------------------------------------------------------------------------------
-def lpt_assign(sizes, n_ranks):
-    """Longest-processing-time greedy: pair -> rank, balancing the signal counts."""
-    load = [0] * n_ranks
-    owner = np.zeros(len(sizes), dtype=np.int64)
-    for p in np.argsort(-np.asarray(sizes), kind="stable"):
-        r = int(np.argmin(load))
-        owner[p] = r
-        load[r] += int(sizes[p])
-    return owner
-
-
-def shard_workload(posA, posB, seg_off, owner, rank):
-    """The signals of the pairs `rank` owns, pair order kept -> posA, posB, seg_off of the shard."""
-    mine = np.flatnonzero(owner == rank)
-    sizes = np.diff(seg_off)[mine]
-    idx = np.concatenate([np.arange(seg_off[p], seg_off[p + 1]) for p in mine]) if len(mine) else np.zeros(0, np.int64)
-    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
-    return posA[idx], posB[idx], off, idx
-
-
-# ---------------------------------------------------------------------------------------------------
 # the reference on the host cores
 # ---------------------------------------------------------------------------------------------------
 def _ref_modules():
@@ -325,6 +302,7 @@ def main():
     ap.add_argument("--signals", type=int, default=0, help="override the workload's signal count")
     ap.add_argument("--cov-reads", type=int, default=617_653_966, help="reads for the coverage leg (30X = 617653966)")
     ap.add_argument("--no-coverage", action="store_true")
+    ap.add_argument("--chunks", type=int, default=8, help="pair chunks of the pipelined host path (e2e, N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     ap.add_argument("--ref-crops-per-core", type=int, default=1, help="--impl reference: 50k-signal crops per core per step")
     args = ap.parse_args()
@@ -337,7 +315,7 @@ def main():
     import torch.distributed as dist
     from tiddit_b200 import build
     build.build()
-    from tiddit_b200 import device_ops, synth, _lib
+    from tiddit_b200 import device_ops, engine, synth, _lib
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -354,12 +332,14 @@ def main():
     n_total = len(posA)
     P_total = len(seg_off) - 1
 
-    owner = lpt_assign(np.diff(seg_off), world)
-    a_h, b_h, off_h, idx_h = shard_workload(posA, posB, seg_off, owner, rank) if world > 1 else \
-        (posA, posB, seg_off, None)
+    plan = engine.ShardPlan(seg_off, world)
+    if world > 1:
+        idx_h = plan.shard_index(rank)
+        a_h, b_h, off_h = np.ascontiguousarray(posA[idx_h]), np.ascontiguousarray(posB[idx_h]), plan.shard_seg_off(rank)
+    else:
+        a_h, b_h, off_h = posA, posB, seg_off
     n_mine, P_mine = len(a_h), len(off_h) - 1
-    shard_sizes = [int(np.diff(seg_off)[owner == r].sum()) for r in range(world)]
-    pad = max(shard_sizes)
+    pad = plan.pad
 
     a_pin = torch.from_numpy(a_h).pin_memory()
     b_pin = torch.from_numpy(b_h).pin_memory()
@@ -378,17 +358,19 @@ def main():
         if world > 1:
             dist.all_gather_into_tensor(gathered, labels_d)
 
+    pipe = engine.HostPipeline(n_total, n_chunks=args.chunks) if world == 1 else None
+
     def step_e2e(a_dev, b_dev, off_dev):
+        if world == 1:       # chunked: H2D / kernels / D2H overlap on three streams
+            pipe.run(a_pin, b_pin, off_h, eps, m, L, out_pin)
+            return
         a_dev.copy_(a_pin, non_blocking=True)
         b_dev.copy_(b_pin, non_blocking=True)
         off_dev.copy_(off_pin, non_blocking=True)
         device_ops.cluster_labels_device(a_dev, b_dev, off_dev, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
-        if world > 1:
-            dist.all_gather_into_tensor(gathered, labels_d)
-            if rank == 0:
-                out_pin.copy_(gathered, non_blocking=True)
-        else:
-            out_pin.copy_(labels_d[:n_total], non_blocking=True)
+        dist.all_gather_into_tensor(gathered, labels_d)
+        if rank == 0:
+            out_pin.copy_(gathered, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -451,11 +433,20 @@ def main():
                        "sharding": "pairs LPT over %d ranks, one all-gather of int32 labels" % world if world > 1
                        else "single GPU", "l2": "256 MB flush between timed steps (and inputs > L2 at N=1)"},
             "e2e": {"value": n_total / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
+                    "path": "engine.HostPipeline: %d pair chunks, H2D | kernels | D2H on 3 streams" % args.chunks
+                    if world == 1 else "per-rank H2D, kernels, all-gather, rank-0 D2H",
                     "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + off_h.nbytes),
                     "d2h_bytes_per_step": int(out_pin.numel() * 4) if rank == 0 else 0},
             "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
             "clocks": clocks, "roofline": roofline}
 
+    # result check of what the timed paths produced (the oracle as checker, bounded to the sample pairs' cost)
+    torch.cuda.synchronize()
+    if rank == 0:
+        from oracle import oracle
+        got_all = out_pin.numpy()[plan.gather_index()] if world > 1 else out_pin.numpy()
+        want_all = oracle.cluster_segments(posA, posB, seg_off, eps, m)
+        line["verified"] = bool(np.array_equal(got_all, want_all))
     if world == 1 and rank == 0:
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_cluster_baseline(posA, posB, seg_off, eps, m)

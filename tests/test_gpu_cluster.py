@@ -134,15 +134,19 @@ def test_wgs30x_full_size(oracle):
     got = device_ops.cluster_labels(a, b, off, 500, 3, L)
     want = oracle.cluster_segments(a, b, off, 500, 3)
     assert_same(got, want, "wgs30x")
-    # size-independent properties: idempotent (same input -> same labels), every cluster has >= m members,
-    # ids are dense per pair, a permutation inside pairs that keeps ties in order changes nothing
+    # size-independent properties: idempotent (same input -> same labels); ids stay below the pair's signal
+    # count (tiddit_cluster.pyx:166 hands out len(cluster_pos)+k to noise contigs); reversing the order of the
+    # pairs only moves the label blocks
     again = device_ops.cluster_labels(a, b, off, 500, 3, L)
     assert np.array_equal(got, again)
     for p in (0, 1, 150, 299):
         seg = got[off[p]:off[p + 1]]
-        ids, cnt = np.unique(seg[seg >= 0], return_counts=True)
-        assert len(ids) == 0 or (ids[0] == 0 and ids[-1] == len(ids) - 1)
-        assert len(cnt) == 0 or cnt.min() >= 3
+        assert seg.max() < len(seg) and seg.min() >= -1
+    sizes = np.diff(off)
+    rev = np.concatenate([np.arange(off[p], off[p + 1]) for p in range(len(sizes) - 1, -1, -1)])
+    off_rev = np.concatenate([[0], np.cumsum(sizes[::-1])]).astype(np.int64)
+    got_rev = device_ops.cluster_labels(a[rev], b[rev], off_rev, 500, 3, L)
+    assert np.array_equal(got_rev, got[rev])
     del torch
 
 

@@ -1,0 +1,62 @@
+"""GPU: the host pipeline (chunked H2D / kernels / D2H) and the NCCL-sharded path give the oracle's labels."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("chunks", [1, 3, 8])
+def test_host_pipeline_matches_oracle(chunks, oracle):
+    import torch
+    from tiddit_b200 import engine, synth
+    a, b, off, L = synth.wgs30x_signals(2_000_000)
+    want = oracle.cluster_segments(a, b, off, 500, 3)
+    pipe = engine.HostPipeline(len(a), n_chunks=chunks)
+    a_pin, b_pin = torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory()
+    out = torch.empty(len(a), dtype=torch.int32).pin_memory()
+    for _ in range(2):                       # buffers are reused across calls
+        out.fill_(-7)
+        pipe.run(a_pin, b_pin, off, 500, 3, L, out)
+        assert np.array_equal(out.numpy(), want)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _nccl_worker(rank, world, port, out_dir):
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
+    from tiddit_b200 import engine, synth
+    a, b, off, L = synth.wgs30x_signals(1_000_000)
+    got = engine.sharded_labels(a, b, off, 500, 3, L)
+    np.save(os.path.join(out_dir, "labels_%d.npy" % rank), got)
+    dist.destroy_process_group()
+
+
+def test_sharded_labels_nccl(tmp_path, oracle):
+    import torch
+    import torch.multiprocessing as mp
+    world = min(torch.cuda.device_count(), 4)
+    if world < 2:
+        pytest.skip("needs >= 2 GPUs")
+    mp.spawn(_nccl_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    from tiddit_b200 import synth
+    a, b, off, L = synth.wgs30x_signals(1_000_000)
+    want = oracle.cluster_segments(a, b, off, 500, 3)
+    for r in range(world):
+        assert np.array_equal(np.load(tmp_path / ("labels_%d.npy" % r)), want)

@@ -6,7 +6,7 @@
 //
 // Bytes are classified four at a time in 32-bit words (case folded by |0x20, exact zero-byte test),
 // so the kernel stays HBM-bound at 1 byte per base:
-//   small bins (<= GC_SMALL_MAX bytes): a CTA stages ~48 KB of sequence (a multiple of 16 bins) in
+//   small bins (<= GC_SMALL_MAX bytes): a CTA stages ~40 KB of sequence (a multiple of 16 bins) in
 //       shared memory with 1-D TMA bulk copies and every thread walks its own bins word by word;
 //   large bins: one warp per bin, 16-byte coalesced loads straight from HBM.
 #include "tdt_common.cuh"
@@ -15,7 +15,7 @@ namespace tdt {
 
 constexpr int GC_THREADS = 256;
 constexpr int GC_SMALL_MAX = 192;      // thread-per-bin up to this bin size
-constexpr int GC_TILE_BYTES = 48 * 1024 - 64;
+constexpr int GC_TILE_BYTES = 40 * 1024;  // + static shared memory stays under the 48 KB default limit
 constexpr uint32_t GC_TMA_CHUNK = 32768;
 
 // 0x80 in every byte of t that is zero, 0 elsewhere (exact, no borrow between bytes)
@@ -127,7 +127,7 @@ int tdt_gc_bins(const uint8_t *seq, int64_t len, int32_t bin_size, double n_cuto
     cudaStream_t st = (cudaStream_t)stream;
     ProfScope ps("gc_bins", st);
     if (bin_size <= GC_SMALL_MAX) {
-        const int bpc = (GC_TILE_BYTES / bin_size) & ~15;  // >= 240 bins for bin_size <= 192
+        const int bpc = (GC_TILE_BYTES / bin_size) & ~15;  // >= 208 bins for bin_size <= 192
         const size_t smem = (size_t)bpc * bin_size + 16;
         const int64_t blocks = (n_bins + bpc - 1) / bpc;
         TDT_LAUNCH(gc_small_kernel, (unsigned)blocks, GC_THREADS, smem, st, seq, len, bin_size, n_cutoff, n_bins, bpc,

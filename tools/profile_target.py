@@ -1,0 +1,39 @@
+"""A short, fixed sequence of launches for ncu: 3 clustering passes over the 30X signal set, 2 coverage passes
+over 3X-worth of reads, 1 GC pass over 250 Mbp.  No timing, no CPU work."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tiddit_b200 import device_ops, synth  # noqa: E402
+
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
+a, b, off, L = synth.wgs30x_signals(n)
+a_d, b_d, off_d = torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), torch.from_numpy(off).cuda()
+for _ in range(3):
+    device_ops.cluster_labels_device(a_d, b_d, off_d, len(off) - 1, 500, 3, L)
+torch.cuda.synchronize()
+
+lens = np.array([ln for _, ln in synth.GRCH38], dtype=np.int64)
+n_reads = 61_765_396
+per = np.floor(n_reads * lens / lens.sum()).astype(np.int64)
+starts = [torch.sort((torch.rand(int(k), device="cuda", dtype=torch.float64) * int(ln)).to(torch.int32)).values
+          for ln, k in zip(lens, per)]
+start = torch.cat(starts)
+end = torch.cat([torch.clamp(s + 150, max=int(ln)) for s, ln in zip(starts, lens)])
+nb = np.ceil(lens / 500.0).astype(np.int64)
+read_off = torch.from_numpy(np.concatenate([[0], np.cumsum(per)]).astype(np.int64)).cuda()
+bin_off = torch.from_numpy(np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)).cuda()
+ebs = torch.from_numpy((lens - (nb - 1) * 500).astype(np.int32)).cuda()
+bins = torch.zeros(int(nb.sum()), dtype=torch.float64, device="cuda")
+bad = device_ops.new_first_bad(torch)
+for _ in range(2):
+    device_ops.coverage_accumulate_contigs_device(start, end, read_off, bin_off, ebs, 500, bins, bad)
+torch.cuda.synchronize()
+
+seq, ln = device_ops.padded_sequence_device(synth.fasta_sequence(250_000_000))
+device_ops.gc_bins_device(seq, ln, 50, 0.5)
+torch.cuda.synchronize()
+print("done")
