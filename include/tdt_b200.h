@@ -45,27 +45,22 @@ TDT_API const char *tdt_last_error(void);
  * tiddit/DBSCAN.py:125-129 (main), :33-64 (x_coordinate_clustering), :66-123
  * (y_coordinate_clustering).
  *
- * Signals: posA[i], posB[i] >= 0 (int32), i in [0, n).  Pairs are given either
- *   (a) segmented: seg_off[P+1] (device, int64), signals of pair p are [seg_off[p], seg_off[p+1])
- *       in insertion order (= the order of the reference's global signal index), or
- *   (b) keyed: pair_id[i] in [0, P) per signal, signals in any interleaving; the relative order of
- *       the signals of one pair is their insertion order.
+ * Signals: posA[i], posB[i] >= 0 (int32), i in [0, n).  Pairs are segments: seg_off[P+1] (device, int64),
+ * the signals of pair p are [seg_off[p], seg_off[p+1]) in insertion order (= the order of the reference's
+ * global signal index).
  * labels_out[i] (int32, input order): the reference's own ids -- x-pass ids 0..nx-1 in order of run
  * start, y-pass sub-clusters nx, nx+1, ... in visiting order, -1 = noise -- per pair, so they are
  * bit-identical to int(DBSCAN.main(...)[i]) (ids are < the pair's signal count).
  * max_pos: an upper bound on every posA/posB (e.g. the longest contig); 0 = unknown (31 bits assumed).
- *          It only sizes the radix-sort keys; a coordinate above it returns TDT_E_RANGE.
- * Synchronises `stream` once (the y-pass sort is sized from the x-pass result).
+ *          It only sizes the radix-sort keys; a coordinate with bits above it returns TDT_E_RANGE.
+ * Everything is enqueued without host round trips (data-dependent sizes stay on the device); the call
+ * synchronises `stream` once at the end to read the status word.
  * ------------------------------------------------------------------------------------------ */
 TDT_API size_t tdt_cluster_workspace_bytes(int64_t n, int32_t P);
 
 TDT_API int tdt_cluster_labels(const int32_t *posA, const int32_t *posB, const int64_t *seg_off, int64_t n, int32_t P,
                        int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out, void *ws,
                        size_t ws_bytes, void *stream);
-
-TDT_API int tdt_cluster_labels_keyed(const int32_t *posA, const int32_t *posB, const int32_t *pair_id, int64_t n, int32_t P,
-                             int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out, void *ws,
-                             size_t ws_bytes, void *stream);
 
 /* DBSCAN.py:125-129 on ONE array in the caller's order (the reference does not sort inside
  * DBSCAN.main; its caller does): x-pass over x[] as given -- window max of |x[j]-x[i]|, so unsorted
@@ -115,6 +110,14 @@ TDT_API int tdt_coverage_accumulate_contigs(const int32_t *start, const int32_t 
  * Does not synchronise.
  * ------------------------------------------------------------------------------------------ */
 TDT_API int tdt_gc_bins(const uint8_t *seq, int64_t len, int32_t bin_size, double n_cutoff, int8_t *out, void *stream);
+
+/* Test hook: the segmented stable radix sort on its own.  keys/vals (vals may be NULL = element index) and
+ * off[nseg+1] are device arrays; every segment [off[s], off[s+1]) is sorted by its low key_bits key bits into
+ * keys_out/vals_out.  ws: at least 8*n + 1024 + the sort's temporaries (tdt_cluster_workspace_bytes(n, nseg) is
+ * enough).  Synchronises. */
+TDT_API int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *off, int64_t nseg, int64_t n,
+                              int32_t key_bits, uint32_t *keys_out, int32_t *vals_out, void *ws, size_t ws_bytes,
+                              void *stream);
 
 /* Per-stage device timing for bench.py's roofline line: between tdt_profile_begin() and tdt_profile_end()
  * every stage of every call is bracketed by CUDA events on the caller's stream; tdt_profile_end synchronises

@@ -99,23 +99,6 @@ def test_dense_regime_and_hotspots(oracle):
                     oracle.cluster_segments(a, b, off, eps, m), "dense eps=%d m=%d" % (eps, m))
 
 
-def test_keyed_equals_segmented(oracle):
-    import torch
-    from tiddit_b200 import device_ops
-    rng = np.random.default_rng(5)
-    P, n = 40, 200_000
-    pair = rng.integers(0, P, n).astype(np.int32)
-    a = rng.integers(0, 2_000_000, n).astype(np.int32)
-    b = rng.integers(0, 2_000_000, n).astype(np.int32)
-    got = device_ops.cluster_labels_device(torch.from_numpy(a).cuda(), torch.from_numpy(b).cuda(), None, P, 500, 3,
-                                           2_000_000, pair_id=torch.from_numpy(pair).cuda()).cpu().numpy()
-    order = np.argsort(pair, kind="stable")
-    off = np.concatenate([[0], np.cumsum(np.bincount(pair, minlength=P))]).astype(np.int64)
-    want = np.empty(n, dtype=np.int32)
-    want[order] = oracle.cluster_segments(a[order], b[order], off, 500, 3)
-    assert_same(got, want, "keyed")
-
-
 def test_config2_one_million(oracle):
     """BASELINE config 2: 1 M signals, one pair, eps=500, m=3 -- the reference's ids, bit for bit."""
     from tiddit_b200 import device_ops, synth

@@ -4,23 +4,25 @@
 //     sorted(key=posA) -> DBSCAN.main -> labels back in insertion order
 // (tiddit/tiddit_cluster.pyx:140-160, tiddit/DBSCAN.py:33-129).  The reference "DBSCAN" is a
 // sliding-window run detector on the posA-sorted signals followed by the same detector on posB inside
-// every x-cluster; the kernels below evaluate its closed form (DESIGN.md section 3):
+// every x-cluster; the kernels below evaluate its closed form (DESIGN.md section 2):
 //
 //   ok[i]      = the window of the next `reach` signals of i's segment stays within eps
 //   run        = maximal interval of consecutive ok
 //   label[j]   = index of the latest run whose start is <= j, if an ok lies in [j-m+1, j]; else noise
 //
-//   pack_keys_*          key = segment << bits | pos, value = insertion index
-//   radix sort           (segment, posA) stable                                       [tdt_sort.cuh]
-//   window_runs<X_PAIRS> eps-range query on posA + run labelling + compaction of the labelled signals
-//                        into the y-pass sort input  key2 = x-run << bits | posB
-//   radix sort           (x-run, posB) stable
-//   window_runs<Y_SUBS>  eps-range query on posB inside every x-run + sub-run numbering
-//   group_extra_scan     exclusive scan of max(sub-runs - 1, 0) over the x-runs (DBSCAN.py:121-122)
-//   group_bases          the two id bases of every x-run (DBSCAN.py:113-117)
-//   final_labels         reference ids scattered back to insertion order
+// Pipeline (no host synchronisation until the final status read; all sizes that depend on the data --
+// #x-runs, #labelled signals -- stay on the device, grids are sized by upper bounds):
+//   segsort (posA per pair)      hand-written segmented radix sort, 32-bit keys          [tdt_segsort.cuh]
+//   heads_from_offsets           segment starts as a bitmask
+//   window_runs<X>               THE eps-range-query kernel: 4 B key in, run-start / labelled bitmasks out
+//   pair_first_run               #runs before every pair (ids are per pair)
+//   pack_y                       labelled signals compacted: posB gathered, x-run id, x-run offsets
+//   segsort (posB per x-run)     same sort, segments = x-runs
+//   window_runs<Y>               eps-range query on posB inside every x-run
+//   group_extra_scan/bases       DBSCAN.py:113-122 id arithmetic per x-run
+//   final_labels                 reference ids scattered back to insertion order
 #include "tdt_common.cuh"
-#include "tdt_sort.cuh"
+#include "tdt_segsort.cuh"
 
 namespace tdt {
 
@@ -31,61 +33,67 @@ constexpr int WR_WORDS = WR_TILE / 32;   // ballot words per tile
 constexpr int WR_MAX_M = 8192;           // shared-memory halo limit: (TILE + 2*m) keys per CTA
 constexpr uint32_t WR_TMA_CHUNK = 32768; // bytes per bulk copy
 
-enum { OUT_X_PAIRS = 0, OUT_X_LABELS = 1, OUT_Y_SUBS = 2 };
+enum { MODE_X = 0, MODE_Y = 1 };
 enum { ERR_NONE = 0, ERR_RANGE_A = 1, ERR_RANGE_B = 2, ERR_PAIR = 3 };
 
-struct WRParams {
-    const void *keys;   // sorted keys (K*), padded to a multiple of 16 bytes past n
-    int64_t n;
-    int m;              // min_pts
-    u64 eps;            // 0: nothing is ever within eps
-    int shift;          // key >> shift = segment (pair or x-run)
-    u64 *status;        // look-back tile states, zeroed
-    u32 *ticket;        // tile ticket, zeroed
-    // X_PAIRS / X_LABELS
-    const int32_t *vals;   // insertion index per sorted position (nullptr: identity)
-    const int32_t *posB;
-    int bwB;
-    int32_t max_pos;
-    u64 *key2;
-    int32_t *val2;
-    int32_t *grp_pair;
-    int32_t *gfirst;
-    u32 *totals;           // [0] = #x-runs, [1] = #labelled signals
-    int *err;
-    int32_t *labels_out;   // X_LABELS
-    int32_t *last_id_out;  // X_LABELS
-    // Y_SUBS
-    int32_t *ys;
-    int32_t *gcnt_start;
-    int64_t n_groups;
+struct Dims {          // device-resident sizes
+    int64_t n, nseg;
 };
 
-static size_t wr_smem_bytes(int m, size_t key_bytes) {
+struct WRParams {
+    const u32 *keys;      // coordinates, sorted inside every segment; readable up to the next multiple of 4 past n
+    const u32 *heads;     // bit j set <=> j is the first element of a segment; zero beyond n
+    const Dims *dims;     // dims->n = number of elements
+    int m;                // min_pts
+    u64 eps;              // 0: nothing is ever within eps
+    u64 *status;          // look-back tile states, zeroed
+    u32 *ticket;          // tile ticket, zeroed
+    u32 *stw;             // out: run-start bits      (one word per 32 elements)
+    u32 *cvw;             // out: "labelled" bits
+    u32 *tile_pref;       // out: [tile][2] = run starts before the tile, second sum before the tile
+    u32 *totals;          // out: [0] = #runs, [1] = second sum (X: #labelled elements, Y: #segments)
+    int32_t *gcnt_start;  // Y: [segment rank] = run starts before the segment; [#segments] = #runs
+    int32_t *rank_of;     // Y, optional: rank_of[seg_value[j]] = segment rank, written at segment heads
+    const int32_t *seg_value;
+};
+
+static size_t wr_smem_bytes(int m) {
     const size_t HL = ((size_t)(m - 1) + 31) & ~(size_t)31;
     const size_t HR = ((size_t)m + 3) & ~(size_t)3;
-    return (HL + WR_TILE + HR) * key_bytes + ((HL + WR_TILE) / 32 + 4 * WR_WORDS) * sizeof(u32);
+    const size_t head_words = (HL + WR_TILE + HR) / 32 + 2;
+    return (HL + WR_TILE + HR) * 4 + ((HL + WR_TILE) / 32 + head_words + 4 * WR_WORDS) * sizeof(u32);
+}
+
+// any segment head among shared-memory bit positions [a, b] (a <= b)?
+__device__ __forceinline__ bool any_head(const u32 *hw, int a, int b) {
+    const int wa = a >> 5, wb = b >> 5;
+    const u32 first = 0xffffffffu << (a & 31);
+    const u32 last = 0xffffffffu >> (31 - (b & 31));
+    if (wa == wb) return (hw[wa] & first & last) != 0u;
+    if (hw[wa] & first) return true;
+    for (int w = wa + 1; w < wb; w++)
+        if (hw[w]) return true;
+    return (hw[wb] & last) != 0u;
 }
 
 // ----------------------------------------------------------------------------------------------
 // The eps-range-query + run-labelling kernel (DBSCAN.py:40-62 for posA, :90-110 for posB).
 //
-// One CTA = one tile of WR_TILE sorted signals.  Thread 0 takes the tile ticket and issues 1-D TMA
+// One CTA = one tile of WR_TILE sorted coordinates.  Thread 0 takes the tile ticket and issues 1-D TMA
 // bulk copies (UBLKCP) of the tile plus a left halo of m-1 and a right halo of m keys into shared
 // memory; every warp then evaluates 32 windows at a time and packs the outcome with a ballot:
 //   X (reach m, DBSCAN.py:44 slices data[i+1:i+m+1], cut at the segment end):
-//        ok[i] = seg(i+m) == seg(i) ? key[i+m] - key[i] < eps
-//                                   : seg(i+m-1) == seg(i) && key[i+m-1] - key[i] < eps
+//        ok[i] = i+m in i's segment ? key[i+m] - key[i] < eps
+//                                   : i+m-1 in i's segment && key[i+m-1] - key[i] < eps
 //   Y (reach m-1, DBSCAN.py:93 slices y[i+1:i+m], never cut inside range(0, k-m+1)):
-//        ok[i] = seg(i+m-1) == seg(i) && key[i+m-1] - key[i] < eps
-// (sorted keys of one segment differ by exactly the coordinate difference; GENERAL evaluates the
-// reference's max(|x[j]-x[i]|) literally for input that is not sorted.)
-// The last m-1 signals of a segment are never ok, so neither run starts nor the m-1 look-back of the
-// labelling rule can leak across segments, and a halo of m-1 on the left makes both local to the
-// tile: only the NUMBER of run starts (and of labelled signals) before the tile is carried, by the
-// single-pass look-back scan of tdt_common.cuh.
+//        ok[i] = i+m-1 in i's segment && key[i+m-1] - key[i] < eps
+// (GENERAL evaluates the reference's max(|x[j]-x[i]|) literally for input that is not sorted.)
+// "t in i's segment" <=> no segment-head bit in (i, t].  The last m-1 elements of a segment are never ok, so
+// neither run starts nor the m-1 look-back of the labelling rule leak across segments, and a left halo of
+// m-1 makes both local to the tile: only the NUMBER of run starts (and a second sum) before the tile is
+// carried, by the single-pass look-back scan of tdt_common.cuh.  Output is two bits per element.
 // ----------------------------------------------------------------------------------------------
-template <typename K, int OUT, bool GENERAL>
+template <int MODE, bool GENERAL>
 __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
@@ -96,17 +104,18 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
     const int HL = ((m - 1) + 31) & ~31;
     const int HR = (m + 3) & ~3;
     const int EXT = HL + WR_TILE;  // positions whose ok bit is evaluated here
-    K *keys_s = (K *)smem_raw;
-    u32 *okw = (u32 *)(keys_s + (HL + WR_TILE + HR));
-    u32 *stw = okw + EXT / 32;
+    const int HEADW = (EXT + HR) / 32 + 2;
+    u32 *keys_s = (u32 *)smem_raw;
+    u32 *okw = keys_s + (HL + WR_TILE + HR);
+    u32 *hw = okw + EXT / 32;
+    u32 *stw = hw + HEADW;
     u32 *cvw = stw + WR_WORDS;
     u32 *pfxS = cvw + WR_WORDS;
     u32 *pfxC = pfxS + WR_WORDS;
 
     const int lane = threadIdx.x & 31;
     const int warp = threadIdx.x >> 5;
-    const int64_t n = p.n;
-    const K *keys = (const K *)p.keys;
+    const int64_t n = p.dims->n;
 
     if (threadIdx.x == 0) {
         s_tile = (int)atomicAdd(p.ticket, 1u);
@@ -116,23 +125,32 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
     __syncthreads();
     const int tile = s_tile;
     const int64_t tile_base = (int64_t)tile * WR_TILE;
+    if (tile_base >= n) return;               // grids are sized by an upper bound of n
     const int64_t ext_base = tile_base - HL;  // global index of shared position 0
 
     if (threadIdx.x == 0) {
-        constexpr int64_t PER16 = 16 / (int64_t)sizeof(K);
-        const int64_t n_pad = (n + PER16 - 1) / PER16 * PER16;
+        const int64_t n_pad = (n + 3) & ~(int64_t)3;
         const int64_t jlo = ext_base < 0 ? 0 : ext_base;
         int64_t jhi = tile_base + WR_TILE + HR;
         if (jhi > n_pad) jhi = n_pad;
-        const uint32_t bytes = (uint32_t)((jhi - jlo) * (int64_t)sizeof(K));
+        const uint32_t bytes = (uint32_t)((jhi - jlo) * 4);
         mbar_expect_tx(&mbar, bytes);
-        const unsigned char *src = (const unsigned char *)(keys + jlo);
+        const unsigned char *src = (const unsigned char *)(p.keys + jlo);
         unsigned char *dst = (unsigned char *)(keys_s + (jlo - ext_base));
         for (uint32_t off = 0; off < bytes; off += WR_TMA_CHUNK) {
             const uint32_t len = bytes - off < WR_TMA_CHUNK ? bytes - off : WR_TMA_CHUNK;
             tma_load_1d(dst + off, src + off, len, &mbar);
         }
     }
+    {   // segment-head words of [ext_base, ext_base + EXT + HR + 32): plain loads, they overlap the bulk copy
+        const int64_t w0 = ext_base >> 5;  // ext_base is a multiple of 32 (may be negative)
+        const int64_t nwords = (n + 31) >> 5;
+        for (int i = threadIdx.x; i < HEADW; i += WR_THREADS) {
+            const int64_t w = w0 + i;
+            hw[i] = (w >= 0 && w < nwords) ? p.heads[w] : 0u;
+        }
+    }
+    __syncthreads();
     mbar_wait(&mbar, 0);
 
     // ---- phase 1: one ballot word per 32 windows -------------------------------------------
@@ -141,28 +159,25 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
         const int64_t j = ext_base + e;
         bool ok = false;
         if (j >= 0 && j + m - 1 < n) {
-            const K kj = keys_s[e];
+            const u32 kj = keys_s[e];
             if (GENERAL) {
-                // DBSCAN.py:44-51 literally: max |x[i+d] - x[i]| over the next m signals (cut at n)
+                // DBSCAN.py:44-51 literally: max |x[i+d] - x[i]| over the next m elements (cut at n); one segment
                 const int64_t left = n - 1 - j;
                 const int cnt = left < (int64_t)m ? (int)left : m;
-                u64 dmax = 0;
+                u32 dmax = 0;
                 for (int d = 1; d <= cnt; d++) {
-                    const K kt = keys_s[e + d];
-                    const u64 dd = kt > kj ? (u64)(kt - kj) : (u64)(kj - kt);
+                    const u32 kt = keys_s[e + d];
+                    const u32 dd = kt > kj ? kt - kj : kj - kt;
                     dmax = dd > dmax ? dd : dmax;
                 }
-                ok = dmax < p.eps;
-            } else if (OUT == OUT_Y_SUBS) {
-                const K kt = keys_s[e + m - 1];
-                ok = ((kt >> p.shift) == (kj >> p.shift)) && ((u64)(kt - kj) < p.eps);
+                ok = (u64)dmax < p.eps;
+            } else if (MODE == MODE_Y) {
+                ok = !any_head(hw, e + 1, e + m - 1) && ((u64)(keys_s[e + m - 1] - kj) < p.eps);
             } else {
-                K kt = keys_s[e + m];
-                if (j + m < n && (kt >> p.shift) == (kj >> p.shift)) {
-                    ok = (u64)(kt - kj) < p.eps;
+                if (j + m < n && !any_head(hw, e + 1, e + m)) {
+                    ok = (u64)(keys_s[e + m] - kj) < p.eps;
                 } else {
-                    kt = keys_s[e + m - 1];
-                    ok = ((kt >> p.shift) == (kj >> p.shift)) && ((u64)(kt - kj) < p.eps);
+                    ok = !any_head(hw, e + 1, e + m - 1) && ((u64)(keys_s[e + m - 1] - kj) < p.eps);
                 }
             }
         }
@@ -210,7 +225,8 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
 #pragma unroll
         for (int k = 0; k < PER; k++) {
             s[k] = __popc(stw[lane * PER + k]);
-            c[k] = __popc(cvw[lane * PER + k]);
+            // second sum: labelled elements (X, feeds the compaction) or segment heads (Y, ranks the segments)
+            c[k] = MODE == MODE_X ? __popc(cvw[lane * PER + k]) : __popc(hw[HL / 32 + lane * PER + k]);
             ts += s[k];
             tc += c[k];
         }
@@ -241,120 +257,168 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
             s_pref[1] = exC;
             s_pref[2] = aggS;
             s_pref[3] = aggC;
+            p.tile_pref[2 * (int64_t)tile] = exS;
+            p.tile_pref[2 * (int64_t)tile + 1] = exC;
+        }
+    } else {
+        // the two result bits per element (words beyond n are zero: their ok bits are zero)
+        for (int tw = threadIdx.x - 32; tw < WR_WORDS; tw += WR_THREADS - 32) {
+            const int64_t gw = (tile_base >> 5) + tw;
+            if (gw * 32 < n) {
+                p.stw[gw] = stw[tw];
+                p.cvw[gw] = cvw[tw];
+            }
         }
     }
     __syncthreads();
     const u32 exS = s_pref[0], exC = s_pref[1];
 
-    // ---- phase 4: outputs ---------------------------------------------------------------------
-    for (int tw = warp; tw < WR_WORDS; tw += WR_WARPS) {
-        const int e = HL + tw * 32 + lane;
-        const int64_t j = tile_base + tw * 32 + lane;
-        if (j >= n) continue;
-        const u32 st = stw[tw], cv = cvw[tw];
-        const bool covered = (cv >> lane) & 1u;
-        const bool is_start = (st >> lane) & 1u;
-        const u32 starts_before = exS + pfxS[tw] + __popc(st & lanemask_lt());
-        const u32 starts_incl = starts_before + (is_start ? 1u : 0u);
-        const K kj = keys_s[e];
-        const bool head = (j == 0) || ((keys_s[e - 1] >> p.shift) != (kj >> p.shift));
-        if (OUT == OUT_Y_SUBS) {
-            p.ys[j] = covered ? (int32_t)starts_incl : 0;
-            if (head) p.gcnt_start[(int64_t)(kj >> p.shift)] = (int32_t)starts_before;
-        } else {
-            const int32_t idx = p.vals ? p.vals[j] : (int32_t)j;
-            if (OUT == OUT_X_LABELS) {
-                p.labels_out[idx] = covered ? (int32_t)(starts_incl - 1u) : -1;
-            } else {
-                if (head) p.gfirst[(int64_t)(kj >> p.shift)] = (int32_t)starts_before;
-                if (is_start) p.grp_pair[starts_before] = (int32_t)(kj >> p.shift);
-                if (covered) {
-                    const u32 pos = exC + pfxC[tw] + __popc(cv & lanemask_lt());
-                    const int32_t yb = p.posB[idx];
-                    if (yb < 0 || yb > p.max_pos) atomicMax(p.err, ERR_RANGE_B);
-                    p.key2[pos] = ((u64)(starts_incl - 1u) << p.bwB) | (u64)(u32)yb;
-                    p.val2[pos] = idx;
-                }
+    if (MODE == MODE_Y) {  // segment heads record how many runs precede their segment (DBSCAN.py:88 restarts at 0)
+        for (int tw = warp; tw < WR_WORDS; tw += WR_WARPS) {
+            const int64_t j = tile_base + tw * 32 + lane;
+            const u32 h = hw[HL / 32 + tw];
+            if (j < n && ((h >> lane) & 1u)) {
+                const u32 rank = exC + pfxC[tw] + __popc(h & lanemask_lt());
+                p.gcnt_start[rank] = (int32_t)(exS + pfxS[tw] + __popc(stw[tw] & lanemask_lt()));
+                if (p.rank_of) p.rank_of[p.seg_value[j]] = (int32_t)rank;
             }
         }
     }
     if (threadIdx.x == 0 && tile_base + WR_TILE >= n) {  // the last tile publishes the totals
         const u32 totS = exS + s_pref[2], totC = exC + s_pref[3];
-        if (OUT == OUT_Y_SUBS) {
-            p.gcnt_start[p.n_groups] = (int32_t)totS;
-        } else {
-            if (p.totals) {
-                p.totals[0] = totS;
-                p.totals[1] = totC;
+        p.totals[0] = totS;
+        p.totals[1] = totC;
+        if (MODE == MODE_Y) p.gcnt_start[totC] = (int32_t)totS;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// small helpers around the range-query kernel
+// ----------------------------------------------------------------------------------------------
+__global__ void heads_from_offsets_kernel(const int64_t *__restrict__ off, const Dims *dims, u32 *heads) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= dims->nseg) return;
+    const int64_t q = off[s];
+    if (off[s + 1] > q) atomicOr(heads + (q >> 5), 1u << (q & 31));
+}
+
+__global__ void set_dims_kernel(Dims *dims, int64_t n, int64_t nseg, int64_t *off2) {
+    dims->n = n;
+    dims->nseg = nseg;
+    if (off2) {  // the single-segment offsets {0, n}
+        off2[0] = 0;
+        off2[1] = n;
+    }
+}
+
+// run starts before element q, from the start-bit words and the per-tile carries (one warp per query)
+__device__ __forceinline__ u32 runs_before(const u32 *stw, const u32 *tile_pref, int64_t q, int lane) {
+    const int64_t tile = q / WR_TILE;
+    const int64_t w0 = tile * WR_WORDS, wq = q >> 5;
+    u32 c = 0;
+    for (int64_t w = w0 + lane; w <= wq; w += 32) {
+        u32 bits = stw[w];
+        if (w == wq) bits &= (q & 31) ? (0xffffffffu >> (32 - (q & 31))) : 0u;
+        c += __popc(bits);
+    }
+    return tile_pref[2 * tile] + warp_sum(c);
+}
+
+// gfirst[p] = number of x-runs that start before pair p (x ids of pair p are gfirst[p] .. gfirst[p+1]-1)
+__global__ void pair_first_run_kernel(const int64_t *__restrict__ seg_off, int P, const Dims *dims,
+                                      const u32 *__restrict__ stw, const u32 *__restrict__ tile_pref,
+                                      const u32 *__restrict__ totals, int32_t *__restrict__ gfirst) {
+    const int64_t wid = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (wid > P) return;
+    const int64_t q = seg_off[wid];
+    const u32 v = q >= dims->n ? totals[0] : runs_before(stw, tile_pref, q, lane);
+    if (lane == 0) gfirst[wid] = (int32_t)v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// pack_y: the labelled signals, in posA order, become the input of the posB sort: ykey = posB, yval =
+// insertion index, gx = x-run; goff[g] = where x-run g starts (x-runs are contiguous in posA order).
+// ----------------------------------------------------------------------------------------------
+struct PackParams {
+    const u32 *stw, *cvw, *tile_pref, *totals;
+    const Dims *dims;
+    const int32_t *xv;     // insertion index per sorted position (nullptr: identity)
+    const int32_t *posB;
+    int32_t max_pos;
+    u32 *ykey;
+    int32_t *yval, *gx;
+    int64_t *goff;
+    Dims *dims_y;
+    int *err;
+};
+
+__global__ void __launch_bounds__(WR_THREADS) pack_y_kernel(const PackParams p) {
+    __shared__ u32 stw[WR_WORDS], cvw[WR_WORDS], pfxS[WR_WORDS], pfxC[WR_WORDS];
+    const int64_t n = p.dims->n;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_base = tile * WR_TILE;
+    if (tile_base >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < WR_WORDS) {
+        const int64_t gw = tile * WR_WORDS + threadIdx.x;
+        const bool in = gw * 32 < n;
+        stw[threadIdx.x] = in ? p.stw[gw] : 0u;
+        cvw[threadIdx.x] = in ? p.cvw[gw] : 0u;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int PER = WR_WORDS / 32;
+        u32 s[PER], c[PER], ts = 0, tc = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            s[k] = __popc(stw[lane * PER + k]);
+            c[k] = __popc(cvw[lane * PER + k]);
+            ts += s[k];
+            tc += c[k];
+        }
+        u32 is = ts, ic = tc;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, is, o);
+            const u32 b = __shfl_up_sync(0xffffffffu, ic, o);
+            if (lane >= o) {
+                is += a;
+                ic += b;
             }
-            if (OUT == OUT_X_LABELS && p.last_id_out) *p.last_id_out = (int32_t)totS - 1;
+        }
+        u32 es = is - ts, ec = ic - tc;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            pfxS[lane * PER + k] = es;
+            pfxC[lane * PER + k] = ec;
+            es += s[k];
+            ec += c[k];
         }
     }
-}
-
-// ----------------------------------------------------------------------------------------------
-// key packing (tiddit_cluster.pyx:152: the sort key is posA inside one (chrA,chrB) list)
-// ----------------------------------------------------------------------------------------------
-template <typename K>
-__global__ void pack_keys_seg_kernel(const int32_t *__restrict__ posA, const int64_t *__restrict__ seg_off, int P,
-                                     int64_t n, int bwA, int32_t max_pos, K *__restrict__ keys,
-                                     int32_t *__restrict__ vals, int *err) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const int32_t a = posA[j];
-        if (a < 0 || a > max_pos) atomicMax(err, ERR_RANGE_A);
-        int lo = 0, hi = P;  // largest s in [0, P) with seg_off[s] <= j
-        while (hi - lo > 1) {
-            const int mid = (lo + hi) >> 1;
-            if (seg_off[mid] <= j) lo = mid; else hi = mid;
+    __syncthreads();
+    const u32 exS = p.tile_pref[2 * tile], exC = p.tile_pref[2 * tile + 1];
+#pragma unroll 4
+    for (int tw = warp; tw < WR_WORDS; tw += WR_WARPS) {
+        const int64_t j = tile_base + tw * 32 + lane;
+        const u32 st = stw[tw], cv = cvw[tw];
+        if (j < n && ((cv >> lane) & 1u)) {
+            const u32 pos = exC + pfxC[tw] + __popc(cv & lanemask_lt());
+            const u32 g = exS + pfxS[tw] + __popc(st & lanemask_le()) - 1u;
+            const int32_t idx = p.xv ? p.xv[j] : (int32_t)j;
+            const int32_t yb = p.posB[idx];
+            if (yb < 0 || yb > p.max_pos) atomicMax(p.err, ERR_RANGE_B);
+            p.ykey[pos] = (u32)yb;
+            p.yval[pos] = idx;
+            p.gx[pos] = (int32_t)g;
+            if ((st >> lane) & 1u) p.goff[g] = (int64_t)pos;
         }
-        keys[j] = ((K)lo << bwA) | (K)(u32)a;
-        vals[j] = (int32_t)j;
     }
-}
-
-template <typename K>
-__global__ void pack_keys_keyed_kernel(const int32_t *__restrict__ posA, const int32_t *__restrict__ pair_id, int P,
-                                       int64_t n, int bwA, int32_t max_pos, K *__restrict__ keys,
-                                       int32_t *__restrict__ vals, int *err) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const int32_t a = posA[j];
-        int32_t s = pair_id[j];
-        if (a < 0 || a > max_pos) atomicMax(err, ERR_RANGE_A);
-        if (s < 0 || s >= P) {
-            atomicMax(err, ERR_PAIR);
-            s = 0;
-        }
-        keys[j] = ((K)s << bwA) | (K)(u32)a;
-        vals[j] = (int32_t)j;
+    if (threadIdx.x == 0 && tile_base + WR_TILE >= n) {
+        p.goff[p.totals[0]] = (int64_t)p.totals[1];
+        p.dims_y->n = (int64_t)p.totals[1];
+        p.dims_y->nseg = (int64_t)p.totals[0];
     }
-}
-
-// x as given (no sort): the stand-alone DBSCAN.py entry points cluster the caller's order
-__global__ void pack_plain_kernel(const int32_t *__restrict__ x, int64_t n, int32_t max_pos, u32 *__restrict__ keys,
-                                  int *err) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const int32_t a = x[j];
-        if (a < 0 || a > max_pos) atomicMax(err, ERR_RANGE_A);
-        keys[j] = (u32)a;
-    }
-}
-
-// segments without signals take the run count of the next populated segment; gfirst[P] = #runs
-__global__ void fill_gfirst_kernel(int32_t *gfirst, int P, const u32 *totals) {
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s > P) return;
-    if (s == P) {
-        gfirst[P] = (int32_t)totals[0];
-        return;
-    }
-    if (gfirst[s] >= 0) return;
-    int q = s + 1;
-    while (q < P && gfirst[q] < 0) q++;
-    // populated entries are only ever read here, unpopulated ones only written
-    gfirst[s] = q < P ? gfirst[q] : (int32_t)totals[0];
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -366,15 +430,20 @@ constexpr int GS_ITEMS = 8;
 constexpr int GS_TILE = GS_THREADS * GS_ITEMS;
 
 __global__ void __launch_bounds__(GS_THREADS) group_extra_scan_kernel(const int32_t *__restrict__ gcnt_start,
-                                                                      int64_t G, int32_t *__restrict__ X,
+                                                                      const Dims *dims, int32_t *__restrict__ X,
                                                                       u64 *status, u32 *ticket) {
     __shared__ int s_tile;
     __shared__ u32 s_warp[GS_THREADS / 32];
     __shared__ u32 s_ex;
+    const int64_t G = dims->nseg;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = (int)atomicAdd(ticket, 1u);
     __syncthreads();
     const int tile = s_tile;
+    if ((int64_t)tile * GS_TILE >= G) {
+        if (G == 0 && tile == 0 && threadIdx.x == 0) X[0] = 0;
+        return;
+    }
     const int64_t g0 = (int64_t)tile * GS_TILE + (int64_t)threadIdx.x * GS_ITEMS;
     u32 v[GS_ITEMS], tsum = 0;
     int32_t prev = g0 < G ? gcnt_start[g0] : 0;
@@ -427,129 +496,264 @@ __global__ void __launch_bounds__(GS_THREADS) group_extra_scan_kernel(const int3
 // DBSCAN.py:113-117 per x-run g of pair s (x ids of the pair are gfirst[s] .. gfirst[s+1]-1):
 //   sub-run 1 keeps the pair-local x id            base1 = g - gfirst[s]
 //   sub-run k >= 2 gets  k + cluster_id - 1        base2 + k, base2 = nx + (X[g] - X[gfirst[s]]) - 2
-__global__ void group_bases_kernel(const int32_t *__restrict__ grp_pair, const int32_t *__restrict__ gfirst,
-                                   const int32_t *__restrict__ X, int64_t G, int32_t *__restrict__ base1,
-                                   int32_t *__restrict__ base2) {
+__global__ void group_bases_kernel(const int32_t *__restrict__ gfirst, int P, const int32_t *__restrict__ X,
+                                   const Dims *dims, int32_t *__restrict__ base1, int32_t *__restrict__ base2) {
     const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
-    const int32_t s = grp_pair[g];
-    const int32_t gf = gfirst[s];
-    const int32_t nx = gfirst[s + 1] - gf;
+    if (g >= dims->nseg) return;
+    int lo = 0, hi = P;  // the pair of x-run g: largest s with gfirst[s] <= g (pairs without runs repeat a value)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)gfirst[mid] <= g) lo = mid; else hi = mid;
+    }
+    const int32_t gf = gfirst[lo];
+    const int32_t nx = gfirst[lo + 1] - gf;
     base1[g] = (int32_t)g - gf;
     base2[g] = nx + (X[g] - X[gf]) - 2;
 }
 
-__global__ void final_labels_kernel(const u64 *__restrict__ key2, const int32_t *__restrict__ val2,
-                                    const int32_t *__restrict__ ys, const int32_t *__restrict__ gcnt_start,
-                                    const int32_t *__restrict__ base1, const int32_t *__restrict__ base2, int bwB,
-                                    int64_t n2, int32_t *__restrict__ labels_out) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride) {
-        const int32_t y = ys[j];
-        int32_t label = -1;
-        if (y > 0) {
-            const int64_t g = (int64_t)(key2[j] >> bwB);
-            const int32_t sub = y - gcnt_start[g];
-            label = sub == 1 ? base1[g] : base2[g] + sub;
+struct FinalParams {
+    const u32 *stw, *cvw, *tile_pref;
+    const Dims *dims;                 // y dims
+    const int32_t *yval, *gx, *gcnt_start, *base1, *base2;
+    const int32_t *rank_of;           // plain mode: caller id -> segment rank (nullptr: gx is the rank)
+    int32_t plain_cluster_id;         // plain mode: ids continue after this one
+    const int32_t *X;
+    int32_t *labels_out;
+    int32_t *cluster_id_out;          // plain mode
+};
+
+// final ids (DBSCAN.py:112-119), scattered to insertion order; noise stays at the -1 the output was filled with
+template <bool PLAIN>
+__global__ void __launch_bounds__(WR_THREADS) final_labels_kernel(const FinalParams p) {
+    __shared__ u32 stw[WR_WORDS], cvw[WR_WORDS], pfxS[WR_WORDS];
+    const int64_t n = p.dims->n;
+    const int64_t tile = blockIdx.x;
+    const int64_t tile_base = tile * WR_TILE;
+    if (PLAIN && blockIdx.x == 0 && threadIdx.x == 0) *p.cluster_id_out = p.plain_cluster_id + p.X[p.dims->nseg];
+    if (tile_base >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x < WR_WORDS) {
+        const int64_t gw = tile * WR_WORDS + threadIdx.x;
+        const bool in = gw * 32 < n;
+        stw[threadIdx.x] = in ? p.stw[gw] : 0u;
+        cvw[threadIdx.x] = in ? p.cvw[gw] : 0u;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        constexpr int PER = WR_WORDS / 32;
+        u32 s[PER], ts = 0;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            s[k] = __popc(stw[lane * PER + k]);
+            ts += s[k];
         }
-        labels_out[val2[j]] = label;
+        u32 is = ts;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, is, o);
+            if (lane >= o) is += a;
+        }
+        u32 es = is - ts;
+#pragma unroll
+        for (int k = 0; k < PER; k++) {
+            pfxS[lane * PER + k] = es;
+            es += s[k];
+        }
+    }
+    __syncthreads();
+    const u32 exS = p.tile_pref[2 * tile];
+#pragma unroll 4
+    for (int tw = warp; tw < WR_WORDS; tw += WR_WARPS) {
+        const int64_t j = tile_base + tw * 32 + lane;
+        const u32 st = stw[tw], cv = cvw[tw];
+        if (j < n && ((cv >> lane) & 1u)) {
+            const int32_t starts_incl = (int32_t)(exS + pfxS[tw] + __popc(st & lanemask_le()));
+            const int32_t gv = p.gx[j];
+            const int32_t g = PLAIN ? p.rank_of[gv] : gv;
+            const int32_t sub = starts_incl - p.gcnt_start[g];
+            int32_t label;
+            if (PLAIN) label = sub == 1 ? gv : p.plain_cluster_id + p.X[g] + sub - 1;
+            else label = sub == 1 ? p.base1[g] : p.base2[g] + sub;
+            p.labels_out[p.yval[j]] = label;
+        }
     }
 }
 
-// stand-alone y-pass (DBSCAN.py:66-123 on caller-supplied x ids): key2 = id << bits | y, noise is
-// given the id cluster_id + 1 so that it sorts behind every real cluster
-__global__ void pack_y_kernel(const int32_t *__restrict__ y, const int32_t *__restrict__ labels, int64_t n,
-                              int32_t cluster_id, int bwB, int32_t max_pos, u64 *__restrict__ key2,
-                              int32_t *__restrict__ val2, int *err) {
+// x as given (no sort): the stand-alone DBSCAN.py entry points cluster the caller's order
+__global__ void pack_plain_kernel(const int32_t *__restrict__ x, int64_t n, int32_t max_pos, u32 *__restrict__ keys,
+                                  int *err) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
-        const int32_t b = y[j];
+        const int32_t a = x[j];
+        if (a < 0 || a > max_pos) atomicMax(err, ERR_RANGE_A);
+        keys[j] = (u32)a;
+    }
+}
+
+// x-pass labels in the caller's order (DBSCAN.py:33-64 return value): one warp per 32 elements
+__global__ void __launch_bounds__(WR_THREADS) expand_xlabels_kernel(const u32 *__restrict__ stw_g,
+                                                                    const u32 *__restrict__ cvw_g,
+                                                                    const u32 *__restrict__ tile_pref, int64_t n,
+                                                                    const u32 *__restrict__ totals,
+                                                                    int32_t *__restrict__ labels_out,
+                                                                    int32_t *last_id_out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t warp_global = ((int64_t)blockIdx.x * WR_THREADS + threadIdx.x) >> 5;
+    const int64_t warps = ((int64_t)gridDim.x * WR_THREADS) >> 5;
+    if (blockIdx.x == 0 && threadIdx.x == 0 && last_id_out) *last_id_out = (int32_t)totals[0] - 1;
+    for (int64_t gw = warp_global; gw * 32 < n; gw += warps) {
+        const int64_t j = gw * 32 + lane;
+        const u32 before = runs_before(stw_g, tile_pref, gw * 32, lane);
+        const u32 st = stw_g[gw], cv = cvw_g[gw];
+        if (j < n) labels_out[j] = ((cv >> lane) & 1u) ? (int32_t)(before + __popc(st & lanemask_le())) - 1 : -1;
+    }
+}
+
+// stand-alone y-pass (DBSCAN.py:66-123 on caller-supplied ids): sort keys = the id, noise behind every real id
+__global__ void ypass_label_keys_kernel(const int32_t *__restrict__ labels, int64_t n, int32_t cluster_id,
+                                        u32 *__restrict__ keys, int *err) {
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
         int32_t l = labels[j];
-        if (b < 0 || b > max_pos) atomicMax(err, ERR_RANGE_B);
         if (l < -1 || l > cluster_id) {
             atomicMax(err, ERR_PAIR);
             l = -1;
         }
-        if (l < 0) l = cluster_id + 1;
-        key2[j] = ((u64)(u32)l << bwB) | (u64)(u32)b;
-        val2[j] = (int32_t)j;
+        keys[j] = l < 0 ? (u32)(cluster_id + 1) : (u32)l;
     }
 }
 
-// ids that no signal carries have no head to write their start count: take the next one's
-__global__ void fill_gcnt_kernel(int32_t *gcnt_start, int64_t G) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G || gcnt_start[g] >= 0) return;
-    int64_t q = g + 1;
-    while (q < G && gcnt_start[q] < 0) q++;
-    gcnt_start[g] = gcnt_start[q];  // q == G holds the total, written by the last tile
-}
-
-// DBSCAN.py:113-117 with caller ids: sub-run 1 keeps id g, sub-run k >= 2 gets k + (cluster_id + X[g]) - 1;
-// the noise group (g == G - 1) stays noise whatever its windows say
-__global__ void group_bases_plain_kernel(const int32_t *__restrict__ X, int64_t G, int32_t cluster_id,
-                                         int32_t *__restrict__ base1, int32_t *__restrict__ base2,
-                                         int32_t *cluster_id_out) {
-    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= G) return;
-    base1[g] = (int32_t)g;
-    base2[g] = cluster_id + X[g] - 1;
-    if (g == G - 1) *cluster_id_out = cluster_id + X[g];
-}
-
-__global__ void final_labels_plain_kernel(const u64 *__restrict__ key2, const int32_t *__restrict__ val2,
-                                          const int32_t *__restrict__ ys, const int32_t *__restrict__ gcnt_start,
-                                          const int32_t *__restrict__ base1, const int32_t *__restrict__ base2,
-                                          int bwB, int64_t n2, int64_t noise_group, int32_t *__restrict__ labels_out) {
+// sorted ids -> goff[id] = first position of the id (ids without members are filled in afterwards),
+// ykey = y gathered, gx = id
+__global__ void ypass_offsets_kernel(const u32 *__restrict__ ids, const int32_t *__restrict__ idx, int64_t n,
+                                     const int32_t *__restrict__ y, int32_t max_pos, int64_t *__restrict__ goff,
+                                     u32 *__restrict__ ykey, int32_t *__restrict__ gx, int *err) {
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n2; j += stride) {
-        const int32_t y = ys[j];
-        const int64_t g = (int64_t)(key2[j] >> bwB);
-        int32_t label = -1;
-        if (y > 0 && g != noise_group) {
-            const int32_t sub = y - gcnt_start[g];
-            label = sub == 1 ? base1[g] : base2[g] + sub;
-        }
-        labels_out[val2[j]] = label;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const u32 v = ids[j];
+        if (j == 0 || ids[j - 1] != v) goff[v] = j;
+        const int32_t b = y[idx[j]];
+        if (b < 0 || b > max_pos) atomicMax(err, ERR_RANGE_B);
+        ykey[j] = (u32)b;
+        gx[j] = (int32_t)v;
     }
+}
+
+// goff has n_ids + 2 entries: ids 0..n_ids-1, the noise id, the end; unset (-1) ones take the next set one
+__global__ void ypass_fill_offsets_kernel(int64_t *goff, int64_t n_ids, int64_t n) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n_ids + 1) return;
+    if (g == n_ids + 1) {
+        goff[g] = n;
+        return;
+    }
+    if (goff[g] >= 0) return;
+    int64_t q = g + 1;
+    while (q <= n_ids && goff[q] < 0) q++;
+    goff[g] = q <= n_ids ? goff[q] : n;  // set entries are only read, unset ones only written
+}
+
+// stand-alone y-pass: ids without members were skipped by the segment ranking; continue with the ranked count
+__global__ void set_nseg_from_totals_kernel(Dims *dims_y, const u32 *totals_y) { dims_y->nseg = (int64_t)totals_y[1]; }
+
+__global__ void ypass_dims_kernel(const int64_t *goff, int64_t n_ids, Dims *dims_y) {
+    dims_y->n = goff[n_ids];  // where the noise id starts = number of clustered elements
+    dims_y->nseg = n_ids;
 }
 
 // ----------------------------------------------------------------------------------------------
 // host side
 // ----------------------------------------------------------------------------------------------
+struct Small {  // device scalars, one 256-byte block, zeroed per call
+    u32 ticket[4];
+    u32 totals_x[2];
+    u32 totals_y[2];
+    int err;
+    int32_t pad;
+    Dims dims_x, dims_y;
+    int64_t off2[2];
+};
+
 struct ClusterPlan {
-    int64_t n, n_pad;
+    int64_t n, n_pad, tiles, words, gmax;
     int P;
-    size_t keys_bytes, vals_bytes, status_bytes, small_bytes, gfirst_bytes, grp_bytes, sort_bytes;
+    size_t arr, bits, status, tile_pref, gfirst, g32, g64, sort;
     size_t total;
 };
 
 static int64_t wr_tiles(int64_t n) { return (n + WR_TILE - 1) / WR_TILE; }
+static size_t al256(size_t b) { return (b + 255) & ~(size_t)255; }
 
 static ClusterPlan make_plan(int64_t n, int32_t P) {
     ClusterPlan pl;
     pl.n = n;
     pl.P = P;
     pl.n_pad = (n + 63) & ~(int64_t)63;
-    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
-    pl.keys_bytes = al((size_t)pl.n_pad * 8 + 256);
-    pl.vals_bytes = al((size_t)pl.n_pad * 4 + 256);
-    pl.status_bytes = al(((size_t)wr_tiles(n) + 64) * 8);
-    pl.small_bytes = 256;
-    pl.gfirst_bytes = al(((size_t)P + 2) * 4);
-    pl.grp_bytes = al(((size_t)n / 2 + 4) * 4);
-    pl.sort_bytes = al(sort_temp_bytes(n));
-    pl.total = 2 * pl.keys_bytes + 2 * pl.vals_bytes + 2 * pl.status_bytes + pl.small_bytes + pl.gfirst_bytes +
-               5 * pl.grp_bytes + pl.sort_bytes + 4096;
+    pl.tiles = wr_tiles(n) + 1;
+    pl.words = pl.tiles * WR_WORDS + 64;
+    pl.gmax = n / 2 + 4;
+    pl.arr = al256((size_t)pl.n_pad * 4 + 256);
+    pl.bits = al256((size_t)pl.words * 4);
+    pl.status = al256((size_t)(pl.tiles + 64) * 8);
+    pl.tile_pref = al256((size_t)pl.tiles * 8);
+    pl.gfirst = al256(((size_t)P + 2) * 4);
+    pl.g32 = al256((size_t)pl.gmax * 4);
+    pl.g64 = al256((size_t)pl.gmax * 8);
+    const size_t s1 = segsort_temp_bytes(n, P > 0 ? P : 1), s2 = segsort_temp_bytes(n, pl.gmax);
+    pl.sort = al256(s1 > s2 ? s1 : s2);
+    pl.total = 7 * pl.arr + 6 * pl.bits + 3 * pl.status + 2 * pl.tile_pref + 256 + pl.gfirst + 4 * pl.g32 + pl.g64 +
+               pl.sort + 4096;
     return pl;
 }
 
-struct Small {  // device scalars, one 256-byte block
-    u32 ticket[4];
-    u32 totals[2];
-    int err;
-    int32_t last_id;
+struct Buffers {
+    u32 *xs, *tmpK, *ykey;
+    int32_t *xv, *tmpV, *yval, *gx;
+    u32 *headsX, *stwX, *cvwX, *headsY, *stwY, *cvwY;
+    u64 *statusX, *statusY, *statusG;
+    u32 *tprefX, *tprefY;
+    Small *small;
+    int32_t *gfirst, *gcnt_start, *X, *base1, *base2;
+    int64_t *goff;
+    void *sort_temp;
+    bool ok;
 };
+
+static Buffers carve(const ClusterPlan &pl, void *ws, size_t ws_bytes) {
+    Arena ar(ws, ws_bytes);
+    Buffers b;
+    b.xs = (u32 *)ar.take<char>(pl.arr);
+    b.xv = (int32_t *)ar.take<char>(pl.arr);
+    b.tmpK = (u32 *)ar.take<char>(pl.arr);
+    b.tmpV = (int32_t *)ar.take<char>(pl.arr);
+    b.ykey = (u32 *)ar.take<char>(pl.arr);
+    b.yval = (int32_t *)ar.take<char>(pl.arr);
+    b.gx = (int32_t *)ar.take<char>(pl.arr);
+    // everything from headsX up to and including `small` is zeroed by one memset (zero_span)
+    b.headsX = (u32 *)ar.take<char>(pl.bits);
+    b.headsY = (u32 *)ar.take<char>(pl.bits);
+    b.statusX = (u64 *)ar.take<char>(pl.status);
+    b.statusY = (u64 *)ar.take<char>(pl.status);
+    b.statusG = (u64 *)ar.take<char>(pl.status);
+    b.small = (Small *)ar.take<char>(256);
+    b.stwX = (u32 *)ar.take<char>(pl.bits);
+    b.cvwX = (u32 *)ar.take<char>(pl.bits);
+    b.stwY = (u32 *)ar.take<char>(pl.bits);
+    b.cvwY = (u32 *)ar.take<char>(pl.bits);
+    b.tprefX = (u32 *)ar.take<char>(pl.tile_pref);
+    b.tprefY = (u32 *)ar.take<char>(pl.tile_pref);
+    b.gfirst = (int32_t *)ar.take<char>(pl.gfirst);
+    b.gcnt_start = (int32_t *)ar.take<char>(pl.g32);
+    b.X = (int32_t *)ar.take<char>(pl.g32);
+    b.base1 = (int32_t *)ar.take<char>(pl.g32);
+    b.base2 = (int32_t *)ar.take<char>(pl.g32);
+    b.goff = (int64_t *)ar.take<char>(pl.g64);
+    b.sort_temp = ar.take<char>(pl.sort);
+    b.ok = b.sort_temp != nullptr;
+    return b;
+}
+
+static size_t zero_span(const ClusterPlan &pl) { return 2 * pl.bits + 3 * pl.status + 256; }
 
 static int grid_for(int64_t n, int threads) {
     int64_t b = (n + threads - 1) / threads;
@@ -559,22 +763,17 @@ static int grid_for(int64_t n, int threads) {
     return (int)b;
 }
 
-template <typename K, int OUT, bool GENERAL>
-static int launch_window_runs(const WRParams &p, cudaStream_t st) {
-    const size_t smem = wr_smem_bytes(p.m, sizeof(K));
-    static thread_local size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
-        TDT_CUDA(cudaFuncSetAttribute(window_runs_kernel<K, OUT, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+template <int MODE, bool GENERAL>
+static int launch_window_runs(const WRParams &p, int64_t n_max, cudaStream_t st) {
+    const size_t smem = wr_smem_bytes(p.m);
+    if (smem > 48 * 1024)
+        TDT_CUDA(cudaFuncSetAttribute(window_runs_kernel<MODE, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)smem));
-        configured = smem;
-    }
-    const int64_t tiles = wr_tiles(p.n);
-    TDT_LAUNCH((window_runs_kernel<K, OUT, GENERAL>), (unsigned)tiles, WR_THREADS, smem, st, p);
+    TDT_LAUNCH((window_runs_kernel<MODE, GENERAL>), (unsigned)wr_tiles(n_max), WR_THREADS, smem, st, p);
     return TDT_OK;
 }
 
-static int check_common(int64_t n, int32_t min_pts, int32_t eps, void *ws, size_t ws_bytes, size_t need) {
-    (void)eps;
+static int check_common(int64_t n, int32_t min_pts, void *ws, size_t ws_bytes, size_t need) {
     if (n < 0) return fail(TDT_E_ARG, "n = %lld is negative", (long long)n);
     if (n > 2000000000LL) return fail(TDT_E_ARG, "n = %lld exceeds the 2e9 signals one call supports", (long long)n);
     if (min_pts < 2)
@@ -591,165 +790,157 @@ static int err_to_code(int e) {
         case ERR_NONE: return TDT_OK;
         case ERR_RANGE_A: return fail(TDT_E_RANGE, "a posA / x coordinate is negative or above max_pos");
         case ERR_RANGE_B: return fail(TDT_E_RANGE, "a posB / y coordinate is negative or above max_pos");
-        default: return fail(TDT_E_RANGE, "a pair id is outside [0, P)");
+        default: return fail(TDT_E_RANGE, "a pair / cluster id is outside its range");
     }
 }
 
-// y-pass on the compacted (x-run, posB) pairs + final ids.  key2/val2 in bufs `cur`; `alt` free.
-static int run_ypass(const ClusterPlan &pl, char *keys_cur, char *keys_alt, int32_t *vals_cur, int32_t *vals_alt,
-                     int64_t n2, int64_t G, int bwB, int32_t eps, int32_t m, int32_t *grp_pair, int32_t *gfirst,
-                     int32_t *gcnt_start, int32_t *X, int32_t *base1, int32_t *base2, u64 *status, Small *small,
-                     void *sort_temp, int32_t *labels_out, cudaStream_t st) {
-    const int bits = bwB + bit_width_u32((uint32_t)(G - 1));
-    int which = 0;
-    int rc;
-    {
-        ProfScope ps("sort_y", st);
-        rc = sort_pairs<u64>((u64 *)keys_cur, (u64 *)keys_alt, vals_cur, vals_alt, n2, bits, sort_temp,
-                             pl.sort_bytes, st, &which);
-    }
-    if (rc) return rc;
-    u64 *k2 = (u64 *)(which ? keys_alt : keys_cur);
-    int32_t *v2 = which ? vals_alt : vals_cur;
-    int32_t *ys = (int32_t *)(which ? keys_cur : keys_alt);  // the buffer the sort left free
-
-    TDT_CUDA(cudaMemsetAsync(status, 0, pl.status_bytes, st));
-    WRParams p = {};
-    p.keys = k2;
-    p.n = n2;
-    p.m = m;
-    p.eps = eps > 0 ? (u64)eps : 0;
-    p.shift = bwB;
-    p.status = status;
-    p.ticket = &small->ticket[1];
-    p.ys = ys;
-    p.gcnt_start = gcnt_start;
-    p.n_groups = G;
-    {
-        ProfScope ps("window_runs_y", st);
-        rc = launch_window_runs<u64, OUT_Y_SUBS, false>(p, st);
-    }
-    if (rc) return rc;
-
-    u64 *status2 = status + (pl.status_bytes / 8);
-    TDT_CUDA(cudaMemsetAsync(status2, 0, pl.status_bytes, st));
-    const unsigned gs_tiles = (unsigned)((G + GS_TILE - 1) / GS_TILE);
-    {
-        ProfScope ps("group_ids", st);
-        TDT_LAUNCH(group_extra_scan_kernel, gs_tiles, GS_THREADS, 0, st, gcnt_start, G, X, status2,
-                   &small->ticket[2]);
-        TDT_LAUNCH(group_bases_kernel, (unsigned)((G + 255) / 256), 256, 0, st, grp_pair, gfirst, X, G, base1, base2);
-    }
-    ProfScope ps("final_labels", st);
-    TDT_LAUNCH(final_labels_kernel, grid_for(n2, 256), 256, 0, st, k2, v2, ys, gcnt_start, base1, base2, bwB, n2,
-               labels_out);
-    return TDT_OK;
-}
-
-template <typename K>
-static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t *seg_off, const int32_t *pair_id,
-                        int64_t n, int32_t P, int32_t eps, int32_t m, int32_t max_pos, int bwA, int32_t *labels_out,
-                        void *ws, size_t ws_bytes, cudaStream_t st, bool presorted_plain) {
-    const ClusterPlan pl = make_plan(n, P);
-    Arena ar(ws, ws_bytes);
-    char *keysA = ar.take<char>(pl.keys_bytes);
-    char *keysB = ar.take<char>(pl.keys_bytes);
-    int32_t *valsA = (int32_t *)ar.take<char>(pl.vals_bytes);
-    int32_t *valsB = (int32_t *)ar.take<char>(pl.vals_bytes);
-    u64 *status = (u64 *)ar.take<char>(2 * pl.status_bytes);
-    Small *small = (Small *)ar.take<char>(pl.small_bytes);
-    int32_t *gfirst = (int32_t *)ar.take<char>(pl.gfirst_bytes);
-    int32_t *grp_pair = (int32_t *)ar.take<char>(pl.grp_bytes);
-    int32_t *gcnt_start = (int32_t *)ar.take<char>(pl.grp_bytes);
-    int32_t *X = (int32_t *)ar.take<char>(pl.grp_bytes);
-    int32_t *base1 = (int32_t *)ar.take<char>(pl.grp_bytes);
-    int32_t *base2 = (int32_t *)ar.take<char>(pl.grp_bytes);
-    void *sort_temp = ar.take<char>(pl.sort_bytes);
-    if (!sort_temp) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
-
-    const int bwP = bit_width_u32((uint32_t)(P - 1));
-    TDT_CUDA(cudaMemsetAsync(labels_out, 0xff, (size_t)n * 4, st));
-    TDT_CUDA(cudaMemsetAsync(status, 0, pl.status_bytes, st));
-    TDT_CUDA(cudaMemsetAsync(small, 0, pl.small_bytes, st));
-    TDT_CUDA(cudaMemsetAsync(gfirst, 0xff, pl.gfirst_bytes, st));
-
-    K *kcur;
-    int32_t *vcur;
-    char *kalt;
-    int32_t *valt;
-    if (presorted_plain) {
-        // DBSCAN.main on the caller's order: no sort, identity permutation
-        TDT_LAUNCH(pack_plain_kernel, grid_for(n, 256), 256, 0, st, posA, n, max_pos, (u32 *)keysA, &small->err);
-        kcur = (K *)keysA;
-        vcur = nullptr;
-        kalt = keysB;
-        valt = valsB;
-    } else {
-        if (seg_off) {
-            ProfScope ps("pack_keys", st);
-            TDT_LAUNCH(pack_keys_seg_kernel<K>, grid_for(n, 256), 256, 0, st, posA, seg_off, P, n, bwA, max_pos,
-                       (K *)keysA, valsA, &small->err);
-        } else {
-            ProfScope ps("pack_keys", st);
-            TDT_LAUNCH(pack_keys_keyed_kernel<K>, grid_for(n, 256), 256, 0, st, posA, pair_id, P, n, bwA, max_pos,
-                       (K *)keysA, valsA, &small->err);
-        }
-        int which = 0;
-        int rc;
-        {
-            ProfScope ps("sort_x", st);
-            rc = sort_pairs<K>((K *)keysA, (K *)keysB, valsA, valsB, n, bwA + bwP, sort_temp, pl.sort_bytes, st,
-                               &which);
-        }
-        if (rc) return rc;
-        kcur = (K *)(which ? keysB : keysA);
-        vcur = which ? valsB : valsA;
-        kalt = which ? keysA : keysB;
-        valt = which ? valsA : valsB;
-    }
-
-    const int bwB = bwA;
-    WRParams p = {};
-    p.keys = kcur;
-    p.n = n;
-    p.m = m;
-    p.eps = eps > 0 ? (u64)eps : 0;
-    p.shift = bwA;
-    p.status = status;
-    p.ticket = &small->ticket[0];
-    p.vals = vcur;
-    p.posB = posB;
-    p.bwB = bwB;
-    p.max_pos = max_pos;
-    p.key2 = (u64 *)kalt;
-    p.val2 = valt;
-    p.grp_pair = grp_pair;
-    p.gfirst = gfirst;
-    p.totals = small->totals;
-    p.err = &small->err;
-    int rc;
-    {
-        ProfScope ps("window_runs_x", st);
-        rc = presorted_plain ? launch_window_runs<K, OUT_X_PAIRS, true>(p, st)
-                             : launch_window_runs<K, OUT_X_PAIRS, false>(p, st);
-    }
-    if (rc) return rc;
-
+static int finish(Buffers &b, cudaStream_t st) {
     Small h;
-    TDT_CUDA(cudaMemcpyAsync(&h, small, sizeof(Small), cudaMemcpyDeviceToHost, st));
+    TDT_CUDA(cudaMemcpyAsync(&h, b.small, sizeof(Small), cudaMemcpyDeviceToHost, st));
     TDT_CUDA(cudaStreamSynchronize(st));
-    if (h.err) return err_to_code(h.err);
-    const int64_t G = h.totals[0], n2 = h.totals[1];
-    if (G == 0) return TDT_OK;  // everything is noise
-    TDT_LAUNCH(fill_gfirst_kernel, (unsigned)((P + 1 + 255) / 256), 256, 0, st, gfirst, P, small->totals);
-    // the sorted x keys / insertion indices are dead now: their buffers become the sort's alternates
-    char *dead_keys = (char *)kcur == keysA ? keysA : keysB;
-    int32_t *dead_vals = (valt == valsA) ? valsB : valsA;
-    return run_ypass(pl, kalt, dead_keys, valt, dead_vals, n2, G, bwB, eps, m, grp_pair, gfirst, gcnt_start, X, base1,
-                     base2, status, small, sort_temp, labels_out, st);
+    return err_to_code(h.err);
 }
 
 static int pos_bits(int32_t max_pos) { return bit_width_u32(max_pos > 0 ? (uint32_t)max_pos : 0x7fffffffu); }
+
+// y-pass on the compacted (posB, insertion index, x-run) triples in ykey/yval/gx with offsets goff and
+// sizes dims_y; writes the final ids.  PLAIN: caller ids (stand-alone y-pass).
+template <bool PLAIN>
+static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, int key_bits, int P,
+                     int32_t plain_cluster_id, int32_t *rank_of, int32_t *labels_out, int32_t *cluster_id_out,
+                     cudaStream_t st) {
+    const int64_t n = pl.n;
+    const int64_t gmax = PLAIN ? (int64_t)plain_cluster_id + 1 : pl.gmax;
+    {
+        ProfScope ps("sort_y", st);
+        int rc = segsort_pairs(b.ykey, b.yval, b.xs, b.xv, b.tmpK, b.tmpV, b.goff, (const int64_t *)&b.small->dims_y, n,
+                               gmax, key_bits, b.sort_temp, pl.sort, &b.small->err, st);
+        if (rc) return rc;
+        TDT_LAUNCH(heads_from_offsets_kernel, (unsigned)((gmax + 255) / 256), 256, 0, st, b.goff, &b.small->dims_y,
+                   b.headsY);
+    }
+    WRParams p = {};
+    p.keys = b.xs;
+    p.heads = b.headsY;
+    p.dims = &b.small->dims_y;
+    p.m = m;
+    p.eps = eps > 0 ? (u64)eps : 0;
+    p.status = b.statusY;
+    p.ticket = &b.small->ticket[1];
+    p.stw = b.stwY;
+    p.cvw = b.cvwY;
+    p.tile_pref = b.tprefY;
+    p.totals = b.small->totals_y;
+    p.gcnt_start = b.gcnt_start;
+    p.rank_of = PLAIN ? rank_of : nullptr;
+    p.seg_value = b.gx;
+    {
+        ProfScope ps("window_runs_y", st);
+        int rc = launch_window_runs<MODE_Y, false>(p, n, st);
+        if (rc) return rc;
+        if (PLAIN) TDT_LAUNCH(set_nseg_from_totals_kernel, 1, 1, 0, st, &b.small->dims_y, b.small->totals_y);
+    }
+    {
+        ProfScope ps("group_ids", st);
+        const unsigned gs_tiles = (unsigned)((gmax + GS_TILE - 1) / GS_TILE);
+        TDT_LAUNCH(group_extra_scan_kernel, gs_tiles, GS_THREADS, 0, st, b.gcnt_start, &b.small->dims_y, b.X,
+                   b.statusG, &b.small->ticket[2]);
+        if (!PLAIN)
+            TDT_LAUNCH(group_bases_kernel, (unsigned)((gmax + 255) / 256), 256, 0, st, b.gfirst, P, b.X,
+                       &b.small->dims_y, b.base1, b.base2);
+    }
+    FinalParams f = {};
+    f.stw = b.stwY;
+    f.cvw = b.cvwY;
+    f.tile_pref = b.tprefY;
+    f.dims = &b.small->dims_y;
+    f.yval = b.xv;
+    f.gx = b.gx;
+    f.gcnt_start = b.gcnt_start;
+    f.base1 = b.base1;
+    f.base2 = b.base2;
+    f.rank_of = rank_of;
+    f.plain_cluster_id = plain_cluster_id;
+    f.X = b.X;
+    f.labels_out = labels_out;
+    f.cluster_id_out = cluster_id_out;
+    ProfScope ps("final_labels", st);
+    TDT_LAUNCH(final_labels_kernel<PLAIN>, (unsigned)wr_tiles(n), WR_THREADS, 0, st, f);
+    return TDT_OK;
+}
+
+// seg_off: device offsets of the P pairs, or nullptr with presorted_plain (one segment, no sort)
+static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t *seg_off, int64_t n, int32_t P,
+                        int32_t eps, int32_t m, int32_t max_pos, int32_t *labels_out, void *ws, size_t ws_bytes,
+                        cudaStream_t st, bool presorted_plain) {
+    const ClusterPlan pl = make_plan(n, P);
+    Buffers b = carve(pl, ws, ws_bytes);
+    if (!b.ok) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
+    const int key_bits = pos_bits(max_pos);
+
+    TDT_CUDA(cudaMemsetAsync(labels_out, 0xff, (size_t)n * 4, st));
+    TDT_CUDA(cudaMemsetAsync(b.headsX, 0, zero_span(pl), st));
+    TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &b.small->dims_x, n, (int64_t)P, b.small->off2);
+
+    const int32_t *xv = nullptr;
+    if (presorted_plain) {
+        // DBSCAN.main on the caller's order: no sort, identity permutation, one segment
+        TDT_LAUNCH(pack_plain_kernel, grid_for(n, 256), 256, 0, st, posA, n, max_pos, b.xs, &b.small->err);
+        seg_off = b.small->off2;
+    } else {
+        ProfScope ps("sort_x", st);
+        // posA as unsigned keys: a negative coordinate has bit 31 set and trips the key-range check
+        int rc = segsort_pairs((const u32 *)posA, nullptr, b.xs, b.xv, b.tmpK, b.tmpV, seg_off,
+                               (const int64_t *)&b.small->dims_x, n, P, key_bits, b.sort_temp, pl.sort, &b.small->err,
+                               st);
+        if (rc) return rc;
+        xv = b.xv;
+    }
+    TDT_LAUNCH(heads_from_offsets_kernel, (unsigned)((P + 255) / 256), 256, 0, st, seg_off, &b.small->dims_x, b.headsX);
+
+    WRParams p = {};
+    p.keys = b.xs;
+    p.heads = b.headsX;
+    p.dims = &b.small->dims_x;
+    p.m = m;
+    p.eps = eps > 0 ? (u64)eps : 0;
+    p.status = b.statusX;
+    p.ticket = &b.small->ticket[0];
+    p.stw = b.stwX;
+    p.cvw = b.cvwX;
+    p.tile_pref = b.tprefX;
+    p.totals = b.small->totals_x;
+    {
+        ProfScope ps("window_runs_x", st);
+        int rc = presorted_plain ? launch_window_runs<MODE_X, true>(p, n, st)
+                                 : launch_window_runs<MODE_X, false>(p, n, st);
+        if (rc) return rc;
+    }
+    {
+        ProfScope ps("pack_y", st);
+        TDT_LAUNCH(pair_first_run_kernel, (unsigned)(((int64_t)(P + 1) * 32 + 255) / 256), 256, 0, st, seg_off, P,
+                   &b.small->dims_x, b.stwX, b.tprefX, b.small->totals_x, b.gfirst);
+        PackParams k = {};
+        k.stw = b.stwX;
+        k.cvw = b.cvwX;
+        k.tile_pref = b.tprefX;
+        k.totals = b.small->totals_x;
+        k.dims = &b.small->dims_x;
+        k.xv = xv;
+        k.posB = posB;
+        k.max_pos = max_pos;
+        k.ykey = b.ykey;
+        k.yval = b.yval;
+        k.gx = b.gx;
+        k.goff = b.goff;
+        k.dims_y = &b.small->dims_y;
+        k.err = &b.small->err;
+        TDT_LAUNCH(pack_y_kernel, (unsigned)wr_tiles(n), WR_THREADS, 0, st, k);
+    }
+    int rc = run_ypass<false>(pl, b, eps, m, key_bits, P, 0, nullptr, labels_out, nullptr, st);
+    if (rc) return rc;
+    return finish(b, st);
+}
 
 }  // namespace tdt
 
@@ -768,53 +959,28 @@ int tdt_cluster_labels(const int32_t *posA, const int32_t *posB, const int64_t *
                        void *stream) {
     if (P < 1 && n > 0) return fail(TDT_E_ARG, "P = %d pairs for %lld signals", P, (long long)n);
     if (max_pos < 0) return fail(TDT_E_ARG, "max_pos = %d is negative", max_pos);
-    int rc = check_common(n, min_pts, eps, ws, ws_bytes, make_plan(n, P < 1 ? 1 : P).total);
+    int rc = check_common(n, min_pts, ws, ws_bytes, make_plan(n, P < 1 ? 1 : P).total);
     if (rc || n == 0) return rc;
     if (!posA || !posB || !seg_off || !labels_out) return fail(TDT_E_ARG, "null pointer argument");
-    const int bwA = pos_bits(max_pos);
     if (max_pos == 0) max_pos = 0x7fffffff;
-    const int bits = bwA + bit_width_u32((uint32_t)(P - 1));
-    if (bits <= 32)
-        return cluster_impl<u32>(posA, posB, seg_off, nullptr, n, P, eps, min_pts, max_pos, bwA, labels_out, ws,
-                                 ws_bytes, (cudaStream_t)stream, false);
-    return cluster_impl<u64>(posA, posB, seg_off, nullptr, n, P, eps, min_pts, max_pos, bwA, labels_out, ws, ws_bytes,
-                             (cudaStream_t)stream, false);
-}
-
-int tdt_cluster_labels_keyed(const int32_t *posA, const int32_t *posB, const int32_t *pair_id, int64_t n, int32_t P,
-                             int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out, void *ws,
-                             size_t ws_bytes, void *stream) {
-    if (P < 1 && n > 0) return fail(TDT_E_ARG, "P = %d pairs for %lld signals", P, (long long)n);
-    if (max_pos < 0) return fail(TDT_E_ARG, "max_pos = %d is negative", max_pos);
-    int rc = check_common(n, min_pts, eps, ws, ws_bytes, make_plan(n, P < 1 ? 1 : P).total);
-    if (rc || n == 0) return rc;
-    if (!posA || !posB || !pair_id || !labels_out) return fail(TDT_E_ARG, "null pointer argument");
-    const int bwA = pos_bits(max_pos);
-    if (max_pos == 0) max_pos = 0x7fffffff;
-    const int bits = bwA + bit_width_u32((uint32_t)(P - 1));
-    if (bits <= 32)
-        return cluster_impl<u32>(posA, posB, nullptr, pair_id, n, P, eps, min_pts, max_pos, bwA, labels_out, ws,
-                                 ws_bytes, (cudaStream_t)stream, false);
-    return cluster_impl<u64>(posA, posB, nullptr, pair_id, n, P, eps, min_pts, max_pos, bwA, labels_out, ws, ws_bytes,
-                             (cudaStream_t)stream, false);
+    return cluster_impl(posA, posB, seg_off, n, P, eps, min_pts, max_pos, labels_out, ws, ws_bytes,
+                        (cudaStream_t)stream, false);
 }
 
 int tdt_dbscan_main(const int32_t *x, const int32_t *y, int64_t n, int32_t eps, int32_t min_pts, int32_t max_pos,
                     int32_t *labels_out, void *ws, size_t ws_bytes, void *stream) {
     if (max_pos < 0) return fail(TDT_E_ARG, "max_pos = %d is negative", max_pos);
-    int rc = check_common(n, min_pts, eps, ws, ws_bytes, make_plan(n, 1).total);
+    int rc = check_common(n, min_pts, ws, ws_bytes, make_plan(n, 1).total);
     if (rc || n == 0) return rc;
     if (!x || !y || !labels_out) return fail(TDT_E_ARG, "null pointer argument");
-    const int bw = pos_bits(max_pos);
     if (max_pos == 0) max_pos = 0x7fffffff;
-    // keys are the plain 31-bit x values: a shift of 31 puts every signal in segment 0
-    return cluster_impl<u32>(x, y, nullptr, nullptr, n, 1, eps, min_pts, max_pos, bw, labels_out, ws, ws_bytes,
-                             (cudaStream_t)stream, true);
+    return cluster_impl(x, y, nullptr, n, 1, eps, min_pts, max_pos, labels_out, ws, ws_bytes, (cudaStream_t)stream,
+                        true);
 }
 
 int tdt_xpass_labels(const int32_t *x, int64_t n, int32_t eps, int32_t min_pts, int32_t *labels_out,
                      int32_t *last_id_out, void *ws, size_t ws_bytes, void *stream) {
-    int rc = check_common(n, min_pts, eps, ws, ws_bytes, make_plan(n, 1).total);
+    int rc = check_common(n, min_pts, ws, ws_bytes, make_plan(n, 1).total);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     if (n == 0) {
@@ -823,100 +989,98 @@ int tdt_xpass_labels(const int32_t *x, int64_t n, int32_t eps, int32_t min_pts, 
     }
     if (!x || !labels_out) return fail(TDT_E_ARG, "null pointer argument");
     const ClusterPlan pl = make_plan(n, 1);
-    Arena ar(ws, ws_bytes);
-    char *keysA = ar.take<char>(pl.keys_bytes);
-    ar.take<char>(pl.keys_bytes);
-    ar.take<char>(2 * pl.vals_bytes);
-    u64 *status = (u64 *)ar.take<char>(2 * pl.status_bytes);
-    Small *small = (Small *)ar.take<char>(pl.small_bytes);
-    TDT_CUDA(cudaMemsetAsync(status, 0, pl.status_bytes, st));
-    TDT_CUDA(cudaMemsetAsync(small, 0, pl.small_bytes, st));
-    TDT_LAUNCH(pack_plain_kernel, grid_for(n, 256), 256, 0, st, x, n, 0x7fffffff, (u32 *)keysA, &small->err);
+    Buffers b = carve(pl, ws, ws_bytes);
+    if (!b.ok) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
+    TDT_CUDA(cudaMemsetAsync(b.headsX, 0, zero_span(pl), st));
+    TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &b.small->dims_x, n, (int64_t)1, b.small->off2);
+    TDT_LAUNCH(pack_plain_kernel, grid_for(n, 256), 256, 0, st, x, n, 0x7fffffff, b.xs, &b.small->err);
+    TDT_LAUNCH(heads_from_offsets_kernel, 1, 256, 0, st, b.small->off2, &b.small->dims_x, b.headsX);
     WRParams p = {};
-    p.keys = keysA;
-    p.n = n;
+    p.keys = b.xs;
+    p.heads = b.headsX;
+    p.dims = &b.small->dims_x;
     p.m = min_pts;
     p.eps = eps > 0 ? (u64)eps : 0;
-    p.shift = 31;
-    p.status = status;
-    p.ticket = &small->ticket[0];
-    p.labels_out = labels_out;
-    p.last_id_out = last_id_out;
-    return launch_window_runs<u32, OUT_X_LABELS, true>(p, st);
+    p.status = b.statusX;
+    p.ticket = &b.small->ticket[0];
+    p.stw = b.stwX;
+    p.cvw = b.cvwX;
+    p.tile_pref = b.tprefX;
+    p.totals = b.small->totals_x;
+    rc = launch_window_runs<MODE_X, true>(p, n, st);
+    if (rc) return rc;
+    TDT_LAUNCH(expand_xlabels_kernel, grid_for(n, WR_THREADS), WR_THREADS, 0, st, b.stwX, b.cvwX, b.tprefX, n,
+               b.small->totals_x, labels_out, last_id_out);
+    return finish(b, st);
 }
 
 int tdt_ypass_labels(const int32_t *y, int64_t n, int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_io,
                      int32_t *cluster_id_io, void *ws, size_t ws_bytes, void *stream) {
     if (max_pos < 0) return fail(TDT_E_ARG, "max_pos = %d is negative", max_pos);
-    int rc = check_common(n, min_pts, eps, ws, ws_bytes, make_plan(n, 1).total);
+    int rc = check_common(n, min_pts, ws, ws_bytes, make_plan(n, 1).total);
     if (rc || n == 0) return rc;
     if (!y || !labels_io || !cluster_id_io) return fail(TDT_E_ARG, "null pointer argument");
     cudaStream_t st = (cudaStream_t)stream;
-    const int bwB = pos_bits(max_pos);
+    const int key_bits = pos_bits(max_pos);
     if (max_pos == 0) max_pos = 0x7fffffff;
     int32_t cluster_id = -1;
     TDT_CUDA(cudaMemcpyAsync(&cluster_id, cluster_id_io, 4, cudaMemcpyDeviceToHost, st));
     TDT_CUDA(cudaStreamSynchronize(st));
-    if (cluster_id < -1 || (int64_t)cluster_id >= n)
-        return fail(TDT_E_ARG, "cluster_id = %d is not the id count of %lld signals", cluster_id, (long long)n);
-
+    if (cluster_id < -1) return fail(TDT_E_ARG, "cluster_id = %d", cluster_id);
+    if (cluster_id < 0) return TDT_OK;  // no clusters: nothing to do
     const ClusterPlan pl = make_plan(n, 1);
-    Arena ar(ws, ws_bytes);
-    char *keysA = ar.take<char>(pl.keys_bytes);
-    char *keysB = ar.take<char>(pl.keys_bytes);
-    int32_t *valsA = (int32_t *)ar.take<char>(pl.vals_bytes);
-    int32_t *valsB = (int32_t *)ar.take<char>(pl.vals_bytes);
-    u64 *status = (u64 *)ar.take<char>(2 * pl.status_bytes);
-    Small *small = (Small *)ar.take<char>(pl.small_bytes);
-    ar.take<char>(pl.gfirst_bytes);
-    // G = cluster_id + 2 ids (noise last) can exceed n/2 + 4 only for ids without signals; size check
-    const int64_t G = (int64_t)cluster_id + 2;
-    int32_t *grp = (int32_t *)ar.take<char>(5 * pl.grp_bytes);
-    void *sort_temp = ar.take<char>(pl.sort_bytes);
-    if (!sort_temp) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
-    const size_t per = (size_t)(G + 2);
-    if (4 * per * 4 > 5 * pl.grp_bytes)
-        return fail(TDT_E_ARG, "cluster_id = %d: more ids than the workspace of %lld signals holds", cluster_id,
+    if ((int64_t)cluster_id + 4 > pl.gmax)
+        return fail(TDT_E_ARG, "cluster_id = %d: the x-pass never yields more than n/2 ids (n = %lld)", cluster_id,
                     (long long)n);
-    int32_t *gcnt_start = grp, *X = grp + per, *base1 = grp + 2 * per, *base2 = grp + 3 * per;
+    Buffers b = carve(pl, ws, ws_bytes);
+    if (!b.ok) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
+    const int64_t n_ids = (int64_t)cluster_id + 1;  // real ids 0..cluster_id; the noise id is n_ids
 
-    TDT_CUDA(cudaMemsetAsync(status, 0, 2 * pl.status_bytes, st));
-    TDT_CUDA(cudaMemsetAsync(small, 0, pl.small_bytes, st));
-    TDT_CUDA(cudaMemsetAsync(gcnt_start, 0xff, per * 4, st));
-    TDT_LAUNCH(pack_y_kernel, grid_for(n, 256), 256, 0, st, y, labels_io, n, cluster_id, bwB, max_pos, (u64 *)keysA,
-               valsA, &small->err);
-    const int bits = bwB + bit_width_u32((uint32_t)(G - 1));
-    int which = 0;
-    rc = sort_pairs<u64>((u64 *)keysA, (u64 *)keysB, valsA, valsB, n, bits, sort_temp, pl.sort_bytes, st, &which);
+    TDT_CUDA(cudaMemsetAsync(b.headsX, 0, zero_span(pl), st));
+    TDT_CUDA(cudaMemsetAsync(b.goff, 0xff, (size_t)(n_ids + 2) * 8, st));
+    TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &b.small->dims_x, n, (int64_t)1, b.small->off2);
+    // 1. group the elements by id (stable): one segment, keys = id
+    TDT_LAUNCH(ypass_label_keys_kernel, grid_for(n, 256), 256, 0, st, labels_io, n, cluster_id, b.ykey, &b.small->err);
+    rc = segsort_pairs(b.ykey, nullptr, b.xs, b.xv, b.tmpK, b.tmpV, b.small->off2, (const int64_t *)&b.small->dims_x, n,
+                       1, bit_width_u32((uint32_t)(cluster_id + 1)), b.sort_temp, pl.sort, &b.small->err, st);
     if (rc) return rc;
-    u64 *k2 = (u64 *)(which ? keysB : keysA);
-    int32_t *v2 = which ? valsB : valsA;
-    int32_t *ys = (int32_t *)(which ? keysA : keysB);
-    WRParams p = {};
-    p.keys = k2;
-    p.n = n;
-    p.m = min_pts;
-    p.eps = eps > 0 ? (u64)eps : 0;
-    p.shift = bwB;
-    p.status = status;
-    p.ticket = &small->ticket[1];
-    p.ys = ys;
-    p.gcnt_start = gcnt_start;
-    p.n_groups = G;
-    rc = launch_window_runs<u64, OUT_Y_SUBS, false>(p, st);
+    // 2. offsets per id, y gathered; the noise block (last) is left out of everything that follows
+    TDT_LAUNCH(ypass_offsets_kernel, grid_for(n, 256), 256, 0, st, b.xs, b.xv, n, y, max_pos, b.goff, b.ykey, b.gx,
+               &b.small->err);
+    TDT_LAUNCH(ypass_fill_offsets_kernel, (unsigned)((n_ids + 2 + 255) / 256), 256, 0, st, b.goff, n_ids, n);
+    TDT_LAUNCH(ypass_dims_kernel, 1, 1, 0, st, b.goff, n_ids, &b.small->dims_y);
+    // yval = insertion index in id order (b.xv): copied, because the y sort writes its result into xs / xv
+    TDT_CUDA(cudaMemcpyAsync(b.yval, b.xv, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+    // labels of clustered elements are rewritten by final_labels; members of sub-clusters that dissolve become noise
+    TDT_CUDA(cudaMemsetAsync(labels_io, 0xff, (size_t)n * 4, st));
+    int32_t *rank_of = b.base1;  // id -> rank among the ids that have members (base1 is unused in plain mode)
+    rc = run_ypass<true>(pl, b, eps, min_pts, key_bits, 1, cluster_id, rank_of, labels_io, cluster_id_io, st);
     if (rc) return rc;
-    TDT_LAUNCH(fill_gcnt_kernel, (unsigned)((G + 255) / 256), 256, 0, st, gcnt_start, G);
-    u64 *status2 = status + (pl.status_bytes / 8);
-    TDT_LAUNCH(group_extra_scan_kernel, (unsigned)((G + GS_TILE - 1) / GS_TILE), GS_THREADS, 0, st, gcnt_start, G, X,
-               status2, &small->ticket[2]);
-    TDT_LAUNCH(group_bases_plain_kernel, (unsigned)((G + 255) / 256), 256, 0, st, X, G, cluster_id, base1, base2,
-               cluster_id_io);
-    TDT_LAUNCH(final_labels_plain_kernel, grid_for(n, 256), 256, 0, st, k2, v2, ys, gcnt_start, base1, base2, bwB, n,
-               G - 1, labels_io);
-    int herr = 0;
-    TDT_CUDA(cudaMemcpyAsync(&herr, &small->err, 4, cudaMemcpyDeviceToHost, st));
+    return finish(b, st);
+}
+
+/* test hook: the segmented sort on its own (keys/vals/off are device arrays; nseg segments, n elements) */
+int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *off, int64_t nseg, int64_t n,
+                      int32_t key_bits, uint32_t *keys_out, int32_t *vals_out, void *ws, size_t ws_bytes, void *stream) {
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n <= 0 || nseg <= 0) return TDT_OK;
+    const size_t arr = al256((size_t)n * 4 + 256), tmp = al256(segsort_temp_bytes(n, nseg));
+    if (ws_bytes < 2 * arr + 512 + tmp)
+        return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, 2 * arr + 512 + tmp);
+    Arena ar(ws, ws_bytes);
+    u32 *tk = (u32 *)ar.take<char>(arr);
+    int32_t *tv = (int32_t *)ar.take<char>(arr);
+    Small *small = (Small *)ar.take<char>(256);
+    void *temp = ar.take<char>(tmp);
+    TDT_CUDA(cudaMemsetAsync(small, 0, 256, st));
+    TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &small->dims_x, n, nseg, (int64_t *)nullptr);
+    int rc = segsort_pairs(keys, vals, keys_out, vals_out, tk, tv, off, (const int64_t *)&small->dims_x, n, nseg,
+                           key_bits, temp, tmp, &small->err, st);
+    if (rc) return rc;
+    Small h;
+    TDT_CUDA(cudaMemcpyAsync(&h, small, sizeof(Small), cudaMemcpyDeviceToHost, st));
     TDT_CUDA(cudaStreamSynchronize(st));
-    return err_to_code(herr);
+    return h.err ? fail(TDT_E_RANGE, "a key has bits above key_bits") : TDT_OK;
 }
 
 }  // extern "C"

@@ -28,11 +28,10 @@ def check_min_pts(m, n):
 # ---------------------------------------------------------------------------------------------
 # clustering
 # ---------------------------------------------------------------------------------------------
-def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_out=None, pair_id=None):
+def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_out=None):
     """All (chrA,chrB) segments in one call; int32 CUDA tensors in, int32 CUDA labels (insertion order) out.
 
-    Replaces tiddit_cluster.pyx:140-160 + DBSCAN.py:125-129.  Exactly one of seg_off (int64, P+1) and
-    pair_id (int32, n) is given."""
+    Replaces tiddit_cluster.pyx:140-160 + DBSCAN.py:125-129.  seg_off: int64 CUDA tensor of P+1 offsets."""
     torch = _lib.torch_cuda()
     L = _lib.lib()
     n = int(posA.numel())
@@ -44,13 +43,8 @@ def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_
     need = L.tdt_cluster_workspace_bytes(n, int(P))
     ws = _lib.workspace(torch, need)
     st = _lib.stream_ptr(torch)
-    if pair_id is None:
-        rc = L.tdt_cluster_labels(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(seg_off), n, int(P), eps_to_int(epsilon),
-                                  int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws), ws.numel(), st)
-    else:
-        rc = L.tdt_cluster_labels_keyed(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(pair_id), n, int(P),
-                                        eps_to_int(epsilon), int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws),
-                                        ws.numel(), st)
+    rc = L.tdt_cluster_labels(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(seg_off), n, int(P), eps_to_int(epsilon),
+                              int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws), ws.numel(), st)
     _lib.check(rc)
     return labels_out
 
@@ -112,6 +106,23 @@ def ypass_device(y, epsilon, m, labels_io, cluster_id_io, max_pos=0):
                             _lib.ptr(cluster_id_io), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch))
     _lib.check(rc)
     return labels_io, cluster_id_io
+
+
+def segsort_device(keys, vals, off, key_bits):
+    """Test hook: every segment [off[s], off[s+1]) of (keys uint32-as-int32, vals int32 or None) sorted by key,
+    stable -> (keys_out, vals_out) CUDA tensors."""
+    torch = _lib.torch_cuda()
+    L = _lib.lib()
+    n, nseg = int(keys.numel()), int(off.numel()) - 1
+    ko = torch.empty_like(keys)
+    vo = torch.empty(n, dtype=torch.int32, device=keys.device)
+    if n == 0 or nseg <= 0:
+        return ko, vo
+    ws = _lib.workspace(torch, L.tdt_cluster_workspace_bytes(n, nseg))
+    rc = L.tdt_debug_segsort(_lib.ptr(keys), _lib.ptr(vals), _lib.ptr(off), nseg, n, int(key_bits), _lib.ptr(ko),
+                             _lib.ptr(vo), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return ko, vo
 
 
 # ---------------------------------------------------------------------------------------------
