@@ -113,11 +113,11 @@ TDT_API int tdt_gc_bins(const uint8_t *seq, int64_t len, int32_t bin_size, doubl
 
 /* Test hook: the segmented stable radix sort on its own.  keys/vals (vals may be NULL = element index) and
  * off[nseg+1] are device arrays; every segment [off[s], off[s+1]) is sorted by its low key_bits key bits into
- * keys_out/vals_out.  ws: at least 8*n + 1024 + the sort's temporaries (tdt_cluster_workspace_bytes(n, nseg) is
+ * keys_out/vals_out.  segid (may be NULL): segment of every element, enables the counting path for tiny segments.  ws: at least 8*n + 1024 + the sort's temporaries (tdt_cluster_workspace_bytes(n, nseg) is
  * enough).  Synchronises. */
-TDT_API int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *off, int64_t nseg, int64_t n,
-                              int32_t key_bits, uint32_t *keys_out, int32_t *vals_out, void *ws, size_t ws_bytes,
-                              void *stream);
+TDT_API int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *off, const int32_t *segid,
+                              int64_t nseg, int64_t n, int32_t key_bits, uint32_t *keys_out, int32_t *vals_out,
+                              void *ws, size_t ws_bytes, void *stream);
 
 /* Per-stage device timing for bench.py's roofline line: between tdt_profile_begin() and tdt_profile_end()
  * every stage of every call is bracketed by CUDA events on the caller's stream; tdt_profile_end synchronises

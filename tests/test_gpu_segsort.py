@@ -15,13 +15,17 @@ def _expect(keys, vals, off):
     return ko, vo
 
 
-def _run(keys, vals, off, key_bits):
+def _run(keys, vals, off, key_bits, with_segid=False):
     import torch
     from tiddit_b200 import device_ops
     k = torch.from_numpy(keys.astype(np.int64).astype(np.uint32).view(np.int32)).cuda()
     v = torch.from_numpy(vals).cuda() if vals is not None else None
-    o = torch.from_numpy(np.asarray(off, dtype=np.int64)).cuda()
-    ko, vo = device_ops.segsort_device(k, v, o, key_bits)
+    off = np.asarray(off, dtype=np.int64)
+    o = torch.from_numpy(off).cuda()
+    sid = None
+    if with_segid:   # per-element segment index: switches the counting path for segments of <= 32 elements on
+        sid = torch.from_numpy(np.repeat(np.arange(len(off) - 1, dtype=np.int32), np.diff(off))).cuda()
+    ko, vo = device_ops.segsort_device(k, v, o, key_bits, sid)
     return ko.cpu().numpy().view(np.uint32), vo.cpu().numpy()
 
 
@@ -42,21 +46,22 @@ def test_segsort_matches_numpy(sizes, key_bits, ties):
     got_k, got_v = _run(keys, vals, off, key_bits)
     assert np.array_equal(got_k, want_k)
     assert np.array_equal(got_v, want_v)
-    # vals = None -> element index
-    got_k2, got_v2 = _run(keys, None, off, key_bits)
+    # vals = None -> element index; with a segment-id array (tiny segments take the counting path)
+    got_k2, got_v2 = _run(keys, None, off, key_bits, with_segid=True)
     want_k2, want_v2 = _expect(keys, np.arange(n, dtype=np.int32), off)
     assert np.array_equal(got_k2, want_k2) and np.array_equal(got_v2, want_v2)
 
 
 def test_segsort_many_tiny_and_huge_mix():
     rng = np.random.default_rng(9)
-    sizes = np.concatenate([rng.integers(0, 12, 400_000), [3_000_000], rng.integers(0, 5000, 300)])
+    sizes = np.concatenate([rng.integers(0, 12, 400_000), rng.integers(20, 80, 20_000), [3_000_000],
+                            rng.integers(0, 5000, 300)])
     rng.shuffle(sizes)
     off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
     n = int(off[-1])
     keys = rng.integers(0, 250_000_000, n, dtype=np.int64).astype(np.uint32)
     vals = np.arange(n, dtype=np.int32)
-    got_k, got_v = _run(keys, vals, off, 28)
+    got_k, got_v = _run(keys, vals, off, 28, with_segid=True)
     # check by properties (a python loop over 400k segments is slow): sorted inside segments, stable, a permutation
     seg = np.repeat(np.arange(len(sizes)), sizes)
     order = np.lexsort((vals, keys, seg))

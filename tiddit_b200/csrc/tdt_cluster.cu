@@ -45,9 +45,8 @@ struct WRParams {
     const u32 *heads;     // bit j set <=> j is the first element of a segment; zero beyond n
     const Dims *dims;     // dims->n = number of elements
     int m;                // min_pts
-    u64 eps;              // 0: nothing is ever within eps
+    u32 eps;              // 0: nothing is ever within eps
     u64 *status;          // look-back tile states, zeroed
-    u32 *ticket;          // tile ticket, zeroed
     u32 *stw;             // out: run-start bits      (one word per 32 elements)
     u32 *cvw;             // out: "labelled" bits
     u32 *tile_pref;       // out: [tile][2] = run starts before the tile, second sum before the tile
@@ -97,7 +96,6 @@ template <int MODE, bool GENERAL>
 __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams p) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ int s_tile;
     __shared__ u32 s_pref[4];  // exS, exC, aggS, aggC
 
     const int m = p.m;
@@ -117,18 +115,16 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
     const int warp = threadIdx.x >> 5;
     const int64_t n = p.dims->n;
 
-    if (threadIdx.x == 0) {
-        s_tile = (int)atomicAdd(p.ticket, 1u);
-        mbar_init(&mbar, 1);
-        fence_mbar_init();
-    }
-    __syncthreads();
-    const int tile = s_tile;
+    // Tiles are taken in blockIdx order: the look-back below waits only on tiles with a smaller index, which
+    // the hardware has already scheduled (the forward-progress assumption CUB's DeviceScan makes as well).
+    const int tile = blockIdx.x;
     const int64_t tile_base = (int64_t)tile * WR_TILE;
     if (tile_base >= n) return;               // grids are sized by an upper bound of n
     const int64_t ext_base = tile_base - HL;  // global index of shared position 0
 
     if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
         const int64_t n_pad = (n + 3) & ~(int64_t)3;
         const int64_t jlo = ext_base < 0 ? 0 : ext_base;
         int64_t jhi = tile_base + WR_TILE + HR;
@@ -154,13 +150,25 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
     mbar_wait(&mbar, 0);
 
     // ---- phase 1: one ballot word per 32 windows -------------------------------------------
+    const u32 mask_m = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);             // heads in (e, e+m]
+    const u32 mask_m1 = m - 1 >= 32 ? 0xffffffffu : ((1u << (m - 1)) - 1u);  // heads in (e, e+m-1]
     for (int w = warp; w < EXT / 32; w += WR_WARPS) {
         const int e = w * 32 + lane;
         const int64_t j = ext_base + e;
         bool ok = false;
         if (j >= 0 && j + m - 1 < n) {
             const u32 kj = keys_s[e];
-            if (GENERAL) {
+            if (!GENERAL && m <= 32) {
+                // head bits of positions e+1 .. e+32 in one funnel shift of two head words
+                const u32 hb = lane == 31 ? hw[w + 1] : __funnelshift_r(hw[w], hw[w + 1], lane + 1);
+                if (MODE == MODE_Y) {
+                    ok = !(hb & mask_m1) && (keys_s[e + m - 1] - kj < p.eps);
+                } else if (j + m < n && !(hb & mask_m)) {
+                    ok = keys_s[e + m] - kj < p.eps;
+                } else {
+                    ok = !(hb & mask_m1) && (keys_s[e + m - 1] - kj < p.eps);
+                }
+            } else if (GENERAL) {
                 // DBSCAN.py:44-51 literally: max |x[i+d] - x[i]| over the next m elements (cut at n); one segment
                 const int64_t left = n - 1 - j;
                 const int cnt = left < (int64_t)m ? (int)left : m;
@@ -170,14 +178,14 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
                     const u32 dd = kt > kj ? kt - kj : kj - kt;
                     dmax = dd > dmax ? dd : dmax;
                 }
-                ok = (u64)dmax < p.eps;
+                ok = dmax < p.eps;
             } else if (MODE == MODE_Y) {
-                ok = !any_head(hw, e + 1, e + m - 1) && ((u64)(keys_s[e + m - 1] - kj) < p.eps);
+                ok = !any_head(hw, e + 1, e + m - 1) && (keys_s[e + m - 1] - kj < p.eps);
             } else {
                 if (j + m < n && !any_head(hw, e + 1, e + m)) {
-                    ok = (u64)(keys_s[e + m] - kj) < p.eps;
+                    ok = keys_s[e + m] - kj < p.eps;
                 } else {
-                    ok = !any_head(hw, e + 1, e + m - 1) && ((u64)(keys_s[e + m - 1] - kj) < p.eps);
+                    ok = !any_head(hw, e + 1, e + m - 1) && (keys_s[e + m - 1] - kj < p.eps);
                 }
             }
         }
@@ -813,8 +821,8 @@ static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, 
     const int64_t gmax = PLAIN ? (int64_t)plain_cluster_id + 1 : pl.gmax;
     {
         ProfScope ps("sort_y", st);
-        int rc = segsort_pairs(b.ykey, b.yval, b.xs, b.xv, b.tmpK, b.tmpV, b.goff, (const int64_t *)&b.small->dims_y, n,
-                               gmax, key_bits, b.sort_temp, pl.sort, &b.small->err, st);
+        int rc = segsort_pairs(b.ykey, b.yval, b.xs, b.xv, b.tmpK, b.tmpV, b.goff, (const int64_t *)&b.small->dims_y,
+                               b.gx, n, gmax, key_bits, b.sort_temp, pl.sort, &b.small->err, st);
         if (rc) return rc;
         TDT_LAUNCH(heads_from_offsets_kernel, (unsigned)((gmax + 255) / 256), 256, 0, st, b.goff, &b.small->dims_y,
                    b.headsY);
@@ -824,9 +832,8 @@ static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, 
     p.heads = b.headsY;
     p.dims = &b.small->dims_y;
     p.m = m;
-    p.eps = eps > 0 ? (u64)eps : 0;
+    p.eps = eps > 0 ? (u32)eps : 0u;
     p.status = b.statusY;
-    p.ticket = &b.small->ticket[1];
     p.stw = b.stwY;
     p.cvw = b.cvwY;
     p.tile_pref = b.tprefY;
@@ -891,8 +898,8 @@ static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t 
         ProfScope ps("sort_x", st);
         // posA as unsigned keys: a negative coordinate has bit 31 set and trips the key-range check
         int rc = segsort_pairs((const u32 *)posA, nullptr, b.xs, b.xv, b.tmpK, b.tmpV, seg_off,
-                               (const int64_t *)&b.small->dims_x, n, P, key_bits, b.sort_temp, pl.sort, &b.small->err,
-                               st);
+                               (const int64_t *)&b.small->dims_x, nullptr, n, P, key_bits, b.sort_temp, pl.sort,
+                               &b.small->err, st);
         if (rc) return rc;
         xv = b.xv;
     }
@@ -903,9 +910,8 @@ static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t 
     p.heads = b.headsX;
     p.dims = &b.small->dims_x;
     p.m = m;
-    p.eps = eps > 0 ? (u64)eps : 0;
+    p.eps = eps > 0 ? (u32)eps : 0u;
     p.status = b.statusX;
-    p.ticket = &b.small->ticket[0];
     p.stw = b.stwX;
     p.cvw = b.cvwX;
     p.tile_pref = b.tprefX;
@@ -1000,9 +1006,8 @@ int tdt_xpass_labels(const int32_t *x, int64_t n, int32_t eps, int32_t min_pts, 
     p.heads = b.headsX;
     p.dims = &b.small->dims_x;
     p.m = min_pts;
-    p.eps = eps > 0 ? (u64)eps : 0;
+    p.eps = eps > 0 ? (u32)eps : 0u;
     p.status = b.statusX;
-    p.ticket = &b.small->ticket[0];
     p.stw = b.stwX;
     p.cvw = b.cvwX;
     p.tile_pref = b.tprefX;
@@ -1041,8 +1046,9 @@ int tdt_ypass_labels(const int32_t *y, int64_t n, int32_t eps, int32_t min_pts, 
     TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &b.small->dims_x, n, (int64_t)1, b.small->off2);
     // 1. group the elements by id (stable): one segment, keys = id
     TDT_LAUNCH(ypass_label_keys_kernel, grid_for(n, 256), 256, 0, st, labels_io, n, cluster_id, b.ykey, &b.small->err);
-    rc = segsort_pairs(b.ykey, nullptr, b.xs, b.xv, b.tmpK, b.tmpV, b.small->off2, (const int64_t *)&b.small->dims_x, n,
-                       1, bit_width_u32((uint32_t)(cluster_id + 1)), b.sort_temp, pl.sort, &b.small->err, st);
+    rc = segsort_pairs(b.ykey, nullptr, b.xs, b.xv, b.tmpK, b.tmpV, b.small->off2, (const int64_t *)&b.small->dims_x,
+                       nullptr, n, 1, bit_width_u32((uint32_t)(cluster_id + 1)), b.sort_temp, pl.sort, &b.small->err,
+                       st);
     if (rc) return rc;
     // 2. offsets per id, y gathered; the noise block (last) is left out of everything that follows
     TDT_LAUNCH(ypass_offsets_kernel, grid_for(n, 256), 256, 0, st, b.xs, b.xv, n, y, max_pos, b.goff, b.ykey, b.gx,
@@ -1060,8 +1066,9 @@ int tdt_ypass_labels(const int32_t *y, int64_t n, int32_t eps, int32_t min_pts, 
 }
 
 /* test hook: the segmented sort on its own (keys/vals/off are device arrays; nseg segments, n elements) */
-int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *off, int64_t nseg, int64_t n,
-                      int32_t key_bits, uint32_t *keys_out, int32_t *vals_out, void *ws, size_t ws_bytes, void *stream) {
+int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *off, const int32_t *segid, int64_t nseg,
+                      int64_t n, int32_t key_bits, uint32_t *keys_out, int32_t *vals_out, void *ws, size_t ws_bytes,
+                      void *stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (n <= 0 || nseg <= 0) return TDT_OK;
     const size_t arr = al256((size_t)n * 4 + 256), tmp = al256(segsort_temp_bytes(n, nseg));
@@ -1074,7 +1081,7 @@ int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *
     void *temp = ar.take<char>(tmp);
     TDT_CUDA(cudaMemsetAsync(small, 0, 256, st));
     TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &small->dims_x, n, nseg, (int64_t *)nullptr);
-    int rc = segsort_pairs(keys, vals, keys_out, vals_out, tk, tv, off, (const int64_t *)&small->dims_x, n, nseg,
+    int rc = segsort_pairs(keys, vals, keys_out, vals_out, tk, tv, off, (const int64_t *)&small->dims_x, segid, n, nseg,
                            key_bits, temp, tmp, &small->err, st);
     if (rc) return rc;
     Small h;

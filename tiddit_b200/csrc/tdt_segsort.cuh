@@ -4,29 +4,35 @@
 // (chrA,chrB) pair (tiddit_cluster.pyx:152) and x-cluster members by posB inside every x-cluster
 // (DBSCAN.py:79-81).  Because the segment is implicit in the position (segment s owns
 // [off[s], off[s+1]) before and after the sort) the keys stay 32 bits -- the coordinate alone -- instead of
-// the 64-bit (segment, coordinate) composites a flat device-wide sort needs.
+// the 64-bit (segment, coordinate) composites a flat device-wide sort needs.  Three size classes:
 //
-//   small segments (<= SS_LOCAL_MAX elements; nearly all x-clusters): CTA k takes the segments that START in
-//       element window [k*W, (k+1)*W) -- at most W-1+LOCAL_MAX contiguous elements -- and sorts them together
-//       in shared memory by (local segment index, key): LSD passes over the key digits, then over the
-//       segment index, one global read and one global write per element;
-//   large segments: onesweep-style passes over 4096-element tiles that never straddle a segment: digit
-//       histograms of all passes up front, then per pass a stable in-tile ranking, a per-digit decoupled
-//       look-back over the EARLIER TILES OF THE SAME SEGMENT and a digit-ordered write through shared memory.
+//   tiny   (<= tiny_max elements, only when the caller has a per-element segment id; nearly all x-clusters):
+//          one thread per element counts the members of its segment that precede it -- no shared memory;
+//   small  (<= SS_LOCAL_MAX): CTA k gathers the small segments that START in element window [k*W, (k+1)*W)
+//          into shared memory and sorts them together by (local segment index, key) with 8-bit LSD passes:
+//          one global read and one global write per element;
+//   large  : onesweep-style passes over 4096-element tiles that never straddle a segment: digit histograms
+//          of all passes up front, then per pass a stable in-tile ranking, a per-digit decoupled look-back
+//          over the EARLIER TILES OF THE SAME SEGMENT and a digit-ordered write through shared memory.
 //
-// Stable ranking (both paths): a warp owns a contiguous run of the tile and walks it 32 elements at a time;
-// __match_any_sync groups equal digits, the lowest lane of a group bumps the warp-private digit counter.
+// Stable ranking (small + large): a warp owns a contiguous run of the tile and walks it 32 elements at a time;
+// lanes with equal digits find each other through a shared-memory atomicOr of their lane bits, the lowest
+// lane of a group bumps the warp-private digit counter.
 #pragma once
 #include "tdt_common.cuh"
 
 namespace tdt {
 
-constexpr int SS_THREADS = 256;
+constexpr int SS_THREADS = 256;            // large-segment kernels
 constexpr int SS_WARPS = SS_THREADS / 32;
-constexpr int SS_LOCAL_MAX = 2048;
-constexpr int SS_WINDOW = 2048;
-constexpr int SS_LOCAL_CAP = 4096;  // >= SS_WINDOW - 1 + SS_LOCAL_MAX
 constexpr int SS_TILE = 4096;
+constexpr int SS_CHUNKS = SS_TILE / SS_THREADS;  // 32-element chunks per warp per tile
+constexpr int SS_LTHREADS = 512;           // small-segment kernel
+constexpr int SS_LWARPS = SS_LTHREADS / 32;
+constexpr int SS_LOCAL_MAX = 2048;
+constexpr int SS_WINDOW = 1024;
+constexpr int SS_LOCAL_CAP = 3072;         // >= SS_WINDOW - 1 + SS_LOCAL_MAX
+constexpr int SS_LCHUNKS = SS_LOCAL_CAP / SS_LTHREADS;
 constexpr int SS_MAX_PASSES = 4;
 constexpr int SS_ERR_KEY_RANGE = 1;
 
@@ -37,8 +43,7 @@ struct SSLarge {
 
 struct SSCounters {
     int32_t n_large, n_tiles;
-    uint32_t ticket[SS_MAX_PASSES];
-    int32_t pad[2];
+    int32_t pad[6];
 };
 
 struct SSLayout {  // carved out of the caller's temp storage
@@ -46,10 +51,11 @@ struct SSLayout {  // carved out of the caller's temp storage
     SSLarge *large;
     int32_t *tile_seg;
     int32_t *win_lo, *win_hi;
+    uint32_t *win_cnt;  // elements of the small segments starting in the window
     uint32_t *ghist;   // [n_large][SS_MAX_PASSES][256]
     uint32_t *status;  // [n_tiles][256]
     int64_t nlarge_max, tiles_max, nwin;
-    size_t zero_bytes;  // leading region (counters + windows + status) that one memset initialises
+    size_t zero_bytes;  // leading region (counters + status) that one memset initialises
 };
 
 static inline size_t ss_align(size_t b) { return (b + 255) & ~(size_t)255; }
@@ -64,7 +70,7 @@ static inline size_t segsort_temp_bytes(int64_t n, int64_t nseg_max) {
     const int64_t tiles = n / SS_TILE + nl + 1;
     const int64_t nwin = (n + SS_WINDOW - 1) / SS_WINDOW + 1;
     return ss_align(sizeof(SSCounters)) + ss_align((size_t)nl * sizeof(SSLarge)) + ss_align((size_t)tiles * 4) +
-           2 * ss_align((size_t)nwin * 4) + ss_align((size_t)nl * SS_MAX_PASSES * 256 * 4) +
+           3 * ss_align((size_t)nwin * 4) + ss_align((size_t)nl * SS_MAX_PASSES * 256 * 4) +
            ss_align((size_t)tiles * 256 * 4) + 1024;
 }
 
@@ -78,7 +84,9 @@ static inline SSLayout ss_layout(void *temp, int64_t n, int64_t nseg_max) {
     p += ss_align(sizeof(SSCounters));
     L.status = (uint32_t *)p;
     p += ss_align((size_t)L.tiles_max * 256 * 4);
-    L.win_hi = (int32_t *)p;  // 0xff.. = -1 : "no segment starts here"
+    L.win_cnt = (uint32_t *)p;
+    p += ss_align((size_t)L.nwin * 4);
+    L.win_hi = (int32_t *)p;  // 0xff.. = -1 : "no small segment starts here"
     p += ss_align((size_t)L.nwin * 4);
     L.win_lo = (int32_t *)p;  // 0x7f.. : +inf
     p += ss_align((size_t)L.nwin * 4);
@@ -87,7 +95,7 @@ static inline SSLayout ss_layout(void *temp, int64_t n, int64_t nseg_max) {
     L.tile_seg = (int32_t *)p;
     p += ss_align((size_t)L.tiles_max * 4);
     L.ghist = (uint32_t *)p;
-    L.zero_bytes = (size_t)((char *)L.win_hi - (char *)temp);
+    L.zero_bytes = (size_t)((char *)L.win_hi - (char *)temp);  // counters, status, win_cnt
     return L;
 }
 
@@ -98,8 +106,10 @@ struct SSArgs {
     int32_t *vals_out;
     uint32_t *keys_tmp;
     int32_t *vals_tmp;
-    const int64_t *off;   // [nseg + 1], device
-    const int64_t *dims;  // device: dims[0] = n, dims[1] = nseg (actual values; the grids use upper bounds)
+    const int64_t *off;    // [nseg + 1], device
+    const int64_t *dims;   // device: dims[0] = n, dims[1] = nseg (actual values; the grids use upper bounds)
+    const int32_t *segid;  // optional: segment of every element (enables the tiny-segment path)
+    int tiny_max;          // segments up to this size go through the tiny path (0 without segid)
     int key_bits, n_passes, bits_per_pass;
     SSLayout L;
     int *err;
@@ -113,12 +123,25 @@ __device__ __forceinline__ uint32_t ss_digit(uint32_t key, int pass, int bits) {
 __global__ void segsort_classify_kernel(SSArgs a) {
     const int64_t nseg = a.dims[1];
     const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= nseg) return;
-    const int64_t q = a.off[s], size = a.off[s + 1] - q;
-    if (size <= 0) return;
-    const int64_t k = q / SS_WINDOW;
-    atomicMin(a.L.win_lo + k, (int32_t)s);
-    atomicMax(a.L.win_hi + k, (int32_t)s);
+    const int lane = threadIdx.x & 31;
+    int64_t q = 0, size = 0;
+    if (s < nseg) {
+        q = a.off[s];
+        size = a.off[s + 1] - q;
+    }
+    const bool small = size > a.tiny_max && size <= SS_LOCAL_MAX;
+    // consecutive segments mostly start in the same window: one atomic pair per group of lanes
+    const uint32_t act = __ballot_sync(0xffffffffu, small);
+    if (small) {
+        const int64_t k = q / SS_WINDOW;
+        const uint32_t peers = __match_any_sync(act, k);
+        const uint32_t total = __reduce_add_sync(peers, (uint32_t)size);
+        if ((peers & lanemask_lt()) == 0u) {
+            atomicMin(a.L.win_lo + k, (int32_t)s);
+            atomicAdd(a.L.win_cnt + k, total);
+        }
+        if ((peers >> lane) == 1u) atomicMax(a.L.win_hi + k, (int32_t)s);
+    }
     if (size > SS_LOCAL_MAX) {
         const int32_t idx = atomicAdd(&a.L.cnt->n_large, 1);
         const int32_t nt = (int32_t)((size + SS_TILE - 1) / SS_TILE);
@@ -129,24 +152,104 @@ __global__ void segsort_classify_kernel(SSArgs a) {
         rec.tile_base = tb;
         rec.pad = 0;
         a.L.large[idx] = rec;
-        for (int32_t t = 0; t < nt; t++) a.L.tile_seg[tb + t] = idx;
-        uint32_t *h = a.L.ghist + (size_t)idx * SS_MAX_PASSES * 256;
-        for (int i = 0; i < SS_MAX_PASSES * 256; i++) h[i] = 0u;
     }
 }
 
-// ---- one stable LSD pass over `count` elements held in shared memory ---------------------------------
-// cur -> alt; the digit comes from the key (use_lid false) or from the local segment index (true).
-struct SSLocalBufs {
-    uint32_t *K[2];
-    int32_t *V[2];
-    uint16_t *Lid[2];
-    uint32_t (*wh)[256];  // [SS_WARPS][256]
-    uint32_t *bin;        // [256] scratch for the digit scan
-};
+// one CTA per large segment: its tile -> segment entries and its zeroed digit histograms
+__global__ void __launch_bounds__(256) segsort_fill_kernel(SSArgs a) {
+    const int idx = blockIdx.x;
+    if (idx >= a.L.cnt->n_large) return;
+    const SSLarge L = a.L.large[idx];
+    const int32_t nt = (int32_t)((L.size + SS_TILE - 1) / SS_TILE);
+    for (int32_t t = threadIdx.x; t < nt; t += 256) a.L.tile_seg[L.tile_base + t] = idx;
+    uint32_t *h = a.L.ghist + (size_t)idx * SS_MAX_PASSES * 256;
+    for (int i = threadIdx.x; i < SS_MAX_PASSES * 256; i += 256) h[i] = 0u;
+}
 
+// ---- tiny segments: rank by counting ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) segsort_tiny_kernel(SSArgs a) {
+    const int64_t n = a.dims[0];
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n; j += stride) {
+        const int64_t g = a.segid[j];
+        const int64_t s0 = a.off[g], s1 = a.off[g + 1];
+        if (s1 - s0 > a.tiny_max) continue;
+        const uint32_t key = a.keys_in[j];
+        if (a.key_bits < 32 && (key >> a.key_bits)) atomicMax(a.err, SS_ERR_KEY_RANGE);
+        int rank = 0;
+        for (int64_t i = s0; i < s1; i++) {
+            const uint32_t other = a.keys_in[i];
+            rank += (other < key) || (other == key && i < j);
+        }
+        a.keys_out[s0 + rank] = key;
+        a.vals_out[s0 + rank] = a.vals_in ? a.vals_in[j] : (int32_t)j;
+    }
+}
+
+// ---- stable ranking primitives ------------------------------------------------------------------------
+// lanes holding the same digit: every lane ORs its bit into the warp's mask word of that digit
+// (mm: this warp's 256 words, all zero on entry and on exit)
+__device__ __forceinline__ uint32_t ss_match(uint32_t *mm, uint32_t d, bool valid) {
+    const int lane = threadIdx.x & 31;
+    if (valid) atomicOr(&mm[d], 1u << lane);
+    __syncwarp();
+    const uint32_t peers = valid ? mm[d] : 0u;
+    __syncwarp();
+    if (valid && (peers & lanemask_lt()) == 0u) mm[d] = 0u;
+    return peers;
+}
+
+// info word per element: [7:0] digit, [12:8] rank among the chunk's lanes with the same digit,
+// [18:13] size of that group, [31] valid
+__device__ __forceinline__ uint32_t ss_info(uint32_t d, uint32_t peers) {
+    return d | ((uint32_t)__popc(peers & lanemask_lt()) << 8) | ((uint32_t)__popc(peers) << 13) | 0x80000000u;
+}
+
+// count phase: warp-private digit histograms of the warp's own run of the tile; info[] keeps the match result
+template <int CHUNKS, typename DigitFn>
+__device__ __forceinline__ void ss_count(int count, int epw, uint32_t *wh, uint32_t *mm, uint32_t (&info)[CHUNKS],
+                                         DigitFn digit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; c++) {
+        info[c] = 0u;
+        if (c * 32 < epw) {
+            const int e = warp * epw + c * 32 + lane;
+            const bool valid = e < count;
+            const uint32_t d = valid ? digit(e, c) : 0u;
+            const uint32_t peers = ss_match(mm, d, valid);
+            if (valid) {
+                info[c] = ss_info(d, peers);
+                if ((peers & lanemask_lt()) == 0u) wh[d] += __popc(peers);
+            }
+            __syncwarp();
+        }
+    }
+}
+
+// scatter phase: stable position of every element; wh[d] holds the running base of (this warp, digit)
+template <int CHUNKS, typename EmitFn>
+__device__ __forceinline__ void ss_scatter(int epw, uint32_t *wh, const uint32_t (&info)[CHUNKS], EmitFn emit) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int c = 0; c < CHUNKS; c++) {
+        if (c * 32 < epw) {
+            const uint32_t w = info[c];
+            const bool valid = w >> 31;
+            const uint32_t d = w & 255u, rank = (w >> 8) & 31u, group = (w >> 13) & 63u;
+            uint32_t base = 0;
+            if (valid) base = wh[d];
+            __syncwarp();
+            if (valid && rank == 0u) wh[d] = base + group;
+            __syncwarp();
+            if (valid) emit(warp * epw + c * 32 + lane, c, base + rank);
+        }
+    }
+}
+
+// exclusive scan of one value per thread over the first 256 threads (thread = digit); all threads of the CTA call it
+template <int NWARPS>
 __device__ __forceinline__ uint32_t ss_block_excl_scan_256(uint32_t v, uint32_t *scratch) {
-    // exclusive scan over the 256 threads of the CTA (thread = digit); scratch: >= 8 words
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     uint32_t inc = v;
 #pragma unroll
@@ -154,177 +257,194 @@ __device__ __forceinline__ uint32_t ss_block_excl_scan_256(uint32_t v, uint32_t 
         const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
         if (lane >= o) inc += t;
     }
-    if (lane == 31) scratch[warp] = inc;
+    if (lane == 31 && warp < 8) scratch[warp] = inc;
     __syncthreads();
     uint32_t wbase = 0;
 #pragma unroll
-    for (int w = 0; w < SS_WARPS; w++)
+    for (int w = 0; w < 8; w++)
         if (w < warp) wbase += scratch[w];
     __syncthreads();
     return wbase + inc - v;
 }
 
-// count phase: warp-private digit histograms of the warp's own run of the tile
-template <typename DigitFn>
-__device__ __forceinline__ void ss_count(int count, int epw, uint32_t (*wh)[256], DigitFn digit) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = 0; c < epw; c += 32) {
-        const int e = warp * epw + c + lane;
-        const bool valid = e < count;
-        const uint32_t d = valid ? digit(e) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        if (valid && lane == __ffs(peers) - 1) wh[warp][d] += __popc(peers);
-        __syncwarp();
-    }
-}
-
-// scatter phase: stable position of every element; wh[warp][d] holds the running base of (warp, digit)
-template <typename DigitFn, typename EmitFn>
-__device__ __forceinline__ void ss_scatter(int count, int epw, uint32_t (*wh)[256], DigitFn digit, EmitFn emit) {
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int c = 0; c < epw; c += 32) {
-        const int e = warp * epw + c + lane;
-        const bool valid = e < count;
-        const uint32_t d = valid ? digit(e) : 0xffffffffu;
-        const uint32_t peers = __match_any_sync(0xffffffffu, d);
-        uint32_t base = 0;
-        if (valid) base = wh[warp][d];
-        __syncwarp();
-        if (valid && lane == __ffs(peers) - 1) wh[warp][d] = base + __popc(peers);
-        __syncwarp();
-        if (valid) emit(e, base + __popc(peers & lanemask_lt()));
-    }
-}
-
-// turns the per-warp counts into running bases: wh[w][d] = (#elements with a smaller digit) + (#elements with
-// digit d in earlier warps); returns this thread's digit total and exclusive digit base
+// turns the per-warp counts wh[w][d] into running bases: (#elements with a smaller digit) + (#elements with
+// digit d in earlier warps); returns this thread's digit total and exclusive digit base (threads >= 256: 0)
+template <int NWARPS>
 __device__ __forceinline__ void ss_digit_bases(uint32_t (*wh)[256], uint32_t *scratch, uint32_t &total,
                                                uint32_t &excl) {
     const int d = threadIdx.x;
     uint32_t run = 0;
+    if (d < 256) {
 #pragma unroll
-    for (int w = 0; w < SS_WARPS; w++) {
-        const uint32_t t = wh[w][d];
-        wh[w][d] = run;
-        run += t;
+        for (int w = 0; w < NWARPS; w++) {
+            const uint32_t t = wh[w][d];
+            wh[w][d] = run;
+            run += t;
+        }
     }
     total = run;
-    excl = ss_block_excl_scan_256(run, scratch);
+    excl = ss_block_excl_scan_256<NWARPS>(run, scratch);
+    if (d < 256) {
 #pragma unroll
-    for (int w = 0; w < SS_WARPS; w++) wh[w][d] += excl;
+        for (int w = 0; w < NWARPS; w++) wh[w][d] += excl;
+    }
 }
 
-// ---- small segments: whole sort in shared memory ---------------------------------------------------
-constexpr size_t SS_LOCAL_SMEM = (size_t)SS_LOCAL_CAP * (4 + 4 + 2) * 2 + SS_WARPS * 256 * 4 + 256 * 4 + 128 * 4 + 64;
+// ---- small segments: gather, sort in shared memory, put back ----------------------------------------------
+// A CTA owns a contiguous span of element windows and walks it in BATCHES of consecutive windows whose small
+// segments together fill (at most) the shared-memory capacity, so the per-batch fixed costs are amortised.
+constexpr int SS_SCAN_WINDOWS = 512;  // windows examined per planning round
+constexpr int SS_BATCH_WINDOWS = 60;  // a batch spans < 2^16 element positions (16-bit relative starts)
+constexpr size_t SS_LOCAL_SMEM = (size_t)SS_LOCAL_CAP * (4 + 4 + 2) * 2 + (size_t)SS_LWARPS * 256 * 4 * 2 + 256 * 4 +
+                                 (size_t)(SS_LOCAL_CAP + 2) * 2 * 2 + SS_SCAN_WINDOWS * 4 + 64;
 
-__global__ void __launch_bounds__(SS_THREADS) segsort_local_kernel(SSArgs a) {
+__global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
-    SSLocalBufs B;
     unsigned char *p = ss_smem;
-    B.K[0] = (uint32_t *)p; p += SS_LOCAL_CAP * 4;
-    B.K[1] = (uint32_t *)p; p += SS_LOCAL_CAP * 4;
-    B.V[0] = (int32_t *)p; p += SS_LOCAL_CAP * 4;
-    B.V[1] = (int32_t *)p; p += SS_LOCAL_CAP * 4;
-    B.Lid[0] = (uint16_t *)p; p += SS_LOCAL_CAP * 2;
-    B.Lid[1] = (uint16_t *)p; p += SS_LOCAL_CAP * 2;
-    B.wh = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
-    B.bin = (uint32_t *)p; p += 256 * 4;
-    uint32_t *heads = (uint32_t *)p;  // [128] head bits, then reused as word prefixes
-    __shared__ int64_t s_range[2];
-    __shared__ int s_nheads;
+    uint32_t *K[2];
+    int32_t *V[2];
+    uint16_t *Lid[2];
+    K[0] = (uint32_t *)p; p += SS_LOCAL_CAP * 4;
+    K[1] = (uint32_t *)p; p += SS_LOCAL_CAP * 4;
+    V[0] = (int32_t *)p; p += SS_LOCAL_CAP * 4;
+    V[1] = (int32_t *)p; p += SS_LOCAL_CAP * 4;
+    Lid[0] = (uint16_t *)p; p += SS_LOCAL_CAP * 2;
+    Lid[1] = (uint16_t *)p; p += SS_LOCAL_CAP * 2;
+    uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += SS_LWARPS * 256 * 4;
+    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_LWARPS * 256 * 4;
+    uint32_t *bin = (uint32_t *)p; p += 256 * 4;
+    uint32_t *wcnt = (uint32_t *)p; p += SS_SCAN_WINDOWS * 4;
+    uint16_t *sc_start = (uint16_t *)p; p += (SS_LOCAL_CAP + 2) * 2;  // compact start of every gathered segment
+    uint16_t *sg_rel = (uint16_t *)p;                                 // its global start, relative to the batch
+    __shared__ uint32_t s_warp[SS_LWARPS];
+    __shared__ uint32_t s_carry;
+    __shared__ int s_batch[2];  // next batch: [first window, one past the last window) relative to the round
 
     const int64_t n = a.dims[0];
-    const int64_t k = blockIdx.x;
-    if (k * SS_WINDOW >= n) return;
-    const int32_t lo_s = a.L.win_lo[k], hi_s = a.L.win_hi[k];
-    if (hi_s < 0) return;  // no segment starts in this window
-    if (threadIdx.x == 0) {
-        const int64_t begin = a.off[lo_s];
-        const int64_t last_start = a.off[hi_s], last_end = a.off[hi_s + 1];
-        s_range[0] = begin;
-        s_range[1] = (last_end - last_start > SS_LOCAL_MAX) ? last_start : last_end;  // a large one is not ours
-    }
-    if (threadIdx.x < 128) heads[threadIdx.x] = 0u;
-    __syncthreads();
-    const int64_t begin = s_range[0], end = s_range[1];
-    const int count = (int)(end - begin);
-    if (count <= 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < SS_LWARPS * 256; i += SS_LTHREADS) (&mm[0][0])[i] = 0u;
 
-    for (int64_t s = (int64_t)lo_s + threadIdx.x; s <= hi_s; s += SS_THREADS) {
-        const int64_t q = a.off[s];
-        if (a.off[s + 1] > q && q < end) atomicOr(&heads[(q - begin) >> 5], 1u << ((q - begin) & 31));
-    }
-    for (int e = threadIdx.x; e < count; e += SS_THREADS) {
-        const uint32_t key = a.keys_in[begin + e];
-        if (a.key_bits < 32 && (key >> a.key_bits)) atomicMax(a.err, SS_ERR_KEY_RANGE);
-        B.K[0][e] = key;
-        B.V[0][e] = a.vals_in ? a.vals_in[begin + e] : (int32_t)(begin + e);
-    }
-    __syncthreads();
-    // local segment index = (#heads at or before e) - 1
-    if (threadIdx.x < 32) {
-        const int lane = threadIdx.x;
-        uint32_t c[4], t = 0;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            c[i] = __popc(heads[lane * 4 + i]);
-            t += c[i];
-        }
-        uint32_t inc = t;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
-            if (lane >= o) inc += u;
-        }
-        uint32_t ex = inc - t;
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            B.bin[lane * 4 + i] = ex;  // heads before word lane*4+i
-            ex += c[i];
-        }
-        if (lane == 31) s_nheads = (int)inc;
-    }
-    __syncthreads();
-    for (int e = threadIdx.x; e < count; e += SS_THREADS)
-        B.Lid[0][e] = (uint16_t)(B.bin[e >> 5] + __popc(heads[e >> 5] & (0xffffffffu >> (31 - (e & 31)))) - 1u);
-    const int nheads = s_nheads;
-    __syncthreads();
+    const int64_t nwin = (n + SS_WINDOW - 1) / SS_WINDOW;
+    const int64_t span = (nwin + gridDim.x - 1) / gridDim.x;
+    const int64_t span_lo = (int64_t)blockIdx.x * span;
+    const int64_t span_hi = span_lo + span < nwin ? span_lo + span : nwin;
 
-    const int epw = ((count + SS_THREADS - 1) / SS_THREADS) * 32;  // elements per warp, multiple of 32
-    int cur = 0;
-    const int lid_bits = nheads > 1 ? (32 - __clz(nheads - 1)) : 0;
-    const int lid_passes = (lid_bits + 7) / 8;
-    const int total_passes = a.n_passes + lid_passes;
-    for (int pass = 0; pass < total_passes; pass++) {
-        for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) (&B.wh[0][0])[i] = 0u;
+    for (int64_t round = span_lo; round < span_hi; round += SS_SCAN_WINDOWS) {
+        const int nround = (int)(span_hi - round < SS_SCAN_WINDOWS ? span_hi - round : SS_SCAN_WINDOWS);
         __syncthreads();
-        const bool on_lid = pass >= a.n_passes;
-        const uint32_t *Kc = B.K[cur];
-        const uint16_t *Lc = B.Lid[cur];
-        const int kp = pass, lp = pass - a.n_passes, bits = a.bits_per_pass;
-        auto digit = [&](int e) -> uint32_t {
-            return on_lid ? (((uint32_t)Lc[e] >> (8 * lp)) & 255u) : ss_digit(Kc[e], kp, bits);
-        };
-        ss_count(count, epw, B.wh, digit);
-        __syncthreads();
-        uint32_t total, excl;
-        ss_digit_bases(B.wh, B.bin, total, excl);
-        __syncthreads();
-        uint32_t *Ka = B.K[cur ^ 1];
-        int32_t *Va = B.V[cur ^ 1];
-        uint16_t *La = B.Lid[cur ^ 1];
-        const int32_t *Vc = B.V[cur];
-        ss_scatter(count, epw, B.wh, digit, [&](int e, uint32_t pos) {
-            Ka[pos] = Kc[e];
-            Va[pos] = Vc[e];
-            La[pos] = Lc[e];
-        });
-        __syncthreads();
-        cur ^= 1;
-    }
-    for (int e = threadIdx.x; e < count; e += SS_THREADS) {
-        a.keys_out[begin + e] = B.K[cur][e];
-        a.vals_out[begin + e] = B.V[cur][e];
+        if (threadIdx.x < nround) wcnt[threadIdx.x] = a.L.win_cnt[round + threadIdx.x];
+        int next = 0;
+        while (true) {
+            __syncthreads();
+            if (threadIdx.x == 0) {  // plan: skip empty windows, then take windows while they fit
+                int w = next;
+                while (w < nround && wcnt[w] == 0u) w++;
+                int e = w;
+                uint32_t sum = 0;
+                while (e < nround && e - w < SS_BATCH_WINDOWS && (wcnt[e] == 0u || sum + wcnt[e] <= SS_LOCAL_CAP)) {
+                    sum += wcnt[e];
+                    e++;
+                }
+                while (e > w && wcnt[e - 1] == 0u) e--;  // end on a populated window
+                s_batch[0] = w;
+                s_batch[1] = e;
+                s_carry = 0u;
+            }
+            __syncthreads();
+            const int bw0 = s_batch[0], bw1 = s_batch[1];
+            if (bw0 >= nround) break;
+            next = bw1;
+            const int64_t k0 = round + bw0, k1 = round + bw1;  // windows [k0, k1); both ends populated
+            const int32_t lo_s = a.L.win_lo[k0], hi_s = a.L.win_hi[k1 - 1];
+            const int64_t wbase = k0 * SS_WINDOW;
+            // ---- A: the small segments of the batch, their compact layout (size sum << 16 | count) ----
+            for (int64_t s0 = lo_s; s0 <= hi_s; s0 += SS_LTHREADS) {
+                const int64_t s = s0 + threadIdx.x;
+                uint32_t size = 0;
+                int64_t q = 0;
+                if (s <= hi_s) {
+                    q = a.off[s];
+                    const int64_t sz = a.off[s + 1] - q;
+                    if (sz > a.tiny_max && sz <= SS_LOCAL_MAX) size = (uint32_t)sz;
+                }
+                const uint32_t v = size ? ((size << 16) | 1u) : 0u;
+                uint32_t inc = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+                    if (lane >= o) inc += t;
+                }
+                if (lane == 31) s_warp[warp] = inc;
+                __syncthreads();
+                uint32_t before = s_carry;
+                for (int w = 0; w < warp; w++) before += s_warp[w];
+                const uint32_t ex = before + inc - v;
+                if (size) {
+                    sc_start[ex & 0xffffu] = (uint16_t)(ex >> 16);
+                    sg_rel[ex & 0xffffu] = (uint16_t)(q - wbase);
+                }
+                __syncthreads();
+                if (threadIdx.x == SS_LTHREADS - 1) s_carry = before + inc;
+                __syncthreads();
+            }
+            const uint32_t tot = s_carry;
+            const int nsegs = (int)(tot & 0xffffu), count = (int)(tot >> 16);
+            if (threadIdx.x == 0) sc_start[nsegs] = (uint16_t)count;
+            __syncthreads();
+            // ---- B: gather -------------------------------------------------------------------------------
+            for (int c = threadIdx.x; c < count; c += SS_LTHREADS) {
+                int lo = 0, hi = nsegs;  // segment of compact position c: largest i with sc_start[i] <= c
+                while (hi - lo > 1) {
+                    const int mid = (lo + hi) >> 1;
+                    if ((int)sc_start[mid] <= c) lo = mid; else hi = mid;
+                }
+                const int64_t g = wbase + sg_rel[lo] + (c - (int)sc_start[lo]);
+                const uint32_t key = a.keys_in[g];
+                if (a.key_bits < 32 && (key >> a.key_bits)) atomicMax(a.err, SS_ERR_KEY_RANGE);
+                K[0][c] = key;
+                V[0][c] = a.vals_in ? a.vals_in[g] : (int32_t)g;
+                Lid[0][c] = (uint16_t)lo;
+            }
+            // ---- C: LSD passes over the composite (segment index, key), 8 bits at a time -----------------
+            const int lid_bits = nsegs > 1 ? (32 - __clz(nsegs - 1)) : 0;
+            const int passes = (a.key_bits + lid_bits + 7) / 8;
+            const int epw = ((count + SS_LTHREADS - 1) / SS_LTHREADS) * 32;  // elements per warp, multiple of 32
+            int cur = 0;
+            for (int pass = 0; pass < passes; pass++) {
+                for (int i = threadIdx.x; i < SS_LWARPS * 256; i += SS_LTHREADS) (&wh[0][0])[i] = 0u;
+                __syncthreads();
+                const uint32_t *Kc = K[cur];
+                const int32_t *Vc = V[cur];
+                const uint16_t *Lc = Lid[cur];
+                const int kb = a.key_bits, sh = 8 * pass;
+                uint32_t info[SS_LCHUNKS];
+                ss_count<SS_LCHUNKS>(count, epw, wh[warp], mm[warp], info, [&](int e, int) -> uint32_t {
+                    const unsigned long long comp = ((unsigned long long)Lc[e] << kb) | (unsigned long long)Kc[e];
+                    return (uint32_t)(comp >> sh) & 255u;
+                });
+                __syncthreads();
+                uint32_t total, excl;
+                ss_digit_bases<SS_LWARPS>(wh, bin, total, excl);
+                __syncthreads();
+                uint32_t *Ka = K[cur ^ 1];
+                int32_t *Va = V[cur ^ 1];
+                uint16_t *La = Lid[cur ^ 1];
+                ss_scatter<SS_LCHUNKS>(epw, wh[warp], info, [&](int e, int, uint32_t pos) {
+                    Ka[pos] = Kc[e];
+                    Va[pos] = Vc[e];
+                    La[pos] = Lc[e];
+                });
+                __syncthreads();
+                cur ^= 1;
+            }
+            // ---- D: put back: sorted by (segment, key), so compact position c is rank c - start in its segment
+            for (int c = threadIdx.x; c < count; c += SS_LTHREADS) {
+                const int lid = Lid[cur][c];
+                const int64_t g = wbase + sg_rel[lid] + (c - (int)sc_start[lid]);
+                a.keys_out[g] = K[cur][c];
+                a.vals_out[g] = V[cur][c];
+            }
+        }
     }
 }
 
@@ -394,26 +514,28 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr size_t SS_PASS_SMEM = (size_t)SS_TILE * 4 * 4 + SS_WARPS * 256 * 4 + 256 * 4 + 256 * 8 + 64;
+constexpr size_t SS_PASS_SMEM = (size_t)SS_TILE * 4 * 2 + (size_t)SS_WARPS * 256 * 4 * 2 + 256 * 4 + 256 * 8 + 64;
 
+// One pass over one tile.  Tiles are taken in blockIdx order (the chained scan waits only on tiles with a smaller
+// index, which the hardware has already scheduled -- the same forward-progress assumption as CUB's DeviceScan).
 __global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int pass, const uint32_t *src_k,
                                                                   const int32_t *src_v, uint32_t *dst_k,
                                                                   int32_t *dst_v) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     unsigned char *p = ss_smem;
-    uint32_t *K = (uint32_t *)p; p += SS_TILE * 4;
-    int32_t *V = (int32_t *)p; p += SS_TILE * 4;
     uint32_t *K2 = (uint32_t *)p; p += SS_TILE * 4;
     int32_t *V2 = (int32_t *)p; p += SS_TILE * 4;
     uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
+    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
     uint32_t *bin = (uint32_t *)p; p += 256 * 4;
     int64_t *gbase = (int64_t *)p;
-    __shared__ int s_tile;
 
-    if (threadIdx.x == 0) s_tile = (int)atomicAdd(&a.L.cnt->ticket[pass], 1u);
-    __syncthreads();
-    const int tile = s_tile;
+    const int tile = blockIdx.x;
     if (tile >= a.L.cnt->n_tiles) return;
+    for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) {
+        (&wh[0][0])[i] = 0u;
+        (&mm[0][0])[i] = 0u;
+    }
     const int seg = a.L.tile_seg[tile];
     const SSLarge L = a.L.large[seg];
     const int lt = tile - L.tile_base;
@@ -421,19 +543,28 @@ __global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int 
     const int64_t rem = L.start + L.size - t0;
     const int cnt = rem < SS_TILE ? (int)rem : SS_TILE;
     const int bits = a.bits_per_pass;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr int epw = SS_TILE / SS_WARPS;  // every warp owns 512 consecutive elements of the tile
 
-    for (int e = threadIdx.x; e < cnt; e += SS_THREADS) {
-        K[e] = src_k[t0 + e];
-        V[e] = src_v ? src_v[t0 + e] : (int32_t)(t0 + e);
+    uint32_t key[SS_CHUNKS];
+    int32_t val[SS_CHUNKS];
+#pragma unroll
+    for (int c = 0; c < SS_CHUNKS; c++) {
+        const int e = warp * epw + c * 32 + lane;
+        key[c] = 0u;
+        val[c] = 0;
+        if (e < cnt) {
+            key[c] = src_k[t0 + e];
+            val[c] = src_v ? src_v[t0 + e] : (int32_t)(t0 + e);
+        }
     }
-    for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) (&wh[0][0])[i] = 0u;
     __syncthreads();
-    const int epw = ((cnt + SS_THREADS - 1) / SS_THREADS) * 32;
-    auto digit = [&](int e) -> uint32_t { return ss_digit(K[e], pass, bits); };
-    ss_count(cnt, epw, wh, digit);
+    uint32_t info[SS_CHUNKS];
+    ss_count<SS_CHUNKS>(cnt, epw, wh[warp], mm[warp], info,
+                        [&](int, int c) -> uint32_t { return ss_digit(key[c], pass, bits); });
     __syncthreads();
     uint32_t total, excl;
-    ss_digit_bases(wh, bin, total, excl);
+    ss_digit_bases<SS_WARPS>(wh, bin, total, excl);
     {   // per-digit chained scan over the earlier tiles of this segment (thread = digit)
         const int d = threadIdx.x;
         const uint32_t epoch = (uint32_t)pass + 1u;
@@ -458,15 +589,15 @@ __global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int 
         gbase[d] = L.start + (int64_t)gh + (int64_t)before - (int64_t)excl;
     }
     __syncthreads();
-    ss_scatter(cnt, epw, wh, digit, [&](int e, uint32_t pos) {
-        K2[pos] = K[e];
-        V2[pos] = V[e];
+    ss_scatter<SS_CHUNKS>(epw, wh[warp], info, [&](int, int c, uint32_t pos) {
+        K2[pos] = key[c];
+        V2[pos] = val[c];
     });
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += SS_THREADS) {
-        const uint32_t key = K2[i];
-        const int64_t g = gbase[ss_digit(key, pass, bits)] + i;
-        dst_k[g] = key;
+        const uint32_t k = K2[i];
+        const int64_t g = gbase[ss_digit(k, pass, bits)] + i;
+        dst_k[g] = k;
         dst_v[g] = V2[i];
     }
 }
@@ -475,9 +606,11 @@ __global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int 
 // Sorts every segment [off[s], off[s+1]) of keys_in/vals_in by key (stable) into keys_out/vals_out.
 // n_max / nseg_max: host-side upper bounds that size the grids; the actual n / nseg are read on the device
 // from dims[0] / dims[1].  keys_tmp / vals_tmp: scratch of n_max elements (only touched for large segments).
+// segid (optional): segment index of every element; enables the counting path for segments of <= 32 elements.
 static int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *keys_out, int32_t *vals_out,
-                         uint32_t *keys_tmp, int32_t *vals_tmp, const int64_t *off, const int64_t *dims, int64_t n_max,
-                         int64_t nseg_max, int key_bits, void *temp, size_t temp_bytes, int *err, cudaStream_t st) {
+                         uint32_t *keys_tmp, int32_t *vals_tmp, const int64_t *off, const int64_t *dims,
+                         const int32_t *segid, int64_t n_max, int64_t nseg_max, int key_bits, void *temp,
+                         size_t temp_bytes, int *err, cudaStream_t st) {
     if (n_max <= 0 || nseg_max <= 0) return TDT_OK;
     if (temp_bytes < segsort_temp_bytes(n_max, nseg_max))
         return fail(TDT_E_WORKSPACE, "segmented sort needs %zu bytes of temporary storage, %zu reserved",
@@ -493,6 +626,8 @@ static int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32
     a.vals_tmp = vals_tmp;
     a.off = off;
     a.dims = dims;
+    a.segid = segid;
+    a.tiny_max = segid ? 32 : 0;
     a.key_bits = key_bits;
     a.n_passes = (key_bits + 7) / 8;
     a.bits_per_pass = (key_bits + a.n_passes - 1) / a.n_passes;
@@ -502,6 +637,7 @@ static int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32
     TDT_CUDA(cudaMemsetAsync(a.L.win_hi, 0xff, (size_t)a.L.nwin * 4, st));
     TDT_CUDA(cudaMemsetAsync(a.L.win_lo, 0x7f, (size_t)a.L.nwin * 4, st));
     TDT_LAUNCH(segsort_classify_kernel, (unsigned)((nseg_max + 255) / 256), 256, 0, st, a);
+    TDT_LAUNCH(segsort_fill_kernel, (unsigned)a.L.nlarge_max, 256, 0, st, a);
     static thread_local bool configured = false;
     if (!configured) {
         TDT_CUDA(cudaFuncSetAttribute(segsort_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -510,8 +646,14 @@ static int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32
                                       (int)SS_PASS_SMEM));
         configured = true;
     }
-    const unsigned nwin = (unsigned)((n_max + SS_WINDOW - 1) / SS_WINDOW);
-    TDT_LAUNCH(segsort_local_kernel, nwin, SS_THREADS, SS_LOCAL_SMEM, st, a);
+    if (segid) {
+        int64_t blocks = (n_max + 255) / 256;
+        if (blocks > 148 * 32) blocks = 148 * 32;
+        TDT_LAUNCH(segsort_tiny_kernel, (unsigned)blocks, 256, 0, st, a);
+    }
+    int64_t nwin = (n_max + SS_WINDOW - 1) / SS_WINDOW;
+    if (nwin > 148 * 4) nwin = 148 * 4;
+    TDT_LAUNCH(segsort_local_kernel, (unsigned)nwin, SS_LTHREADS, SS_LOCAL_SMEM, st, a);
     const unsigned tiles = (unsigned)a.L.tiles_max;
     TDT_LAUNCH(segsort_hist_kernel, tiles, SS_THREADS, 0, st, a);
     const int64_t scan_warps = a.L.nlarge_max * SS_MAX_PASSES;

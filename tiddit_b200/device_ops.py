@@ -108,7 +108,7 @@ def ypass_device(y, epsilon, m, labels_io, cluster_id_io, max_pos=0):
     return labels_io, cluster_id_io
 
 
-def segsort_device(keys, vals, off, key_bits):
+def segsort_device(keys, vals, off, key_bits, segid=None):
     """Test hook: every segment [off[s], off[s+1]) of (keys uint32-as-int32, vals int32 or None) sorted by key,
     stable -> (keys_out, vals_out) CUDA tensors."""
     torch = _lib.torch_cuda()
@@ -119,7 +119,7 @@ def segsort_device(keys, vals, off, key_bits):
     if n == 0 or nseg <= 0:
         return ko, vo
     ws = _lib.workspace(torch, L.tdt_cluster_workspace_bytes(n, nseg))
-    rc = L.tdt_debug_segsort(_lib.ptr(keys), _lib.ptr(vals), _lib.ptr(off), nseg, n, int(key_bits), _lib.ptr(ko),
+    rc = L.tdt_debug_segsort(_lib.ptr(keys), _lib.ptr(vals), _lib.ptr(off), _lib.ptr(segid), nseg, n, int(key_bits), _lib.ptr(ko),
                              _lib.ptr(vo), _lib.ptr(ws), ws.numel(), _lib.stream_ptr(torch))
     _lib.check(rc)
     return ko, vo
