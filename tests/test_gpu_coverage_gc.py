@@ -131,3 +131,30 @@ def test_gc_chromosome_scale(oracle):
     from tiddit_b200 import tiddit_gc, synth
     seq = synth.fasta_sequence(60_000_000, seed=4)
     assert np.array_equal(tiddit_gc.gc_bins(seq, 50, 0.5), oracle.gc_bins(seq, 50, 0.5))
+
+
+def test_coverage_weird_reads_and_alignment(oracle):
+    """Negative starts (Python wrap-around), empty / inverted reads, unaligned device slices, bin sizes beyond the
+    quotient table -- everything the reference's arithmetic does without raising."""
+    import torch
+    from tiddit_b200 import device_ops
+    rng = np.random.default_rng(12)
+    for z in (500, 7, 5000, 100_000):
+        ln = 2_000_003
+        nb = -(-ln // z)
+        ebs = ln - (nb - 1) * z
+        s = rng.integers(0, ln, 50_000)
+        e = np.minimum(s + rng.integers(1, 3 * z + 2, 50_000), ln)
+        s[::97] = -rng.integers(1, min(z, 1000), len(s[::97]))      # wraps into the last bins
+        e[::97] = rng.integers(1, 200, len(e[::97]))
+        e[5::89] = s[5::89]                                          # empty reads
+        e[7::83] = np.maximum(s[7::83] - 3, 1)                       # inverted reads
+        want = np.zeros(nb)
+        oracle.update_coverage_batch(s, e, z, want, ebs)
+        sd = torch.from_numpy(np.concatenate([[0, 0, 0], s]).astype(np.int32)).cuda()[3:]   # 12-byte offset
+        ed = torch.from_numpy(np.concatenate([[0], e]).astype(np.int32)).cuda()[1:]
+        got = torch.zeros(nb, dtype=torch.float64, device="cuda")
+        bad = device_ops.new_first_bad(torch)
+        device_ops.coverage_accumulate_device(sd, ed, z, ebs, got, bad)
+        assert int(bad.item()) == device_ops.FIRST_BAD_NONE
+        assert np.array_equal(got.cpu().numpy().view(np.uint64), want.view(np.uint64)), z

@@ -3,51 +3,29 @@
 // Replaces tiddit/tiddit_coverage.pyx:48-74 (update_coverage) applied to a batch of reads.  Every
 // addend is the float32 quotient the reference computes (C `float` division, then promoted to
 // double for the add) or the integer 1.0; all of them are multiples of a common power of two and
-// the bin totals stay far below 2^53 of it, so float64 sums are exact in ANY order: warp-level
+// the bin totals stay far below 2^53 of it, so float64 sums are exact in ANY order: per-thread
 // pre-aggregation + RED.ADD.F64 into HBM is bit-identical to the reference's sequential `+=`.
 //
-// Reads arrive coordinate-sorted (BAM order), so the 32 reads of a warp touch one or two distinct
-// bins: lanes with the same bin form runs, each run is summed with a segmented shuffle scan and its
-// last lane issues ONE atomic -- ~4 atomics per 32 reads instead of 64+.
+// Layout of the work: a CTA stages 8192 reads (start[] and end[], 32 KB each) in shared memory with two 1-D TMA
+// bulk copies; every thread then walks its OWN 32 consecutive reads.  Reads arrive coordinate-sorted (BAM
+// order), so a run touches a handful of neighbouring bins: the thread keeps a window of two adjacent bins in
+// registers and issues atomics only when the window moves; the lanes of a warp work 32 reads apart, so their
+// atomics spread over bins instead of piling 32 deep onto one L2 address.  bin = pos / bin_size uses an exact multiply-shift; the quotients
+// float(a) / float(bin_size) for a in [0, bin_size] come from a shared-memory table filled with the very
+// division the reference performs, so no rounding differs.
 #include "tdt_common.cuh"
 
 namespace tdt {
+
+constexpr int COV_THREADS = 256;
+constexpr int COV_RUN = 32;            // consecutive reads one thread walks (power of two)
+constexpr int COV_TILE = COV_THREADS * COV_RUN;  // reads staged in shared memory per CTA iteration
+constexpr int COV_TABLE_MAX = 4096;    // bin sizes up to this use the quotient table (32 KB of doubles)
 
 __device__ __forceinline__ int64_t floordiv_i64(int64_t a, int64_t b) {  // Python //, b > 0
     int64_t q = a / b;
     if ((a % b != 0) && (a < 0)) q--;
     return q;
-}
-
-// one atomic per run of equal `bin` among adjacent active lanes; v summed exactly in double
-__device__ __forceinline__ void warp_run_add(double *bins, int64_t bin, double v, bool active) {
-    const int lane = threadIdx.x & 31;
-    const u32 act = __ballot_sync(0xffffffffu, active);
-    if (act == 0u) return;
-    const int64_t prev = __shfl_up_sync(0xffffffffu, bin, 1);
-    const bool head = active && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != bin);
-    const u32 heads = __ballot_sync(0xffffffffu, head);
-    const int hl = 31 - __clz((int)(heads & lanemask_le()));  // my run's first lane (valid when active)
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const double t = __shfl_up_sync(0xffffffffu, v, o);
-        if (active && lane - o >= hl) v += t;
-    }
-    const bool tail = active && (lane == 31 || !((act >> (lane + 1)) & 1u) || ((heads >> (lane + 1)) & 1u));
-    if (tail) atomicAdd(bins + bin, v);
-}
-
-// the same for addends that are all 1.0: the run sum is the run length
-__device__ __forceinline__ void warp_run_add_one(double *bins, int64_t bin, bool active) {
-    const int lane = threadIdx.x & 31;
-    const u32 act = __ballot_sync(0xffffffffu, active);
-    if (act == 0u) return;
-    const int64_t prev = __shfl_up_sync(0xffffffffu, bin, 1);
-    const bool head = active && (lane == 0 || !((act >> (lane - 1)) & 1u) || prev != bin);
-    const u32 heads = __ballot_sync(0xffffffffu, head);
-    const int hl = 31 - __clz((int)(heads & lanemask_le()));
-    const bool tail = active && (lane == 31 || !((act >> (lane + 1)) & 1u) || ((heads >> (lane + 1)) & 1u));
-    if (tail) atomicAdd(bins + bin, (double)(lane - hl + 1));
 }
 
 struct CovContig {  // where one contig's reads and bins live (all-contig call)
@@ -57,61 +35,204 @@ struct CovContig {  // where one contig's reads and bins live (all-contig call)
     int C;
 };
 
-template <bool MULTI>
-__global__ void __launch_bounds__(256) coverage_kernel(const int32_t *__restrict__ start,
-                                                       const int32_t *__restrict__ end, int64_t n_reads,
-                                                       int32_t bin_size, int32_t end_bin_size_one,
-                                                       double *__restrict__ bins, int64_t n_bins_one, CovContig cc,
-                                                       unsigned long long *first_bad) {
-    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const int64_t n_round = (n_reads + 31) & ~(int64_t)31;  // whole warps stay converged
+// A thread keeps a window of two adjacent bins [cb, cb+1] of the current contig in registers.  The common read
+// (both of its fractional bins inside the window) is four predicated adds; a read that leaves the window
+// flushes it (two atomics) and re-opens it at the read's first bin, bins further right go straight to memory.
+struct CovAcc {
+    int32_t cb;
+    double s0, s1;
+    double *bins;  // bins of the current contig
+    __device__ __forceinline__ void flush() {
+        if (cb >= 0) {
+            if (s0 != 0.0) atomicAdd(bins + cb, s0);
+            if (s1 != 0.0) atomicAdd(bins + cb + 1, s1);
+        }
+        cb = -1;
+        s0 = s1 = 0.0;
+    }
+    // first bin fb gets v1, last bin eb >= fb gets v2 (0 when eb == fb), bins strictly between get 1.0
+    __device__ __forceinline__ void add_read(int32_t fb, double v1, int32_t eb, double v2) {
+        const uint32_t df = (uint32_t)(fb - cb), de = (uint32_t)(eb - cb);
+        if (cb >= 0 && df <= 1u && de <= 1u) {
+            s0 += (df == 0u ? v1 : 0.0) + (de == 0u ? v2 : 0.0);
+            s1 += (df == 1u ? v1 : 0.0) + (de == 1u ? v2 : 0.0);
+            return;
+        }
+        flush();
+        cb = fb;
+        s0 = v1;
+        if (eb == fb + 1) {
+            s1 = v2;
+        } else if (eb > fb + 1) {
+            s1 = 1.0;
+            for (int32_t b = fb + 2; b < eb; b++) atomicAdd(bins + b, 1.0);
+            atomicAdd(bins + eb, v2);
+        }
+    }
+};
+
+// negative start or empty / inverted read: the reference's arithmetic literally, incl. Python's floor division
+// and negative-index wrap-around (tiddit_coverage.pyx:50-72); rare, so straight atomics
+__device__ __noinline__ void cov_odd_read(int64_t rs, int64_t re, int32_t bin_size, int32_t ebs, double *bins,
+                                          int64_t n_bins, int64_t r, unsigned long long *first_bad) {
     const float fbin = (float)bin_size;
-    for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < n_round; r += stride) {
-        bool valid = r < n_reads;
-        int64_t fb = 0, eb = 0, base = 0, n_bins = n_bins_one;
-        double v1 = 0.0, v2 = 0.0;
-        bool two = false;
-        if (valid) {
-            const int64_t rs = start[r], re = end[r];
-            int32_t ebs = end_bin_size_one;
-            if (MULTI) {
-                int lo = 0, hi = cc.C;  // contig of read r: largest c with read_off[c] <= r
+    const int64_t fb = floordiv_i64(rs, bin_size), eb = floordiv_i64(re - 1, bin_size);
+    if (fb < -n_bins || fb >= n_bins || eb < -n_bins || eb >= n_bins) {
+        atomicMin(first_bad, (unsigned long long)r);
+        return;
+    }
+    const int64_t wfb = fb < 0 ? fb + n_bins : fb, web = eb < 0 ? eb + n_bins : eb;
+    if (eb == fb) {
+        atomicAdd(bins + wfb, (double)__fdiv_rn((float)(re - rs), fbin));
+        return;
+    }
+    atomicAdd(bins + wfb, (double)__fdiv_rn((float)((fb + 1) * (int64_t)bin_size - rs), fbin));
+    const float last = (float)((re - 1) - eb * (int64_t)bin_size);
+    atomicAdd(bins + web, (double)__fdiv_rn(last, eb < n_bins - 1 ? fbin : (float)ebs));
+    for (int64_t b = fb + 1; b < eb; b++) atomicAdd(bins + (b < 0 ? b + n_bins : b), 1.0);
+}
+
+template <bool MULTI>
+__global__ void __launch_bounds__(COV_THREADS) coverage_kernel(const int32_t *__restrict__ start,
+                                                               const int32_t *__restrict__ end, int64_t n_reads,
+                                                               int32_t bin_size, int32_t end_bin_size_one,
+                                                               double *__restrict__ bins, int64_t n_bins_one,
+                                                               CovContig cc, uint32_t magic, int magic_shift,
+                                                               bool vec_ok, unsigned long long *first_bad) {
+    extern __shared__ __align__(128) unsigned char cov_smem[];
+    __shared__ __align__(8) uint64_t mbar;
+    int32_t *s_start = (int32_t *)cov_smem;                 // [COV_TILE]
+    int32_t *s_end = s_start + COV_TILE;                    // [COV_TILE]
+    double *q_table = (double *)(s_end + COV_TILE);         // q_table[a] = (double)((float)a / (float)bin_size)
+    const bool use_table = bin_size <= COV_TABLE_MAX;
+    const float fbin = (float)bin_size;
+    if (use_table)
+        for (int a = threadIdx.x; a <= bin_size; a += COV_THREADS) q_table[a] = (double)__fdiv_rn((float)a, fbin);
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    CovAcc acc;
+    acc.cb = -1;
+    acc.s0 = acc.s1 = 0.0;
+    acc.bins = bins;
+    int32_t n_bins = (int32_t)n_bins_one, ebs = end_bin_size_one;
+    int64_t c_first = 0, c_next = MULTI ? 0 : INT64_MAX;  // reads [c_first, c_next) belong to the current contig
+    const int lane = threadIdx.x & 31;
+    uint32_t phase = 0;
+
+    const int64_t n_tiles = (n_reads + COV_TILE - 1) / COV_TILE;
+    for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int64_t t0 = tile * COV_TILE;
+        const int cnt = n_reads - t0 < COV_TILE ? (int)(n_reads - t0) : COV_TILE;
+        // stage the tile: two 32 KB TMA bulk copies (full, 16-byte aligned tiles) or plain coalesced loads
+        if (vec_ok && cnt == COV_TILE) {
+            if (threadIdx.x == 0) {
+                mbar_expect_tx(&mbar, 2u * COV_TILE * 4u);
+                tma_load_1d(s_start, start + t0, COV_TILE * 4u, &mbar);
+                tma_load_1d(s_end, end + t0, COV_TILE * 4u, &mbar);
+            }
+            mbar_wait(&mbar, phase);
+            phase ^= 1u;
+        } else {
+            for (int i = threadIdx.x; i < cnt; i += COV_THREADS) {
+                s_start[i] = start[t0 + i];
+                s_end[i] = end[t0 + i];
+            }
+            __syncthreads();
+        }
+        // a thread walks its own COV_RUN consecutive reads (rotated by the lane so that the 32 lanes hit 32
+        // different banks): its register window absorbs nearly all adds, and the lanes of a warp work COV_RUN
+        // reads apart, so their atomics go to different bins instead of piling up on one L2 address
+#pragma unroll 2
+        for (int k = 0; k < COV_RUN; k++) {
+            const int idx = threadIdx.x * COV_RUN + ((k + lane) & (COV_RUN - 1));
+            if (idx >= cnt) continue;
+            const int64_t r = t0 + idx;
+            if (MULTI && (r >= c_next || r < c_first)) {
+                // another contig: close the window, look the contig up (largest c with read_off[c] <= r)
+                acc.flush();
+                int lo = 0, hi = cc.C;
                 while (hi - lo > 1) {
                     const int mid = (lo + hi) >> 1;
                     if (cc.read_off[mid] <= r) lo = mid; else hi = mid;
                 }
-                base = cc.bin_off[lo];
-                n_bins = cc.bin_off[lo + 1] - base;
+                c_first = cc.read_off[lo];
+                c_next = cc.read_off[lo + 1];
+                const int64_t base = cc.bin_off[lo];
+                n_bins = (int32_t)(cc.bin_off[lo + 1] - base);
                 ebs = cc.end_bin_size[lo];
+                acc.bins = bins + base;
             }
-            fb = floordiv_i64(rs, bin_size);        // tiddit_coverage.pyx:50
-            eb = floordiv_i64(re - 1, bin_size);    // :51
-            if (eb == fb) {                         // :55-57
-                v1 = (double)__fdiv_rn((float)(re - rs), fbin);
-            } else {                                // :61-69
-                two = true;
-                v1 = (double)__fdiv_rn((float)((fb + 1) * (int64_t)bin_size - rs), fbin);
-                const float last = (float)((re - 1) - eb * (int64_t)bin_size);
-                v2 = (double)__fdiv_rn(last, eb < n_bins - 1 ? fbin : (float)ebs);
-            }
-            // boundscheck + wraparound are on for this function in the reference: i in [-n, n) only
-            if (fb < -n_bins || fb >= n_bins || eb < -n_bins || eb >= n_bins) {
-                atomicMin(first_bad, (unsigned long long)r);
-                valid = false;
+            const int32_t rs = s_start[idx], re = s_end[idx];
+            if (rs >= 0 && re > rs) {
+                // the usual read: exact multiply-shift division (n < 2^31), table quotients
+                const int32_t fb = (int32_t)(((uint32_t)rs + __umulhi((uint32_t)rs, magic)) >> magic_shift);      // :50
+                const int32_t eb =
+                    (int32_t)(((uint32_t)(re - 1) + __umulhi((uint32_t)(re - 1), magic)) >> magic_shift);        // :51
+                if (eb >= n_bins) {  // boundscheck: IndexError in the reference
+                    atomicMin(first_bad, (unsigned long long)r);
+                } else {
+                    const bool same = eb == fb;                                               // :55
+                    const int a1 = same ? re - rs : (fb + 1) * bin_size - rs;                 // :56 / :61
+                    const int a2 = same ? 0 : (re - 1) - eb * bin_size;                       // :63 (q_table[0] = 0)
+                    double v1, v2;
+                    if (use_table) {
+                        v1 = q_table[a1];
+                        v2 = q_table[a2];
+                    } else {
+                        v1 = (double)__fdiv_rn((float)a1, fbin);
+                        v2 = (double)__fdiv_rn((float)a2, fbin);
+                    }
+                    if (!same && eb == n_bins - 1) v2 = (double)__fdiv_rn((float)a2, (float)ebs);   // :69
+                    acc.add_read(fb, v1, eb, v2);
+                }
+            } else {
+                cov_odd_read(rs, re, bin_size, ebs, acc.bins, n_bins, r, first_bad);
             }
         }
-        const int64_t wfb = base + (fb < 0 ? fb + n_bins : fb);
-        const int64_t web = base + (eb < 0 ? eb + n_bins : eb);
-        warp_run_add(bins, wfb, v1, valid);
-        warp_run_add(bins, web, v2, valid && two);
-        // bins strictly between first and last get 1.0 each (:71-72)
-        for (int64_t k = 1;; k++) {
-            const int64_t i = fb + k;
-            const bool mid = valid && two && i < eb;
-            if (!__any_sync(0xffffffffu, mid)) break;
-            warp_run_add_one(bins, base + (i < 0 ? i + n_bins : i), mid);
-        }
+        __syncthreads();  // the tile is consumed: the next bulk copy may overwrite it
     }
+    acc.flush();
+}
+
+// n / d == (n + umulhi(n, magic)) >> shift for every 0 <= n < 2^31: Granlund-Montgomery with
+// M = ceil(2^(32+L) / d) = 2^32 + magic, L = ceil(log2 d) (n + hi(n * magic) < 2^32 because n < 2^31)
+static void magic_for(uint32_t d, uint32_t &magic, int &shift) {
+    int L = 0;
+    while ((1ull << L) < d) L++;
+    shift = L;
+    const unsigned __int128 one = (unsigned __int128)1 << (32 + L);
+    const unsigned __int128 M = (one + d - 1) / d;
+    magic = (uint32_t)(M - ((unsigned __int128)1 << 32));
+}
+
+static int launch_coverage(bool multi, const int32_t *start, const int32_t *end, int64_t n_reads, int32_t bin_size,
+                           int32_t end_bin_size, double *bins, int64_t n_bins, CovContig cc, int64_t *first_bad,
+                           cudaStream_t st) {
+    const bool vec_ok = (((uintptr_t)start | (uintptr_t)end) & 15) == 0;
+    uint32_t magic;
+    int shift;
+    magic_for((uint32_t)bin_size, magic, shift);
+    int64_t blocks = (n_reads + COV_TILE - 1) / COV_TILE;
+    if (blocks > 148 * 3) blocks = 148 * 3;
+    const size_t smem = (size_t)COV_TILE * 8 + (bin_size <= COV_TABLE_MAX ? ((size_t)bin_size + 1) * sizeof(double) : 8);
+    static thread_local bool configured = false;
+    if (!configured) {
+        const int max_smem = COV_TILE * 8 + (COV_TABLE_MAX + 1) * 8;
+        TDT_CUDA(cudaFuncSetAttribute(coverage_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        TDT_CUDA(cudaFuncSetAttribute(coverage_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+        configured = true;
+    }
+    ProfScope ps("coverage", st);
+    if (multi)
+        TDT_LAUNCH(coverage_kernel<true>, (unsigned)blocks, COV_THREADS, smem, st, start, end, n_reads, bin_size, 0, bins,
+                   (int64_t)0, cc, magic, shift, vec_ok, (unsigned long long *)first_bad);
+    else
+        TDT_LAUNCH(coverage_kernel<false>, (unsigned)blocks, COV_THREADS, smem, st, start, end, n_reads, bin_size,
+                   end_bin_size, bins, n_bins, cc, magic, shift, vec_ok, (unsigned long long *)first_bad);
+    return TDT_OK;
 }
 
 }  // namespace tdt
@@ -126,13 +247,9 @@ int tdt_coverage_accumulate(const int32_t *start, const int32_t *end, int64_t n_
     if (bin_size <= 0) return fail(TDT_E_ARG, "bin_size = %d (the reference divides by it)", bin_size);
     if (n_reads == 0) return TDT_OK;
     if (!start || !end || !bins || !first_bad) return fail(TDT_E_ARG, "null pointer argument");
-    int64_t blocks = (n_reads + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
     CovContig cc = {nullptr, nullptr, nullptr, 0};
-    ProfScope ps("coverage", (cudaStream_t)stream);
-    TDT_LAUNCH(coverage_kernel<false>, (unsigned)blocks, 256, 0, (cudaStream_t)stream, start, end, n_reads, bin_size,
-               end_bin_size, bins, n_bins, cc, (unsigned long long *)first_bad);
-    return TDT_OK;
+    return launch_coverage(false, start, end, n_reads, bin_size, end_bin_size, bins, n_bins, cc, first_bad,
+                           (cudaStream_t)stream);
 }
 
 int tdt_coverage_accumulate_contigs(const int32_t *start, const int32_t *end, int64_t n_reads, const int64_t *read_off,
@@ -144,13 +261,8 @@ int tdt_coverage_accumulate_contigs(const int32_t *start, const int32_t *end, in
     if (C < 1) return fail(TDT_E_ARG, "C = %d contigs for %lld reads", C, (long long)n_reads);
     if (!start || !end || !bins || !first_bad || !read_off || !bin_off || !end_bin_size)
         return fail(TDT_E_ARG, "null pointer argument");
-    int64_t blocks = (n_reads + 255) / 256;
-    if (blocks > 148 * 32) blocks = 148 * 32;
     CovContig cc = {read_off, bin_off, end_bin_size, C};
-    ProfScope ps("coverage", (cudaStream_t)stream);
-    TDT_LAUNCH(coverage_kernel<true>, (unsigned)blocks, 256, 0, (cudaStream_t)stream, start, end, n_reads, bin_size, 0,
-               bins, 0, cc, (unsigned long long *)first_bad);
-    return TDT_OK;
+    return launch_coverage(true, start, end, n_reads, bin_size, 0, bins, 0, cc, first_bad, (cudaStream_t)stream);
 }
 
 }  // extern "C"
