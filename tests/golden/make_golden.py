@@ -217,7 +217,33 @@ def cluster_cases():
             json.dump({"args": args, "candidates": _jsonable(cand), "order": order}, f, separators=(",", ":"))
 
 
+def config1_cov():
+    """BASELINE config 1: `tiddit --cov` on a 1-contig 10k-read synthetic BAM, -z 500.  The BAM comes from our
+    writer; the expected bed / wig come from the REFERENCE's coverage functions driven by the loop of
+    tiddit/__main__.py:225-247 (the reference CLI itself cannot start here: it imports pysam)."""
+    from tiddit_b200 import bamio
+    contigs = [("chrS", 1_000_000)]
+    bam = os.path.join(HERE, "config1.bam")
+    bamio.write_bam(bam, contigs, bamio.synthetic_reads(contigs, 10_000, seed=1))
+    cov = R.tiddit_coverage
+    for z, q in ((500, 20), (50, 5)):
+        samfile = bamio.AlignmentFile(bam)
+        header = samfile.header
+        coverage_data, end_bin_size = cov.create_coverage(header, z)
+        for read in samfile.fetch(until_eof=True):
+            if read.is_unmapped or read.is_duplicate:
+                continue
+            if read.mapq >= q:
+                name = read.reference_name
+                coverage_data[name] = cov.update_coverage(read.reference_start, read.reference_end, z,
+                                                          coverage_data[name], end_bin_size[name])
+        cov.print_coverage(coverage_data, header, z, "bed", os.path.join(HERE, "config1_z%d_q%d.bed" % (z, q)))
+        if z == 500:
+            cov.print_coverage(coverage_data, header, z, "wig", os.path.join(HERE, "config1_z%d_q%d.wig" % (z, q)))
+
+
 if __name__ == "__main__":
+    config1_cov()
     dbscan_cases()
     coverage_cases()
     gc_cases()

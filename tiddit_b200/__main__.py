@@ -1,0 +1,93 @@
+"""`python -m tiddit_b200 --cov ...`: the reference's coverage command (tiddit/__main__.py:210-247) on the GPU path.
+
+Same flags, same output files (byte-identical bed / wig).  Reads are decoded on the host (pysam when installed,
+the built-in BAM reader otherwise), buffered per contig and accumulated in batches by the coverage kernel.
+`--sv` needs the reference's own stages (signal extraction, assembly, variant calling, all built on pysam and bwa);
+when the `tiddit` package is importable it is run with this package's clustering / coverage / GC modules swapped in.
+"""
+import argparse
+import os
+import sys
+
+
+def run_cov(argv):
+    parser = argparse.ArgumentParser("""tiddit --cov --bam inputfile [-o prefix]""")
+    parser.add_argument('--cov', help="generate a coverage bed/wig file", required=False, action="store_true")
+    parser.add_argument('--bam', type=str, required=True, help="coordinate sorted bam file(required)")
+    parser.add_argument('-o', type=str, default="output", help="output prefix(default=output)")
+    parser.add_argument('-z', type=int, default=500, help="use bins of specified size(default = 500bp) to measure the coverage of the entire bam file, set output to stdout to print to stdout")
+    parser.add_argument('-w', help="generate wig instead of bed", required=False, action="store_true")
+    parser.add_argument('-q', type=int, help="minimum mapping quality(default=20)", required=False, default=20)
+    parser.add_argument('--ref', type=str, help="reference fasta, used for reading cram")
+    args = parser.parse_args(argv)
+    if not os.path.isfile(args.bam):
+        print("error,  could not find the bam file")
+        return 1
+    from . import bamio, tiddit_coverage
+    samfile = bamio.open_alignment_file(args.bam, reference_filename=args.ref)
+    bam_header = samfile.header
+    cov = tiddit_coverage.DeviceCoverage(bam_header, args.z)
+    names, starts, ends = [], [], []
+    current = None
+
+    def flush():
+        if starts:
+            cov.add_reads(current, starts, ends)
+            del starts[:], ends[:]
+
+    for read in samfile.fetch(until_eof=True):
+        if read.is_unmapped or read.is_duplicate:
+            continue
+        if read.mapq >= args.q:
+            name = read.reference_name
+            if name != current or len(starts) >= 1 << 20:
+                flush()
+                current = name
+            starts.append(read.reference_start)
+            ends.append(read.reference_end)
+    flush()
+    coverage_data, _ = cov.to_host()
+    if args.w:
+        tiddit_coverage.print_coverage(coverage_data, bam_header, args.z, "wig", args.o + ".wig")
+    else:
+        tiddit_coverage.print_coverage(coverage_data, bam_header, args.z, "bed", args.o + ".bed")
+    return 0
+
+
+def run_sv(argv):
+    try:
+        import tiddit.__main__ as ref_main   # needs pysam, bwa, ... (not in this image)
+    except Exception as exc:
+        print("tiddit_b200 replaces the clustering / coverage / GC stages only; --sv also needs the reference "
+              "package (pysam, bwa) for signal extraction, assembly and variant calling: %s" % exc)
+        return 2
+    from . import DBSCAN, tiddit_cluster, tiddit_coverage, tiddit_gc
+    import tiddit
+    for name, mod in (("DBSCAN", DBSCAN), ("tiddit_cluster", tiddit_cluster), ("tiddit_coverage", tiddit_coverage),
+                      ("tiddit_gc", tiddit_gc)):
+        sys.modules["tiddit." + name] = mod
+        setattr(tiddit, name, mod)
+        if hasattr(ref_main, name):
+            setattr(ref_main, name, mod)
+    sys.argv = ["tiddit"] + list(argv)
+    ref_main.main()
+    return 0
+
+
+def main(argv=None):
+    argv = list(sys.argv[1:] if argv is None else argv)
+    parser = argparse.ArgumentParser("""tiddit_b200: TIDDIT's clustering / coverage hot path on B200""", add_help=False)
+    parser.add_argument('--sv', action="store_true")
+    parser.add_argument('--cov', action="store_true")
+    args, _ = parser.parse_known_args(argv)
+    if args.cov:
+        return run_cov(argv)
+    if args.sv:
+        return run_sv(argv)
+    print("usage: python -m tiddit_b200 --cov --bam inputfile [-o prefix] [-z bin] [-q mapq] [-w]\n"
+          "       python -m tiddit_b200 --sv ...   (delegates to the reference pipeline with the GPU modules swapped in)")
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

@@ -301,6 +301,171 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
 }
 
 // ----------------------------------------------------------------------------------------------
+// The same kernel specialised for min_pts <= 32 and sorted input (every real TIDDIT run: -l defaults to 3).
+// A warp owns 16 consecutive ballot words of the tile and recomputes the one word before them, so run
+// starts and "labelled" bits need no other warp: lane t keeps word t in a register, the m-wide OR that marks
+// labelled elements is a log-step shift/OR on the 64-bit (previous:current) word pair, and the prefix over
+// the 16 words is a warp shuffle scan.  Two block barriers in all (tile staged / carry known).
+// ----------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(WR_THREADS) window_runs_small_kernel(const WRParams p) {
+    constexpr int HL = 32, WPW = WR_WORDS / WR_WARPS;  // left halo, words per warp (16)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ u32 s_wtot[WR_WARPS][2], s_wbase[WR_WARPS][2], s_pref[4];
+
+    const int m = p.m;
+    const int HR = (m + 3) & ~3;
+    const int HEADW = (HL + WR_TILE + HR) / 32 + 2;
+    u32 *keys_s = (u32 *)smem_raw;
+    u32 *hw = keys_s + (HL + WR_TILE + HR);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t n = p.dims->n;
+    const int tile = blockIdx.x;  // blockIdx order: see window_runs_kernel
+    const int64_t tile_base = (int64_t)tile * WR_TILE;
+    if (tile_base >= n) return;
+    const int64_t ext_base = tile_base - HL;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&mbar, 1);
+        fence_mbar_init();
+        const int64_t n_pad = (n + 3) & ~(int64_t)3;
+        const int64_t jlo = ext_base < 0 ? 0 : ext_base;
+        int64_t jhi = tile_base + WR_TILE + HR;
+        if (jhi > n_pad) jhi = n_pad;
+        const uint32_t bytes = (uint32_t)((jhi - jlo) * 4);
+        mbar_expect_tx(&mbar, bytes);
+        tma_load_1d(keys_s + (jlo - ext_base), p.keys + jlo, bytes, &mbar);
+    }
+    {
+        const int64_t w0 = ext_base >> 5, nwords = (n + 31) >> 5;
+        for (int i = threadIdx.x; i < HEADW; i += WR_THREADS) {
+            const int64_t w = w0 + i;
+            hw[i] = (w >= 0 && w < nwords) ? p.heads[w] : 0u;
+        }
+    }
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+
+    // ---- windows: 17 ballot words per warp (its 16 + the one before), word t parked in lane t ----
+    const int e_min = tile == 0 ? HL : 0;                                   // positions before element 0
+    const int64_t left = n - ext_base;
+    const int n_rel = left > (1 << 30) ? (1 << 30) : (int)left;             // shared position of element n
+    const u32 mask_m = m >= 32 ? 0xffffffffu : ((1u << m) - 1u);            // heads in (e, e+m]
+    const u32 mask_m1 = (1u << (m - 1)) - 1u;                               // heads in (e, e+m-1]
+    const u32 eps = p.eps;
+    u32 okreg = 0;
+#pragma unroll
+    for (int t = 0; t <= WPW; t++) {
+        const int xw = warp * WPW + t;  // shared word; tile word = xw - 1
+        const int e = xw * 32 + lane;
+        bool ok = false;
+        if (e >= e_min && e + m - 1 < n_rel) {
+            const u32 kj = keys_s[e];
+            const u32 hb = lane == 31 ? hw[xw + 1] : __funnelshift_r(hw[xw], hw[xw + 1], lane + 1);
+            if (MODE == MODE_Y) {
+                ok = !(hb & mask_m1) && (keys_s[e + m - 1] - kj < eps);
+            } else if (e + m < n_rel && !(hb & mask_m)) {
+                ok = keys_s[e + m] - kj < eps;
+            } else {
+                ok = !(hb & mask_m1) && (keys_s[e + m - 1] - kj < eps);
+            }
+        }
+        const u32 word = __ballot_sync(0xffffffffu, ok);
+        if (lane == t) okreg = word;
+    }
+    // ---- lane t in 1..16: run starts and labelled bits of tile word 16*warp + t - 1 ----------------
+    const u32 prev = __shfl_up_sync(0xffffffffu, okreg, 1);
+    const bool mine = lane >= 1 && lane <= WPW;
+    u32 st = 0, cv = 0, hword = 0;
+    if (mine) {
+        st = okreg & ~((okreg << 1) | (prev >> 31));
+        u64 v = ((u64)okreg << 32) | (u64)prev;   // OR of the m positions ending at every bit
+        int span = 1;
+        while (span * 2 <= m) {
+            v |= v << span;
+            span *= 2;
+        }
+        if (span < m) v |= v << (m - span);
+        cv = (u32)(v >> 32);
+        hword = hw[warp * WPW + lane];
+    }
+    const u32 cs = __popc(st), cc = MODE == MODE_X ? __popc(cv) : __popc(hword);
+    u32 is = cs, ic = cc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(0xffffffffu, is, o);
+        const u32 b = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) {
+            is += a;
+            ic += b;
+        }
+    }
+    const int64_t gw = (tile_base >> 5) + warp * WPW + lane - 1;
+    if (mine && gw * 32 < n) {
+        p.stw[gw] = st;
+        p.cvw[gw] = cv;
+    }
+    if (lane == WPW) {
+        s_wtot[warp][0] = is;
+        s_wtot[warp][1] = ic;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        u32 ts = lane < WR_WARPS ? s_wtot[lane][0] : 0u, tc = lane < WR_WARPS ? s_wtot[lane][1] : 0u;
+        u32 ws = ts, wc = tc;
+#pragma unroll
+        for (int o = 1; o < WR_WARPS; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, ws, o);
+            const u32 b = __shfl_up_sync(0xffffffffu, wc, o);
+            if (lane >= o) {
+                ws += a;
+                wc += b;
+            }
+        }
+        if (lane < WR_WARPS) {
+            s_wbase[lane][0] = ws - ts;
+            s_wbase[lane][1] = wc - tc;
+        }
+        const u32 aggS = __shfl_sync(0xffffffffu, ws, WR_WARPS - 1);
+        const u32 aggC = __shfl_sync(0xffffffffu, wc, WR_WARPS - 1);
+        u32 exS, exC;
+        lookback(p.status, tile, aggS, aggC, exS, exC);
+        if (lane == 0) {
+            s_pref[0] = exS;
+            s_pref[1] = exC;
+            s_pref[2] = aggS;
+            s_pref[3] = aggC;
+            p.tile_pref[2 * (int64_t)tile] = exS;
+            p.tile_pref[2 * (int64_t)tile + 1] = exC;
+        }
+    }
+    if (MODE == MODE_X && !(tile_base + WR_TILE >= n)) return;  // X tiles are done; the last one adds the totals
+    __syncthreads();
+    const u32 exS = s_pref[0], exC = s_pref[1];
+    if (MODE == MODE_Y && mine) {
+        // segment heads record how many runs precede their segment (DBSCAN.py:88 restarts the count at 0)
+        const u32 baseS = exS + s_wbase[warp][0] + (is - cs), baseC = exC + s_wbase[warp][1] + (ic - cc);
+        u32 h = hword;
+        while (h) {
+            const int b = __ffs(h) - 1;
+            const u32 below = (1u << b) - 1u;
+            const u32 rank = baseC + __popc(hword & below);
+            p.gcnt_start[rank] = (int32_t)(baseS + __popc(st & below));
+            if (p.rank_of) p.rank_of[p.seg_value[gw * 32 + b]] = (int32_t)rank;
+            h &= h - 1;
+        }
+    }
+    if (threadIdx.x == 0 && tile_base + WR_TILE >= n) {  // the last tile publishes the totals
+        const u32 totS = exS + s_pref[2], totC = exC + s_pref[3];
+        p.totals[0] = totS;
+        p.totals[1] = totC;
+        if (MODE == MODE_Y) p.gcnt_start[totC] = (int32_t)totS;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
 // small helpers around the range-query kernel
 // ----------------------------------------------------------------------------------------------
 __global__ void heads_from_offsets_kernel(const int64_t *__restrict__ off, const Dims *dims, u32 *heads) {
@@ -773,6 +938,12 @@ static int grid_for(int64_t n, int threads) {
 
 template <int MODE, bool GENERAL>
 static int launch_window_runs(const WRParams &p, int64_t n_max, cudaStream_t st) {
+    if (!GENERAL && p.m <= 32) {
+        const size_t HR = ((size_t)p.m + 3) & ~(size_t)3;
+        const size_t smem = (32 + WR_TILE + HR) * 4 + ((32 + WR_TILE + HR) / 32 + 2) * 4;
+        TDT_LAUNCH((window_runs_small_kernel<MODE>), (unsigned)wr_tiles(n_max), WR_THREADS, smem, st, p);
+        return TDT_OK;
+    }
     const size_t smem = wr_smem_bytes(p.m);
     if (smem > 48 * 1024)
         TDT_CUDA(cudaFuncSetAttribute(window_runs_kernel<MODE, GENERAL>, cudaFuncAttributeMaxDynamicSharedMemorySize,
