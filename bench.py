@@ -302,7 +302,8 @@ def main():
     ap.add_argument("--signals", type=int, default=0, help="override the workload's signal count")
     ap.add_argument("--cov-reads", type=int, default=617_653_966, help="reads for the coverage leg (30X = 617653966)")
     ap.add_argument("--no-coverage", action="store_true")
-    ap.add_argument("--chunks", type=int, default=8, help="pair chunks of the pipelined host path (e2e, N=1)")
+    ap.add_argument("--no-graph", action="store_true", help="issue the step's kernels eagerly instead of replaying a CUDA graph")
+    ap.add_argument("--chunks", type=int, default=6, help="pair chunks of the pipelined host path (e2e, N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
     ap.add_argument("--ref-crops-per-core", type=int, default=1, help="--impl reference: 50k-signal crops per core per step")
     args = ap.parse_args()
@@ -353,8 +354,13 @@ def main():
     def flush():
         flush_buf.add_(1)          # 256 MB read+write > the 126 MB L2
 
+    runner = None if args.no_graph else engine.GraphRunner(a_d, b_d, off_d, P_mine, eps, m, L, labels_d[:n_mine])
+
     def step_device():
-        device_ops.cluster_labels_device(a_d, b_d, off_d, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
+        if runner is not None:   # the call's kernels replayed from a CUDA graph (same launches, no host latency)
+            runner.replay()
+        else:
+            device_ops.cluster_labels_device(a_d, b_d, off_d, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
         if world > 1:
             dist.all_gather_into_tensor(gathered, labels_d)
 
@@ -396,10 +402,16 @@ def main():
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item()) / steps
 
+    c0 = _lib.launch_count()
+    device_ops.cluster_labels_device(a_d, b_d, off_d, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
+    launches_per_call = _lib.launch_count() - c0
     launches0 = _lib.launch_count()
     with ClockSampler(local) as clk:
         ms_step = timed(step_device, args.steps, args.warmup)
         launches = (_lib.launch_count() - launches0) // (args.steps + args.warmup)
+        if runner is not None:
+            runner.check()
+            launches = launches_per_call   # replayed launches are not re-issued through the library's counter
         a2, b2, off2 = torch.empty_like(a_d), torch.empty_like(b_d), torch.empty_like(off_d)
         ms_e2e = timed(lambda: step_e2e(a2, b2, off2), max(3, args.steps // 2), 2)
     clocks = clk.summary()
@@ -417,7 +429,7 @@ def main():
     tot_stage = sum(stage_ms.values()) or 1.0
     k_ms = stage_ms.get("window_runs_x", float("nan"))
     alg = 8.0 * n_mine
-    roofline = {"bound": "hbm", "kernel": "window_runs_kernel<X_PAIRS> (eps-range query + run labelling, posA axis)",
+    roofline = {"bound": "hbm", "kernel": "window_runs_small_kernel<X> (eps-range query + run labelling, posA axis)",
                 "achieved": alg / k_ms / 1e6, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": alg / k_ms / 1e6 / hbm_peak, "traffic": None,
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": k_ms,
@@ -431,9 +443,10 @@ def main():
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": w["desc"], "signals": n_total, "pairs": P_total, "eps": eps, "min_pts": m,
                        "sharding": "pairs LPT over %d ranks, one all-gather of int32 labels" % world if world > 1
-                       else "single GPU", "l2": "256 MB flush between timed steps (and inputs > L2 at N=1)"},
+                       else "single GPU", "l2": "256 MB flush between timed steps (and inputs > L2 at N=1)",
+                       "launch": "eager" if args.no_graph else "CUDA-graph replay of the ABI call's kernels"},
             "e2e": {"value": n_total / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
-                    "path": "engine.HostPipeline: %d pair chunks, H2D | kernels | D2H on 3 streams" % args.chunks
+                    "path": "engine.HostPipeline: %d tapered pair chunks, H2D | CUDA-graph replay of the chunk kernels | D2H on 3 streams, one host sync" % args.chunks
                     if world == 1 else "per-rank H2D, kernels, all-gather, rank-0 D2H",
                     "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + off_h.nbytes),
                     "d2h_bytes_per_step": int(out_pin.numel() * 4) if rank == 0 else 0},

@@ -62,6 +62,15 @@ TDT_API int tdt_cluster_labels(const int32_t *posA, const int32_t *posB, const i
                        int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out, void *ws,
                        size_t ws_bytes, void *stream);
 
+/* The same without the final host synchronisation, for callers that pipeline several calls (chunks of pairs)
+ * behind host<->device copies: nothing blocks; a data error (TDT_E_RANGE conditions) is max-reduced as a
+ * positive code into *status_accum (device int32, zeroed by the caller: 1 = posA out of range, 2 = posB out of
+ * range), to be read after the caller's own synchronisation.  The workspace may be reused by the next call on the
+ * same stream. */
+TDT_API int tdt_cluster_labels_async(const int32_t *posA, const int32_t *posB, const int64_t *seg_off, int64_t n,
+                                     int32_t P, int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out,
+                                     void *ws, size_t ws_bytes, int32_t *status_accum, void *stream);
+
 /* DBSCAN.py:125-129 on ONE array in the caller's order (the reference does not sort inside
  * DBSCAN.main; its caller does): x-pass over x[] as given -- window max of |x[j]-x[i]|, so unsorted
  * input behaves like the reference -- then the y-pass.  Same workspace as tdt_cluster_labels(n, 1).

@@ -60,3 +60,17 @@ def test_sharded_labels_nccl(tmp_path, oracle):
     want = oracle.cluster_segments(a, b, off, 500, 3)
     for r in range(world):
         assert np.array_equal(np.load(tmp_path / ("labels_%d.npy" % r)), want)
+
+
+def test_host_pipeline_reports_range_errors():
+    import torch
+    from tiddit_b200 import engine, _lib
+    a = np.array([5, 900, 7, 8], dtype=np.int32)
+    b = np.array([1, 2, 3, 4], dtype=np.int32)
+    pipe = engine.HostPipeline(4, n_chunks=2)
+    out = torch.empty(4, dtype=torch.int32).pin_memory()
+    with pytest.raises(_lib.TdtError) as e:
+        pipe.run(torch.from_numpy(a).pin_memory(), torch.from_numpy(b).pin_memory(), np.array([0, 2, 4]), 10, 2, 100, out)
+    assert e.value.code == _lib.TDT_E_RANGE
+    pipe.run(torch.from_numpy(b).pin_memory(), torch.from_numpy(b).pin_memory(), np.array([0, 2, 4]), 10, 2, 100, out)
+    assert out.tolist() == [0, 0, 0, 0]

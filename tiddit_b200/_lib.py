@@ -25,6 +25,7 @@ SIGNATURES = {
     "tdt_profile_end": (ctypes.c_int, [ctypes.c_char_p, _sz]),
     "tdt_cluster_workspace_bytes": (_sz, [_i64, _i32]),
     "tdt_cluster_labels": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _sz, _p]),
+    "tdt_cluster_labels_async": (ctypes.c_int, [_p, _p, _p, _i64, _i32, _i32, _i32, _i32, _p, _p, _sz, _p, _p]),
     "tdt_dbscan_main": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "tdt_xpass_labels": (ctypes.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _sz, _p]),
     "tdt_ypass_labels": (ctypes.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),

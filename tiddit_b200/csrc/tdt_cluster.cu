@@ -980,6 +980,11 @@ static int finish(Buffers &b, cudaStream_t st) {
     return err_to_code(h.err);
 }
 
+// asynchronous callers: fold this call's error flag into the caller's device-side status word
+__global__ void accumulate_status_kernel(const Small *small, int32_t *status_accum) {
+    if (small->err) atomicMax(status_accum, (int32_t)small->err);
+}
+
 static int pos_bits(int32_t max_pos) { return bit_width_u32(max_pos > 0 ? (uint32_t)max_pos : 0x7fffffffu); }
 
 // y-pass on the compacted (posB, insertion index, x-run) triples in ykey/yval/gx with offsets goff and
@@ -1050,7 +1055,7 @@ static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, 
 // seg_off: device offsets of the P pairs, or nullptr with presorted_plain (one segment, no sort)
 static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t *seg_off, int64_t n, int32_t P,
                         int32_t eps, int32_t m, int32_t max_pos, int32_t *labels_out, void *ws, size_t ws_bytes,
-                        cudaStream_t st, bool presorted_plain) {
+                        cudaStream_t st, bool presorted_plain, int32_t *status_accum = nullptr) {
     const ClusterPlan pl = make_plan(n, P);
     Buffers b = carve(pl, ws, ws_bytes);
     if (!b.ok) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
@@ -1116,6 +1121,10 @@ static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t 
     }
     int rc = run_ypass<false>(pl, b, eps, m, key_bits, P, 0, nullptr, labels_out, nullptr, st);
     if (rc) return rc;
+    if (status_accum) {  // no host round trip: the caller reads its status word when it synchronises
+        TDT_LAUNCH(accumulate_status_kernel, 1, 1, 0, st, b.small, status_accum);
+        return TDT_OK;
+    }
     return finish(b, st);
 }
 
@@ -1142,6 +1151,20 @@ int tdt_cluster_labels(const int32_t *posA, const int32_t *posB, const int64_t *
     if (max_pos == 0) max_pos = 0x7fffffff;
     return cluster_impl(posA, posB, seg_off, n, P, eps, min_pts, max_pos, labels_out, ws, ws_bytes,
                         (cudaStream_t)stream, false);
+}
+
+int tdt_cluster_labels_async(const int32_t *posA, const int32_t *posB, const int64_t *seg_off, int64_t n, int32_t P,
+                             int32_t eps, int32_t min_pts, int32_t max_pos, int32_t *labels_out, void *ws,
+                             size_t ws_bytes, int32_t *status_accum, void *stream) {
+    if (!status_accum) return fail(TDT_E_ARG, "status_accum is null");
+    if (P < 1 && n > 0) return fail(TDT_E_ARG, "P = %d pairs for %lld signals", P, (long long)n);
+    if (max_pos < 0) return fail(TDT_E_ARG, "max_pos = %d is negative", max_pos);
+    int rc = check_common(n, min_pts, ws, ws_bytes, make_plan(n, P < 1 ? 1 : P).total);
+    if (rc || n == 0) return rc;
+    if (!posA || !posB || !seg_off || !labels_out) return fail(TDT_E_ARG, "null pointer argument");
+    if (max_pos == 0) max_pos = 0x7fffffff;
+    return cluster_impl(posA, posB, seg_off, n, P, eps, min_pts, max_pos, labels_out, ws, ws_bytes,
+                        (cudaStream_t)stream, false, status_accum);
 }
 
 int tdt_dbscan_main(const int32_t *x, const int32_t *y, int64_t n, int32_t eps, int32_t min_pts, int32_t max_pos,

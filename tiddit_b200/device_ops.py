@@ -28,10 +28,12 @@ def check_min_pts(m, n):
 # ---------------------------------------------------------------------------------------------
 # clustering
 # ---------------------------------------------------------------------------------------------
-def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_out=None):
+def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_out=None, status=None):
     """All (chrA,chrB) segments in one call; int32 CUDA tensors in, int32 CUDA labels (insertion order) out.
 
-    Replaces tiddit_cluster.pyx:140-160 + DBSCAN.py:125-129.  seg_off: int64 CUDA tensor of P+1 offsets."""
+    Replaces tiddit_cluster.pyx:140-160 + DBSCAN.py:125-129.  seg_off: int64 CUDA tensor of P+1 offsets.
+    status: optional one-element int32 CUDA tensor (zeroed by the caller); when given, nothing synchronises and a
+    data error shows up there as a positive code (check it with `check_async_status`)."""
     torch = _lib.torch_cuda()
     L = _lib.lib()
     n = int(posA.numel())
@@ -43,10 +45,23 @@ def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_
     need = L.tdt_cluster_workspace_bytes(n, int(P))
     ws = _lib.workspace(torch, need)
     st = _lib.stream_ptr(torch)
-    rc = L.tdt_cluster_labels(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(seg_off), n, int(P), eps_to_int(epsilon),
-                              int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws), ws.numel(), st)
+    if status is not None:
+        rc = L.tdt_cluster_labels_async(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(seg_off), n, int(P),
+                                        eps_to_int(epsilon), int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws),
+                                        ws.numel(), _lib.ptr(status), st)
+    else:
+        rc = L.tdt_cluster_labels(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(seg_off), n, int(P), eps_to_int(epsilon),
+                                  int(m), int(max_pos), _lib.ptr(labels_out), _lib.ptr(ws), ws.numel(), st)
     _lib.check(rc)
     return labels_out
+
+
+def check_async_status(code):
+    """Raise what the synchronous call would have returned for a status word of tdt_cluster_labels_async."""
+    if code:
+        what = {1: "a posA / x coordinate is negative or above max_pos",
+                2: "a posB / y coordinate is negative or above max_pos"}.get(int(code), "a pair / cluster id is outside its range")
+        raise _lib.TdtError(_lib.TDT_E_RANGE, what)
 
 
 def cluster_labels(posA, posB, seg_off, epsilon, m, max_pos=0):

@@ -12,27 +12,65 @@ import numpy as np
 from . import _lib, device_ops
 
 
-def plan_chunks(seg_off, n_chunks):
-    """Contiguous pair ranges with roughly equal signal counts -> list of (p0, p1)."""
+def plan_chunks(seg_off, n_chunks, taper=1.0):
+    """Contiguous pair ranges -> list of (p0, p1).  taper = 1: roughly equal signal counts; taper < 1: the last
+    chunk gets about `taper` times the signals of the first (a short last chunk means a short pipeline tail)."""
     seg_off = np.asarray(seg_off, dtype=np.int64)
     P = len(seg_off) - 1
     n = int(seg_off[-1])
     if P <= 0:
         return []
     n_chunks = max(1, min(n_chunks, P))
+    w = np.linspace(1.0, taper, n_chunks)
+    frac = np.concatenate([[0.0], np.cumsum(w) / w.sum()])
     cuts = [0]
     for k in range(1, n_chunks):
-        p = int(np.searchsorted(seg_off, n * k / n_chunks, side="left"))
+        p = int(np.searchsorted(seg_off, n * frac[k], side="left"))
         p = min(max(p, cuts[-1] + 1), P - (n_chunks - k))
         cuts.append(p)
     cuts.append(P)
     return [(cuts[i], cuts[i + 1]) for i in range(n_chunks) if cuts[i + 1] > cuts[i]]
 
 
-class HostPipeline:
-    """Reusable buffers + streams for clustering host-resident signal sets of up to n_max signals."""
+class GraphRunner:
+    """One device-resident clustering call (fixed buffers, fixed shape) captured into a CUDA graph: replay() runs
+    the ~40 kernels / memsets of the call without per-launch host latency.  For callers that cluster the same
+    buffers repeatedly (benchmarks, streaming windows of equal size)."""
 
-    def __init__(self, n_max, n_chunks=8):
+    def __init__(self, posA, posB, seg_off, P, epsilon, m, max_pos, labels_out):
+        torch = _lib.torch_cuda()
+        self.torch = torch
+        self.status = torch.zeros(1, dtype=torch.int32, device=posA.device)
+        self.labels = labels_out
+        args = (posA, posB, seg_off, P, epsilon, m, max_pos)
+        self.stream = torch.cuda.Stream()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):   # warm-up: kernel attributes, workspace
+            device_ops.cluster_labels_device(*args, labels_out=labels_out, status=self.status)
+        self.stream.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph, stream=self.stream):
+            device_ops.cluster_labels_device(*args, labels_out=labels_out, status=self.status)
+
+    def replay(self):
+        """Enqueue the captured call on the current stream; labels land in the buffer given at construction."""
+        self.graph.replay()
+        return self.labels
+
+    def check(self):
+        """Synchronise and raise if any replay since construction saw out-of-range coordinates."""
+        device_ops.check_async_status(int(self.status.item()))
+
+
+class HostPipeline:
+    """Reusable buffers + streams for clustering host-resident signal sets of up to n_max signals.
+
+    Nothing on the GPU side waits for the host: every chunk's ~40 kernels and memsets go through the asynchronous
+    ABI call, captured once per chunk shape into a CUDA graph and replayed (a chunk is launch-bound otherwise);
+    inputs travel on one copy stream in chunk order, labels return on another, and the host synchronises once
+    at the end.  Chunks taper (the last is the smallest) so little work is left when the last input arrives."""
+
+    def __init__(self, n_max, n_chunks=8, p_max=1 << 16, taper=0.25, use_graphs=True):
         torch = _lib.torch_cuda()
         self.torch = torch
         self.n_max = int(n_max)
@@ -40,7 +78,17 @@ class HostPipeline:
         self.a_d = torch.empty(self.n_max, dtype=torch.int32, device="cuda")
         self.b_d = torch.empty(self.n_max, dtype=torch.int32, device="cuda")
         self.lab_d = torch.empty(self.n_max, dtype=torch.int32, device="cuda")
+        self.off_pin = torch.empty(p_max + 2 * self.n_chunks + 2, dtype=torch.int64).pin_memory()
+        self.off_d = torch.empty_like(self.off_pin, device="cuda")
+        self.status_d = torch.zeros(1, dtype=torch.int32, device="cuda")
+        self.status_pin = torch.zeros(1, dtype=torch.int32).pin_memory()
+        self.taper = float(taper)
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
+        self._events = [[torch.cuda.Event() for _ in range(3)] for _ in range(self.n_chunks)]
+        L = _lib.lib()
+        _lib.workspace(torch, L.tdt_cluster_workspace_bytes(self.n_max, min(p_max, self.n_max + 1)))
 
     def run(self, posA, posB, seg_off, epsilon, m, max_pos, out):
         """posA / posB / out: pinned CPU int32 tensors; seg_off: numpy int64 (P+1).  Returns `out` (filled when the
@@ -51,38 +99,74 @@ class HostPipeline:
             raise ValueError("HostPipeline sized for %d signals, got %d" % (self.n_max, n))
         device_ops.check_min_pts(m, n)
         seg_off = np.asarray(seg_off, dtype=np.int64)
-        chunks = plan_chunks(seg_off, self.n_chunks)
-        offs = [torch.from_numpy(seg_off[p0:p1 + 1] - seg_off[p0]).pin_memory() for p0, p1 in chunks]
+        chunks = plan_chunks(seg_off, self.n_chunks, self.taper)
+        if len(seg_off) + 2 * len(chunks) > self.off_pin.numel():
+            raise ValueError("HostPipeline sized for %d pairs" % (self.off_pin.numel() - 2 * self.n_chunks - 2))
+        # chunk-relative offsets, back to back in one pinned buffer -> one small copy
+        views, pos = [], 0
+        off_np = self.off_pin.numpy()
+        for p0, p1 in chunks:
+            k = p1 - p0 + 1
+            off_np[pos:pos + k] = seg_off[p0:p1 + 1] - seg_off[p0]
+            views.append((pos, k))
+            pos += k
         cur = torch.cuda.current_stream()
         for s in (self.s_in, self.s_run, self.s_out):
             s.wait_stream(cur)
-        ready, done, offs_d = [], [], []
         with torch.cuda.stream(self.s_in):
-            for (p0, p1), off in zip(chunks, offs):
+            self.off_d[:pos].copy_(self.off_pin[:pos], non_blocking=True)
+            self.status_d.zero_()
+            for k, (p0, p1) in enumerate(chunks):
                 lo, hi = int(seg_off[p0]), int(seg_off[p1])
                 self.a_d[lo:hi].copy_(posA[lo:hi], non_blocking=True)
                 self.b_d[lo:hi].copy_(posB[lo:hi], non_blocking=True)
-                offs_d.append(off.cuda(non_blocking=True))
-                ev = torch.cuda.Event()
-                ev.record(self.s_in)
-                ready.append(ev)
+                self._events[k][0].record(self.s_in)
         for k, (p0, p1) in enumerate(chunks):
             lo, hi = int(seg_off[p0]), int(seg_off[p1])
-            with torch.cuda.stream(self.s_run):
-                self.s_run.wait_event(ready[k])
-                if hi > lo:
-                    device_ops.cluster_labels_device(self.a_d[lo:hi], self.b_d[lo:hi], offs_d[k], p1 - p0, epsilon, m,
-                                                     max_pos, labels_out=self.lab_d[lo:hi])
-                ev = torch.cuda.Event()
-                ev.record(self.s_run)
-                done.append(ev)
+            ev_in, _, ev_done = self._events[k]
+            o0, ok = views[k]
+            self.s_run.wait_event(ev_in)
+            if hi > lo:
+                self._launch_chunk(lo, hi, o0, ok, p1 - p0, epsilon, m, max_pos)
+            ev_done.record(self.s_run)
             with torch.cuda.stream(self.s_out):
-                self.s_out.wait_event(done[k])
+                self.s_out.wait_event(ev_done)
                 out[lo:hi].copy_(self.lab_d[lo:hi], non_blocking=True)
+        with torch.cuda.stream(self.s_out):
+            self.status_pin.copy_(self.status_d, non_blocking=True)
         cur.wait_stream(self.s_out)
-        cur.wait_stream(self.s_run)
         self.s_out.synchronize()
+        device_ops.check_async_status(int(self.status_pin[0]))
         return out
+
+
+    def _chunk_call(self, lo, hi, o0, ok, P, epsilon, m, max_pos):
+        device_ops.cluster_labels_device(self.a_d[lo:hi], self.b_d[lo:hi], self.off_d[o0:o0 + ok], P, epsilon, m,
+                                         max_pos, labels_out=self.lab_d[lo:hi], status=self.status_d)
+
+    def _launch_chunk(self, lo, hi, o0, ok, P, epsilon, m, max_pos):
+        torch = self.torch
+        if not self.use_graphs:
+            with torch.cuda.stream(self.s_run):
+                self._chunk_call(lo, hi, o0, ok, P, epsilon, m, max_pos)
+            return
+        key = (lo, hi, o0, ok, P, device_ops.eps_to_int(epsilon), int(m), int(max_pos))
+        graph = self._graphs.get(key)
+        if graph is None:
+            # first time for this chunk shape: run it eagerly (the result of this call), then capture it for later
+            # calls; everything the call touches (buffers, workspace, offsets) lives as long as this object
+            with torch.cuda.stream(self.s_run):
+                self._chunk_call(lo, hi, o0, ok, P, epsilon, m, max_pos)
+            self.s_run.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=self.s_run):
+                self._chunk_call(lo, hi, o0, ok, P, epsilon, m, max_pos)
+            if len(self._graphs) > 256:
+                self._graphs.clear()
+            self._graphs[key] = graph
+            return
+        with torch.cuda.stream(self.s_run):
+            graph.replay()
 
 
 # ---------------------------------------------------------------------------------------------
