@@ -211,6 +211,21 @@ def run_reference(args):
 # ---------------------------------------------------------------------------------------------------
 # coverage leg (N = 1)
 # ---------------------------------------------------------------------------------------------------
+def ncu_traffic(kernel, note_only=False):
+    """DRAM bytes per launch of `kernel` from the newest committed ncu --set full summary (profiles/*_traffic.json)."""
+    import glob
+    files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
+    if not files:
+        return None
+    rec = json.load(open(files[-1])).get(kernel)
+    if rec is None:
+        return None
+    if note_only:
+        return "%s: %.1f MB per launch in the profiled (61.8M-read) shape" % (os.path.basename(files[-1]),
+                                                                             rec["first_launch_bytes"] / 1e6)
+    return rec["first_launch_bytes"]
+
+
 def coverage_leg(torch, args, hbm_peak, flush):
     from tiddit_b200 import device_ops, synth, _lib
     lens = np.array([ln for _, ln in synth.GRCH38], dtype=np.int64)
@@ -222,9 +237,8 @@ def coverage_leg(torch, args, hbm_peak, flush):
     g.manual_seed(7)
     starts, ends = [], []
     for ln, k in zip(lens, per):                       # coordinate-sorted per contig, like a BAM
-        s = torch.sort((torch.rand(int(k), device="cuda", generator=g, dtype=torch.float64) * int(ln)).to(torch.int32)).values
-        starts.append(s)
-        ends.append(torch.clamp(s + 150, max=int(ln)))
+        starts.append(synth.sorted_starts_device(torch, int(k), int(ln), g))
+        ends.append(torch.clamp(starts[-1] + 150, max=int(ln)))
     start, end = torch.cat(starts), torch.cat(ends)
     del starts, ends
     nb = np.ceil(lens / float(z)).astype(np.int64)
@@ -253,6 +267,7 @@ def coverage_leg(torch, args, hbm_peak, flush):
            "bins_per_sec": n_bins / ms * 1e3, "mean_coverage": mean_cov,
            "roofline": {"bound": "hbm", "achieved": alg_bytes / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                         "frac": alg_bytes / ms / 1e6 / hbm_peak, "traffic": None, "kernel": "coverage_kernel",
+                        "traffic_note": ncu_traffic("coverage_kernel<1>", note_only=True),
                         "algorithmic_bytes": "8 B/read + 8 B/bin"}}
     if args.no_cpu:
         return out
@@ -429,12 +444,25 @@ def main():
     tot_stage = sum(stage_ms.values()) or 1.0
     k_ms = stage_ms.get("window_runs_x", float("nan"))
     alg = 8.0 * n_mine
+    n_pass = (max(int(L), 1).bit_length() + 7) // 8
+    sx_ms = stage_ms.get("sort_x", float("nan"))
+    sort_bytes = (4.0 + 16.0 * n_pass) * n_mine
+    same_shape = world == 1 and args.workload == "wgs30x" and not args.signals   # the shape the ncu capture was taken on
     roofline = {"bound": "hbm", "kernel": "window_runs_small_kernel<X> (eps-range query + run labelling, posA axis)",
                 "achieved": alg / k_ms / 1e6, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
-                "frac": alg / k_ms / 1e6 / hbm_peak, "traffic": None,
+                "frac": alg / k_ms / 1e6 / hbm_peak,
+                "traffic": ncu_traffic("window_runs_small_kernel<0>") if same_shape else None,
+                "traffic_source": "profiles/*_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of this kernel's "
+                                  "launch in the committed ncu --set full capture of the same 20M-signal set",
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": k_ms,
                 "share_of_step": k_ms / tot_stage,
                 "stages_ms": {k: round(v, 4) for k, v in stage_ms.items()},
+                "largest_stage": {"name": "sort_x (segmented radix sort of posA: histogram + %d passes)" % n_pass,
+                                  "ms": sx_ms, "share_of_step": sx_ms / tot_stage,
+                                  "bytes_moved": sort_bytes, "achieved": sort_bytes / sx_ms / 1e6,
+                                  "frac": sort_bytes / sx_ms / 1e6 / hbm_peak,
+                                  "note": "implementation traffic (4 B/key histogram read + 16 B/element per pass), "
+                                          "not algorithmic bytes"},
                 "pipeline": {"algorithmic_bytes": 12.0 * n_mine, "achieved": 12.0 * n_mine / ms_step / 1e6,
                              "frac": 12.0 * n_mine / ms_step / 1e6 / hbm_peak}}
 

@@ -118,6 +118,17 @@ def coverage_reads(n_reads, seed=7, contigs=GRCH38, read_len=150):
     return np.concatenate(starts), np.concatenate(ends), np.array(off, dtype=np.int64), lens
 
 
+def sorted_starts_device(torch, k, ln, generator=None):
+    """k sorted uniform read starts in [0, ln) generated ON the device without a sort: normalised running sums of
+    exponential gaps are distributed exactly like the order statistics of k uniforms (bench / profiling input only)."""
+    if k <= 0:
+        return torch.empty(0, dtype=torch.int32, device="cuda")
+    gaps = -torch.log1p(-torch.rand(k + 1, device="cuda", generator=generator, dtype=torch.float64))
+    c = torch.cumsum(gaps, 0)
+    s = torch.floor(c[:k] * (float(ln) / float(c[k]))).clamp_(0, ln - 1)
+    return s.to(torch.int32)
+
+
 def fasta_sequence(length, seed=9, gc=0.41):
     """uint8 bases: i.i.d. with `gc` GC content, half soft-masked in blocks of 300-3000 bp, one N block in the
     middle (3 % of the contig, <= 3 Mbp) and 10 kb (<= 1 %) N telomeres."""

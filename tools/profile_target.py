@@ -19,8 +19,7 @@ torch.cuda.synchronize()
 lens = np.array([ln for _, ln in synth.GRCH38], dtype=np.int64)
 n_reads = 61_765_396
 per = np.floor(n_reads * lens / lens.sum()).astype(np.int64)
-starts = [torch.sort((torch.rand(int(k), device="cuda", dtype=torch.float64) * int(ln)).to(torch.int32)).values
-          for ln, k in zip(lens, per)]
+starts = [synth.sorted_starts_device(torch, int(k), int(ln)) for ln, k in zip(lens, per)]
 start = torch.cat(starts)
 end = torch.cat([torch.clamp(s + 150, max=int(ln)) for s, ln in zip(starts, lens)])
 nb = np.ceil(lens / 500.0).astype(np.int64)
