@@ -158,3 +158,43 @@ def test_coverage_weird_reads_and_alignment(oracle):
         device_ops.coverage_accumulate_device(sd, ed, z, ebs, got, bad)
         assert int(bad.item()) == device_ops.FIRST_BAD_NONE
         assert np.array_equal(got.cpu().numpy().view(np.uint64), want.view(np.uint64)), z
+
+
+@pytest.mark.parametrize("z", [500, 50, 4096, 5000])
+def test_coverage_contigs_call_tile_paths(z, oracle):
+    """The all-contig ABI call on a read set whose 8192-read tiles are mostly inside one contig (fast tiles), straddle
+    contig boundaries, cover whole tiny contigs, and pile reads onto the last (short) bin of every contig."""
+    import torch
+    from tiddit_b200 import device_ops
+    rng = np.random.default_rng(z)
+    lens = [1_000_003, 700, 2_500_000, 8191 * 3, 123_457, 1, 3_000_000]
+    counts = [120_000, 300, 90_000, 8192, 30_000, 5, 150_000]
+    ss, ee, want, ebs_l, nb_l = [], [], [], [], []
+    for ln, k in zip(lens, counts):
+        s = rng.integers(0, ln, k)
+        s[: k // 10] = ln - 1 - rng.integers(0, min(ln, 2 * z), k // 10)      # crowd the contig end
+        s = np.sort(s)
+        e = np.minimum(s + rng.integers(1, 301, k), ln)
+        nb = -(-ln // z)
+        ebs = ln - (nb - 1) * z
+        w = np.zeros(nb)
+        oracle.update_coverage_batch(s, e, z, w, ebs)
+        ss.append(s); ee.append(e); want.append(w); ebs_l.append(ebs); nb_l.append(nb)
+    start = torch.from_numpy(np.concatenate(ss).astype(np.int32)).cuda()
+    end = torch.from_numpy(np.concatenate(ee).astype(np.int32)).cuda()
+    read_off = torch.from_numpy(np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)).cuda()
+    bin_off = torch.from_numpy(np.concatenate([[0], np.cumsum(nb_l)]).astype(np.int64)).cuda()
+    ebs_d = torch.tensor(ebs_l, dtype=torch.int32, device="cuda")
+    bins = torch.zeros(int(sum(nb_l)), dtype=torch.float64, device="cuda")
+    bad = device_ops.new_first_bad(torch)
+    device_ops.coverage_accumulate_contigs_device(start, end, read_off, bin_off, ebs_d, z, bins, bad)
+    assert int(bad.item()) == device_ops.FIRST_BAD_NONE
+    got = bins.cpu().numpy()
+    assert np.array_equal(got.view(np.uint64), np.concatenate(want).view(np.uint64))
+    # a read past its contig's end is reported (IndexError in the reference), everything else still lands
+    end2 = end.clone()
+    k_bad = int(counts[0]) - 1
+    end2[k_bad] = lens[0] + 2 * z
+    bins.zero_()
+    device_ops.coverage_accumulate_contigs_device(start, end2, read_off, bin_off, ebs_d, z, bins, bad)
+    assert int(bad.item()) == k_bad

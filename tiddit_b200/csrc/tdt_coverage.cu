@@ -6,6 +6,11 @@
 // the bin totals stay far below 2^53 of it, so float64 sums are exact in ANY order: per-thread
 // pre-aggregation + RED.ADD.F64 into HBM is bit-identical to the reference's sequential `+=`.
 //
+// Fast tiles (full tile, one contig, table-sized bin -- all but ~25 tiles of a genome): every thread anchors a
+// window of two adjacent bins at its lowest read and tests each read against it with two subtractions and
+// unsigned compares -- no division; both addends are table look-ups whose INDEX is selected (0 -> adds 0.0), so a
+// read costs ~25 instructions: two LDS.64 and two DADD.  A read outside the window flushes and re-anchors it.
+//
 // Layout of the work: a CTA stages 8192 reads (start[] and end[], 32 KB each) in shared memory with two 1-D TMA
 // bulk copies; every thread then walks its OWN 32 consecutive reads.  Reads arrive coordinate-sorted (BAM
 // order), so a run touches a handful of neighbouring bins: the thread keeps a window of two adjacent bins in
@@ -92,6 +97,105 @@ __device__ __noinline__ void cov_odd_read(int64_t rs, int64_t re, int32_t bin_si
     for (int64_t b = fb + 1; b < eb; b++) atomicAdd(bins + (b < 0 ? b + n_bins : b), 1.0);
 }
 
+// ---- fast tiles ------------------------------------------------------------------------------------------
+struct CovWin {      // two adjacent bins [cb, cb+1] of the contig, sums in registers
+    double s0, s1;
+    int32_t cb;
+    uint32_t lim;    // a read with (end-1) - cb*bin < lim stays inside the window: 2*bin, or bin when bin cb+1 is the
+                     // contig's last bin (its divisor differs, tiddit_coverage.pyx:66-69) or does not exist
+};
+
+struct CovGeom {
+    int32_t bin_size, n_bins, ebs;
+    uint32_t magic;
+    int magic_shift;
+    const double *q_table;
+    double *bins;    // bins of the tile's contig
+};
+
+__device__ __forceinline__ uint32_t cov_lim(int32_t cb, const CovGeom &g) {
+    return cb + 1 < g.n_bins - 1 ? 2u * (uint32_t)g.bin_size : (uint32_t)g.bin_size;
+}
+
+__device__ __forceinline__ void cov_win_flush(const CovWin &w, double *bins) {
+    if (w.s0 != 0.0) atomicAdd(bins + w.cb, w.s0);
+    if (w.s1 != 0.0) atomicAdd(bins + w.cb + 1, w.s1);
+}
+
+// a read that is not inside the window: flush, then the reference's arithmetic with the exact division and the
+// window re-anchored at the read's first bin
+__device__ __noinline__ CovWin cov_miss(CovWin w, int32_t rs, int32_t re, int64_t r, CovGeom g,
+                                        unsigned long long *first_bad) {
+    cov_win_flush(w, g.bins);
+    w.s0 = w.s1 = 0.0;
+    if (!(rs >= 0 && re > rs)) {
+        cov_odd_read(rs, re, g.bin_size, g.ebs, g.bins, g.n_bins, r, first_bad);
+        return w;
+    }
+    const int32_t fb = (int32_t)(((uint32_t)rs + __umulhi((uint32_t)rs, g.magic)) >> g.magic_shift);            // :50
+    const int32_t eb = (int32_t)(((uint32_t)(re - 1) + __umulhi((uint32_t)(re - 1), g.magic)) >> g.magic_shift);  // :51
+    if (eb >= g.n_bins) {  // boundscheck: IndexError in the reference
+        atomicMin(first_bad, (unsigned long long)r);
+        return w;
+    }
+    const bool same = eb == fb;
+    const int a1 = same ? re - rs : (fb + 1) * g.bin_size - rs;
+    const int a2 = same ? 0 : (re - 1) - eb * g.bin_size;
+    double v2 = g.q_table[a2];
+    if (!same && eb == g.n_bins - 1) v2 = (double)__fdiv_rn((float)a2, (float)g.ebs);
+    w.cb = fb;
+    w.lim = cov_lim(fb, g);
+    w.s0 = g.q_table[a1];
+    if (eb == fb + 1) {
+        w.s1 = v2;
+    } else if (eb > fb + 1) {
+        w.s1 = 1.0;
+        for (int32_t b = fb + 2; b < eb; b++) atomicAdd(g.bins + b, 1.0);
+        atomicAdd(g.bins + eb, v2);
+    }
+    return w;
+}
+
+__device__ __forceinline__ void cov_tile_fast(const int32_t *s_start, const int32_t *s_end, int64_t t0, const CovGeom &g,
+                                              unsigned long long *first_bad) {
+    const int t = threadIdx.x, lane = t & 31;
+    const uint32_t bin = (uint32_t)g.bin_size;
+    // anchor the window at the first bin of the thread's lowest read (reads are coordinate-sorted)
+    const int32_t rs0 = s_start[t * COV_RUN];
+    CovWin w;
+    w.s0 = w.s1 = 0.0;
+    w.cb = rs0 > 0 ? (int32_t)(((uint32_t)rs0 + __umulhi((uint32_t)rs0, g.magic)) >> g.magic_shift) : 0;
+    if (w.cb > g.n_bins - 1) w.cb = g.n_bins - 1;
+    w.lim = cov_lim(w.cb, g);
+    uint32_t wb = (uint32_t)w.cb * bin;
+    const int4 *S4 = (const int4 *)s_start + t * (COV_RUN / 4);
+    const int4 *E4 = (const int4 *)s_end + t * (COV_RUN / 4);
+#pragma unroll 2
+    for (int k4 = 0; k4 < COV_RUN / 4; k4++) {
+        // 16-byte shared loads, rotated by the lane so that the 8 lanes of a quarter warp hit 8 different bank groups
+        const int q = (k4 + lane) & (COV_RUN / 4 - 1);
+        const int4 S = S4[q], E = E4[q];
+        const int32_t rsv[4] = {S.x, S.y, S.z, S.w}, rev[4] = {E.x, E.y, E.z, E.w};
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int32_t rs = rsv[j], re = rev[j];
+            const uint32_t os = (uint32_t)rs - wb, oe = (uint32_t)re - 1u - wb;
+            if (os <= oe && oe < w.lim) {
+                const bool df = os >= bin, de = oe >= bin;        // in the window's second bin?
+                const uint32_t len = (uint32_t)(re - rs);
+                const uint32_t i0 = df ? 0u : (de ? bin - os : len);   // :56 / :61 -> bin cb
+                const uint32_t i1 = de ? (df ? len : oe - bin) : 0u;   // :56 / :63 -> bin cb+1   (q_table[0] = 0)
+                w.s0 += g.q_table[i0];
+                w.s1 += g.q_table[i1];
+            } else {
+                w = cov_miss(w, rs, re, t0 + t * COV_RUN + q * 4 + j, g, first_bad);
+                wb = (uint32_t)w.cb * bin;
+            }
+        }
+    }
+    cov_win_flush(w, g.bins);
+}
+
 template <bool MULTI>
 __global__ void __launch_bounds__(COV_THREADS) coverage_kernel(const int32_t *__restrict__ start,
                                                                const int32_t *__restrict__ end, int64_t n_reads,
@@ -141,6 +245,36 @@ __global__ void __launch_bounds__(COV_THREADS) coverage_kernel(const int32_t *__
                 s_end[i] = end[t0 + i];
             }
             __syncthreads();
+        }
+        bool fast = use_table && cnt == COV_TILE;
+        if (MULTI && fast && !(t0 >= c_first && t0 + cnt <= c_next)) {
+            // the contig of the tile's first read (the same look-up in every thread)
+            acc.flush();
+            int lo = 0, hi = cc.C;
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (cc.read_off[mid] <= t0) lo = mid; else hi = mid;
+            }
+            c_first = cc.read_off[lo];
+            c_next = cc.read_off[lo + 1];
+            const int64_t base = cc.bin_off[lo];
+            n_bins = (int32_t)(cc.bin_off[lo + 1] - base);
+            ebs = cc.end_bin_size[lo];
+            acc.bins = bins + base;
+            fast = t0 + cnt <= c_next;
+        }
+        if (fast && n_bins >= 1) {
+            CovGeom g;
+            g.bin_size = bin_size;
+            g.n_bins = n_bins;
+            g.ebs = ebs;
+            g.magic = magic;
+            g.magic_shift = magic_shift;
+            g.q_table = q_table;
+            g.bins = acc.bins;
+            cov_tile_fast(s_start, s_end, t0, g, first_bad);
+            __syncthreads();
+            continue;
         }
         // a thread walks its own COV_RUN consecutive reads (rotated by the lane so that the 32 lanes hit 32
         // different banks): its register window absorbs nearly all adds, and the lanes of a warp work COV_RUN
@@ -192,9 +326,9 @@ __global__ void __launch_bounds__(COV_THREADS) coverage_kernel(const int32_t *__
                 cov_odd_read(rs, re, bin_size, ebs, acc.bins, n_bins, r, first_bad);
             }
         }
+        acc.flush();
         __syncthreads();  // the tile is consumed: the next bulk copy may overwrite it
     }
-    acc.flush();
 }
 
 // n / d == (n + umulhi(n, magic)) >> shift for every 0 <= n < 2^31: Granlund-Montgomery with
