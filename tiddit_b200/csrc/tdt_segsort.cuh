@@ -23,7 +23,10 @@
 
 namespace tdt {
 
-constexpr int SS_THREADS = 256;            // large-segment kernels
+#ifndef TDT_SS_THREADS
+#define TDT_SS_THREADS 256
+#endif
+constexpr int SS_THREADS = TDT_SS_THREADS;  // large-segment kernels (>= 256: thread d owns digit d)
 constexpr int SS_WARPS = SS_THREADS / 32;
 constexpr int SS_TILE = 4096;
 constexpr int SS_CHUNKS = SS_TILE / SS_THREADS;  // 32-element chunks per warp per tile
@@ -189,7 +192,25 @@ __global__ void __launch_bounds__(256) segsort_tiny_kernel(SSArgs a) {
 // ---- stable ranking primitives ------------------------------------------------------------------------
 // lanes holding the same digit: every lane ORs its bit into the warp's mask word of that digit
 // (mm: this warp's 256 words, all zero on entry and on exit)
-__device__ __forceinline__ uint32_t ss_match(uint32_t *mm, uint32_t d, bool valid) {
+#ifndef TDT_SS_MATCH_BALLOT
+#define TDT_SS_MATCH_BALLOT 0   // measured on B200 (r01, posA sort of the 30X set): ballots 0.74 ms, atomicOr 0.65 ms
+#endif
+constexpr int SS_MM = TDT_SS_MATCH_BALLOT ? 0 : 1;  // per-warp match words only for the atomicOr variant
+__device__ __forceinline__ uint32_t ss_match(uint32_t *mm, uint32_t d, bool valid, int bits) {
+#if TDT_SS_MATCH_BALLOT
+    // one ballot per digit bit, intersected: no shared memory (an ATOMS.OR costs ~2 cycles per lane of the LSU pipe,
+    // which made the L1 pipe the limiter of the sort passes)
+    uint32_t peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+    for (int b = 0; b < 8; b++) {
+        if (b < bits) {
+            const bool bit = (d >> b) & 1u;
+            const uint32_t bal = __ballot_sync(0xffffffffu, bit);
+            peers &= bit ? bal : ~bal;
+        }
+    }
+    return valid ? peers : 0u;
+#else
     const int lane = threadIdx.x & 31;
     if (valid) atomicOr(&mm[d], 1u << lane);
     __syncwarp();
@@ -197,6 +218,7 @@ __device__ __forceinline__ uint32_t ss_match(uint32_t *mm, uint32_t d, bool vali
     __syncwarp();
     if (valid && (peers & lanemask_lt()) == 0u) mm[d] = 0u;
     return peers;
+#endif
 }
 
 // info word per element: [7:0] digit, [12:8] rank among the chunk's lanes with the same digit,
@@ -208,7 +230,7 @@ __device__ __forceinline__ uint32_t ss_info(uint32_t d, uint32_t peers) {
 // count phase: warp-private digit histograms of the warp's own run of the tile; info[] keeps the match result
 template <int CHUNKS, typename DigitFn>
 __device__ __forceinline__ void ss_count(int count, int epw, uint32_t *wh, uint32_t *mm, uint32_t (&info)[CHUNKS],
-                                         DigitFn digit) {
+                                         int bits, DigitFn digit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < CHUNKS; c++) {
@@ -217,7 +239,7 @@ __device__ __forceinline__ void ss_count(int count, int epw, uint32_t *wh, uint3
             const int e = warp * epw + c * 32 + lane;
             const bool valid = e < count;
             const uint32_t d = valid ? digit(e, c) : 0u;
-            const uint32_t peers = ss_match(mm, d, valid);
+            const uint32_t peers = ss_match(mm, d, valid, bits);
             if (valid) {
                 info[c] = ss_info(d, peers);
                 if ((peers & lanemask_lt()) == 0u) wh[d] += __popc(peers);
@@ -295,7 +317,7 @@ __device__ __forceinline__ void ss_digit_bases(uint32_t (*wh)[256], uint32_t *sc
 // segments together fill (at most) the shared-memory capacity, so the per-batch fixed costs are amortised.
 constexpr int SS_SCAN_WINDOWS = 512;  // windows examined per planning round
 constexpr int SS_BATCH_WINDOWS = 60;  // a batch spans < 2^16 element positions (16-bit relative starts)
-constexpr size_t SS_LOCAL_SMEM = (size_t)SS_LOCAL_CAP * (4 + 4 + 2) * 2 + (size_t)SS_LWARPS * 256 * 4 * 2 + 256 * 4 +
+constexpr size_t SS_LOCAL_SMEM = (size_t)SS_LOCAL_CAP * (4 + 4 + 2) * 2 + (size_t)SS_LWARPS * 256 * 4 * (1 + SS_MM) + 256 * 4 +
                                  (size_t)(SS_LOCAL_CAP + 2) * 2 * 2 + SS_SCAN_WINDOWS * 4 + 64;
 
 __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
@@ -311,7 +333,7 @@ __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
     Lid[0] = (uint16_t *)p; p += SS_LOCAL_CAP * 2;
     Lid[1] = (uint16_t *)p; p += SS_LOCAL_CAP * 2;
     uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += SS_LWARPS * 256 * 4;
-    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_LWARPS * 256 * 4;
+    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_MM * SS_LWARPS * 256 * 4;
     uint32_t *bin = (uint32_t *)p; p += 256 * 4;
     uint32_t *wcnt = (uint32_t *)p; p += SS_SCAN_WINDOWS * 4;
     uint16_t *sc_start = (uint16_t *)p; p += (SS_LOCAL_CAP + 2) * 2;  // compact start of every gathered segment
@@ -322,7 +344,8 @@ __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
 
     const int64_t n = a.dims[0];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < SS_LWARPS * 256; i += SS_LTHREADS) (&mm[0][0])[i] = 0u;
+    if (SS_MM)
+        for (int i = threadIdx.x; i < SS_LWARPS * 256; i += SS_LTHREADS) (&mm[0][0])[i] = 0u;
 
     const int64_t nwin = (n + SS_WINDOW - 1) / SS_WINDOW;
     const int64_t span = (nwin + gridDim.x - 1) / gridDim.x;
@@ -418,7 +441,7 @@ __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
                 const uint16_t *Lc = Lid[cur];
                 const int kb = a.key_bits, sh = 8 * pass;
                 uint32_t info[SS_LCHUNKS];
-                ss_count<SS_LCHUNKS>(count, epw, wh[warp], mm[warp], info, [&](int e, int) -> uint32_t {
+                ss_count<SS_LCHUNKS>(count, epw, wh[warp], mm[warp], info, 8, [&](int e, int) -> uint32_t {
                     const unsigned long long comp = ((unsigned long long)Lc[e] << kb) | (unsigned long long)Kc[e];
                     return (uint32_t)(comp >> sh) & 255u;
                 });
@@ -514,11 +537,17 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
-constexpr size_t SS_PASS_SMEM = (size_t)SS_TILE * 4 * 2 + (size_t)SS_WARPS * 256 * 4 * 2 + 256 * 4 + 256 * 8 + 64;
+constexpr size_t SS_PASS_SMEM = (size_t)SS_TILE * 4 * 2 + (size_t)SS_WARPS * 256 * 4 * (1 + SS_MM) + 256 * 4 + 256 * 8 + 64;
 
 // One pass over one tile.  Tiles are taken in blockIdx order (the chained scan waits only on tiles with a smaller
 // index, which the hardware has already scheduled -- the same forward-progress assumption as CUB's DeviceScan).
-__global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int pass, const uint32_t *src_k,
+#ifndef TDT_SS_LB
+#define TDT_SS_LB 4
+#endif
+#ifndef TDT_SS_PASS_MINBLOCKS
+#define TDT_SS_PASS_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pass_kernel(SSArgs a, int pass, const uint32_t *src_k,
                                                                   const int32_t *src_v, uint32_t *dst_k,
                                                                   int32_t *dst_v) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
@@ -526,7 +555,7 @@ __global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int 
     uint32_t *K2 = (uint32_t *)p; p += SS_TILE * 4;
     int32_t *V2 = (int32_t *)p; p += SS_TILE * 4;
     uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
-    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
+    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_MM * SS_WARPS * 256 * 4;
     uint32_t *bin = (uint32_t *)p; p += 256 * 4;
     int64_t *gbase = (int64_t *)p;
 
@@ -534,7 +563,7 @@ __global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int 
     if (tile >= a.L.cnt->n_tiles) return;
     for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) {
         (&wh[0][0])[i] = 0u;
-        (&mm[0][0])[i] = 0u;
+        if (SS_MM) (&mm[0][0])[i] = 0u;
     }
     const int seg = a.L.tile_seg[tile];
     const SSLarge L = a.L.large[seg];
@@ -560,39 +589,54 @@ __global__ void __launch_bounds__(SS_THREADS) segsort_pass_kernel(SSArgs a, int 
     }
     __syncthreads();
     uint32_t info[SS_CHUNKS];
-    ss_count<SS_CHUNKS>(cnt, epw, wh[warp], mm[warp], info,
+    ss_count<SS_CHUNKS>(cnt, epw, wh[warp], mm[warp], info, bits,
                         [&](int, int c) -> uint32_t { return ss_digit(key[c], pass, bits); });
     __syncthreads();
     uint32_t total, excl;
     ss_digit_bases<SS_WARPS>(wh, bin, total, excl);
-    {   // per-digit chained scan over the earlier tiles of this segment (thread = digit)
-        const int d = threadIdx.x;
-        const uint32_t epoch = (uint32_t)pass + 1u;
-        uint32_t *row = a.L.status + (size_t)tile * 256 + d;
-        uint32_t before = 0;
-        if (lt == 0) {
-            st_volatile_u32(row, ss_pack(2u, epoch, total));
-        } else {
-            st_volatile_u32(row, ss_pack(1u, epoch, total));
-            for (int t = tile - 1;; t--) {
-                const uint32_t *prow = a.L.status + (size_t)t * 256 + d;
-                uint32_t s;
-                do {
-                    s = ld_volatile_u32(prow);
-                } while ((s >> 30) == 0u || ((s >> 26) & 15u) != epoch);
-                before += s & 0x3ffffffu;
-                if ((s >> 30) == 2u) break;
-            }
-            st_volatile_u32(row, ss_pack(2u, epoch, before + total));
-        }
-        const uint32_t gh = a.L.ghist[((size_t)seg * SS_MAX_PASSES + pass) * 256 + d];
-        gbase[d] = L.start + (int64_t)gh + (int64_t)before - (int64_t)excl;
+    // per-digit chained scan over the earlier tiles of this segment (thread = digit), in two halves: the tile's
+    // digit totals are published first, the walk over the predecessors happens AFTER the shared-memory scatter,
+    // when more of them hold a complete prefix (the walk was ~30 % of the pass when it came first)
+    const uint32_t epoch = (uint32_t)pass + 1u;
+    uint32_t *row = a.L.status + (size_t)tile * 256 + threadIdx.x;
+    const bool live = threadIdx.x < (1u << bits);  // digits that exist in this pass
+    uint32_t gh = 0;
+    if (live) {
+        st_volatile_u32(row, ss_pack(lt == 0 ? 2u : 1u, epoch, total));
+        gh = a.L.ghist[((size_t)seg * SS_MAX_PASSES + pass) * 256 + threadIdx.x];
     }
-    __syncthreads();
+    __syncthreads();  // wh holds every warp's digit bases
     ss_scatter<SS_CHUNKS>(epw, wh[warp], info, [&](int, int c, uint32_t pos) {
         K2[pos] = key[c];
         V2[pos] = val[c];
     });
+    {
+        uint32_t before = 0;
+        if (lt != 0 && live) {
+            constexpr int LB = TDT_SS_LB;  // predecessors inspected per round trip
+            const uint32_t *prow = row - 256;
+            int left = lt;  // tiles of this segment before this one
+            bool done = false;
+            while (!done) {
+                uint32_t sv[LB];
+#pragma unroll
+                for (int i = 0; i < LB; i++) sv[i] = i < left ? ld_volatile_u32(prow - (size_t)i * 256) : 0u;
+#pragma unroll
+                for (int i = 0; i < LB; i++) {
+                    if (!done && i < left) {
+                        uint32_t s = sv[i];
+                        while ((s >> 30) == 0u || ((s >> 26) & 15u) != epoch) s = ld_volatile_u32(prow - (size_t)i * 256);
+                        before += s & 0x3ffffffu;
+                        done = (s >> 30) == 2u;
+                    }
+                }
+                prow -= (size_t)LB * 256;
+                left -= LB;
+            }
+            st_volatile_u32(row, ss_pack(2u, epoch, before + total));
+        }
+        if (threadIdx.x < 256) gbase[threadIdx.x] = L.start + (int64_t)gh + (int64_t)before - (int64_t)excl;
+    }
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += SS_THREADS) {
         const uint32_t k = K2[i];
