@@ -92,6 +92,47 @@ TDT_API int tdt_ypass_labels(const int32_t *y, int64_t n, int32_t eps, int32_t m
                      int32_t *labels_io, int32_t *cluster_id_io, void *ws, size_t ws_bytes, void *stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Candidate aggregation.  Replaces tiddit/tiddit_cluster.pyx:156-254 (labels folded into candidates, signal by
+ * signal) and :258-336 (per-candidate N_discordants / N_splits / N_contigs, posA / posB, startA / endA / startB /
+ * endB) for ALL pairs in one call.  Per-signal inputs are the reference's records (:72,101,134) as
+ * struct-of-arrays in insertion order, pairs back to back like tdt_cluster_labels:
+ *   labels   the output of tdt_cluster_labels;  posA/posB  int(rec[3]) / int(rec[5]) (0 <= pos <= max_pos < 2^30)
+ *   span     [n][4] = rec[8..11] (startA, endA, startB, endB), 16-byte aligned
+ *   name_id  equal ids <=> equal read names (0 <= id <= n_names < 2^30; n_names = 0: unknown)
+ *   flags    TDT_SIG_* bits;  same_chrom[P]  1 if chrA == chrB
+ * Noise (-1) survives only as an intra-chromosomal assembly contig with posB - posA < 2*max_ins_len, as a
+ * singleton candidate with id len(pair) + k (:162-168).
+ * Outputs (caller-owned, sized for the worst case n):
+ *   cand_out[c][TDT_CAND_COLS]  one row per candidate, rows in the reference's dict insertion order (pair by
+ *                               pair, candidates by first appearance): TDT_CAND_* columns
+ *   member_idx_out[n]           signal indices grouped by candidate: the members of row c are
+ *                               member_idx_out[row[MEMBER_OFF] .. + row[SIZE]) in insertion order
+ *   counts_out[4] (int64)       {candidates, signals kept, data error (0 = none), 0}
+ * Does not synchronise.  Workspace: tdt_aggregate_workspace_bytes(n, P).
+ * ------------------------------------------------------------------------------------------ */
+#define TDT_SIG_KIND_MASK 0x03 /* 0 = discordant pair ("D"), 1 = split read ("S"), 2 = assembly contig ("A") */
+#define TDT_SIG_A_TRUE 0x04    /* orientation string of side A (rec[4]) == "True"  */
+#define TDT_SIG_A_FALSE 0x08   /*                                        == "False" */
+#define TDT_SIG_B_TRUE 0x10    /* rec[6] == "True"  */
+#define TDT_SIG_B_FALSE 0x20   /* rec[6] == "False" */
+#define TDT_CAND_COLS 16
+enum {
+    TDT_CAND_PAIR = 0, TDT_CAND_ID = 1, TDT_CAND_FIRST = 2, TDT_CAND_MEMBER_OFF = 3, TDT_CAND_SIZE = 4,
+    TDT_CAND_N_DISCORDANTS = 5, TDT_CAND_N_SPLITS = 6, TDT_CAND_N_CONTIGS = 7, TDT_CAND_POSA = 8, TDT_CAND_POSB = 9,
+    TDT_CAND_STARTA = 10, TDT_CAND_ENDA = 11, TDT_CAND_STARTB = 12, TDT_CAND_ENDB = 13,
+    TDT_CAND_RULE = 14 /* 0 splits >= min_reads, 1 contigs, 2 splits, 3 discordants by orientation, 4 by mode */
+};
+
+TDT_API size_t tdt_aggregate_workspace_bytes(int64_t n, int32_t P);
+
+TDT_API int tdt_cluster_aggregate(const int32_t *labels, const int32_t *posA, const int32_t *posB, const int32_t *span,
+                                  const int32_t *name_id, const uint8_t *flags, const int64_t *seg_off,
+                                  const uint8_t *same_chrom, int64_t n, int32_t P, int32_t max_ins_len, int32_t is_mp,
+                                  int32_t min_reads, int32_t max_pos, int32_t n_names, int32_t *cand_out,
+                                  int32_t *member_idx_out, int64_t *counts_out, void *ws, size_t ws_bytes,
+                                  void *stream);
+
+/* --------------------------------------------------------------------------------------------
  * Coverage.  Replaces tiddit/tiddit_coverage.pyx:48-74 (update_coverage) applied to a batch of
  * reads: bins[] (float64) is accumulated IN PLACE (the reference's `+=`).  Every addend is the
  * float32 quotient the reference computes, all partial sums are exact in float64, so the result is

@@ -46,6 +46,10 @@ def lib():
         L.tdt_oracle_gc.restype = ctypes.c_int64
         L.tdt_oracle_gc.argtypes = [ctypes.POINTER(ctypes.c_uint8), ctypes.c_int64, ctypes.c_int32,
                                     ctypes.c_double, ctypes.POINTER(ctypes.c_int8)]
+        u8p = ctypes.POINTER(ctypes.c_uint8)
+        L.tdt_oracle_aggregate.restype = ctypes.c_int64
+        L.tdt_oracle_aggregate.argtypes = [i32p, i32p, i32p, i32p, i32p, u8p, i64p, u8p, ctypes.c_int64, ctypes.c_int32,
+                                           ctypes.c_int32, ctypes.c_int32, i32p, i32p, i64p]
         _lib = L
     return _lib
 
@@ -107,6 +111,26 @@ def cluster_segments(posA, posB, seg_off, epsilon, m):
     if rc == -2:
         raise ValueError("max() arg is an empty sequence")
     return out
+
+
+def cluster_aggregate(labels, posA, posB, span, name_id, flags, seg_off, same_chrom, max_ins_len, is_mp, min_reads,
+                      max_pos=0, n_names=0):
+    """tiddit_cluster.pyx:156-336 on packed arrays -> (rows int32 [C,16] in dict insertion order, member_idx [M]);
+    same contract as tiddit_b200.device_ops.cluster_aggregate."""
+    c = lambda a, t: np.ascontiguousarray(a, dtype=t)
+    labels, posA, posB, name_id = c(labels, np.int32), c(posA, np.int32), c(posB, np.int32), c(name_id, np.int32)
+    span = c(span, np.int32).reshape(-1, 4)
+    flags, same_chrom, seg_off = c(flags, np.uint8), c(same_chrom, np.uint8), c(seg_off, np.int64)
+    n = len(labels)
+    rows = np.zeros((max(n, 1), 16), dtype=np.int32)
+    mem = np.zeros(max(n, 1), dtype=np.int32)
+    kept = np.zeros(1, dtype=np.int64)
+    C = lib().tdt_oracle_aggregate(_p(labels, ctypes.c_int32), _p(posA, ctypes.c_int32), _p(posB, ctypes.c_int32),
+                                   _p(span, ctypes.c_int32), _p(name_id, ctypes.c_int32), _p(flags, ctypes.c_uint8),
+                                   _p(seg_off, ctypes.c_int64), _p(same_chrom, ctypes.c_uint8), len(seg_off) - 1,
+                                   int(max_ins_len), int(bool(is_mp)), int(min_reads), _p(rows, ctypes.c_int32),
+                                   _p(mem, ctypes.c_int32), _p(kept, ctypes.c_int64))
+    return rows[:C].copy(), mem[:int(kept[0])].copy()
 
 
 def create_coverage(bam_header, bin_size, c="all"):

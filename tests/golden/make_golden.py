@@ -242,10 +242,101 @@ def config1_cov():
             cov.print_coverage(coverage_data, header, z, "wig", os.path.join(HERE, "config1_z%d_q%d.wig" % (z, q)))
 
 
+def aggregate_cases():
+    """Candidate aggregation (tiddit_cluster.pyx:156-336): random tab files written to a scratch directory, the REAL
+    tiddit_cluster.main run on them, and per case the packed arrays (our reader, itself pinned by cluster_cases) +
+    the reference's labels + one expected numeric row per candidate in dict order.  Scenarios are built to reach every
+    branch of :265-330 (splits >= min_reads, contigs, few splits, discordants by orientation in PE and MP libraries,
+    discordants by mode) with ties in the modes and repeated read names."""
+    import tempfile
+    from tiddit_b200.signals import PackedSignals
+    contigs = {"chr1": 90000, "chr2": 70000, "chr3": 40000, "chrX": 52000, "small": 800}
+    names = list(contigs)
+    rng = np.random.default_rng(77)
+    out = {}
+    scenarios = []
+    for k in range(14):
+        scenarios.append(dict(samples=["S1"] if k % 3 else ["S1", "S2"], is_mp=bool(k % 2), skip_assembly=(k % 5 == 4),
+                              eps=int(rng.integers(100, 600)), m=int(rng.integers(2, 6)), min_reads=int(rng.integers(1, 7)),
+                              n_disc=int(rng.integers(200, 900)), n_split=int(rng.integers(0, 400)) if k % 4 else 0,
+                              n_ctg=int(rng.integers(0, 60)) if k % 3 == 0 else 0, jitter=int(rng.choice([2, 30, 120])),
+                              max_ins_len=int(rng.integers(200, 600))))
+    tmp = tempfile.mkdtemp(prefix="tdt_agg_")
+    for case, sc in enumerate(scenarios):
+        prefix = os.path.join(tmp, "case%d" % case)
+        os.makedirs(prefix + "_tiddit")
+        centres = []
+        for _ in range(int(rng.integers(6, 25))):
+            a, b = sorted(rng.integers(0, 4, 2).tolist())
+            centres.append((names[a], names[b], int(rng.integers(200, contigs[names[a]] - 200)),
+                            int(rng.integers(200, contigs[names[b]] - 200)), float(rng.choice([0.02, 0.5, 0.97])),
+                            float(rng.choice([0.02, 0.5, 0.97]))))
+        for sample in sc["samples"]:
+            with open("%s_tiddit/discordants_%s.tab" % (prefix, sample), "w") as f:
+                for k in range(sc["n_disc"]):
+                    ca, cb, xa, xb, pa, pb = centres[int(rng.integers(0, len(centres)))]
+                    if rng.random() < 0.2:
+                        xa, xb = int(rng.integers(1, contigs[ca])), int(rng.integers(1, contigs[cb]))
+                    sa = max(1, xa + int(rng.integers(-sc["jitter"], sc["jitter"] + 1)))
+                    sb = max(1, xb + int(rng.integers(-sc["jitter"], sc["jitter"] + 1)))
+                    if rng.random() < 0.02:
+                        sa = contigs[ca] + 30
+                    if rng.random() < 0.02:
+                        sb = contigs[cb] + 30
+                    f.write("\t".join(["read%d" % int(rng.integers(0, sc["n_disc"] // 2 + 1)), ca, cb, str(sa), str(sa + 100),
+                                       str(rng.random() < pa), str(sb), str(sb + 100), str(rng.random() < pb)]) + "\n")
+            with open("%s_tiddit/splits_%s.tab" % (prefix, sample), "w") as f:
+                for k in range(sc["n_split"]):
+                    ca, cb, xa, xb, pa, pb = centres[int(rng.integers(0, len(centres)))]
+                    qa = max(1, xa + int(rng.integers(-2, 3))); qb = max(1, xb + int(rng.integers(-2, 3)))
+                    if rng.random() < 0.02:
+                        qb = contigs[cb] + 5
+                    extra = ["x"] * 8 if rng.random() < 0.1 else []   # readers only use the first 11 fields
+                    f.write("\t".join(["split%d" % int(rng.integers(0, sc["n_split"] // 2 + 1)), ca, cb, str(qa),
+                                       str(rng.random() < pa), str(qb), str(rng.random() < pb), str(qa - 40), str(qa),
+                                       str(qb), str(qb + 40)] + extra) + "\n")
+            with open("%s_tiddit/contigs_%s.tab" % (prefix, sample), "w") as f:
+                for k in range(sc["n_ctg"]):
+                    ca, cb, xa, xb, pa, pb = centres[int(rng.integers(0, len(centres)))]
+                    if rng.random() < 0.5:
+                        cb = ca
+                        xa = int(rng.integers(1, contigs[ca] - 1500)); xb = xa + int(rng.integers(10, 1400))
+                    f.write("\t".join(["ctg%d" % k, ca, cb, str(xa), str(rng.random() < 0.5), str(xb),
+                                       str(rng.random() < 0.5), str(xa - 200), str(xa), str(xb), str(xb + 200)]) + "\n")
+        chromosomes = ["chr1", "chr2", "chrX", "chr3", "small"]
+        cand = R.tiddit_cluster.main(prefix, chromosomes, contigs, sc["samples"], sc["is_mp"], sc["eps"], sc["m"],
+                                     sc["max_ins_len"], 1000, sc["skip_assembly"], sc["min_reads"])
+        pk = PackedSignals.from_tab(prefix, chromosomes, contigs, sc["samples"], sc["is_mp"], 1000, sc["skip_assembly"])
+        labels = np.full(len(pk), -1, dtype=np.int32)
+        for p in range(pk.n_pairs):
+            lo, hi = int(pk.seg_off[p]), int(pk.seg_off[p + 1])
+            rows = sorted([[int(pk.posA[i]), int(pk.posB[i]), i - lo] for i in range(lo, hi)], key=lambda l: l[0])
+            arr = np.array(rows)
+            lab = R.DBSCAN.main(arr, sc["eps"], sc["m"])
+            labels[lo + arr[:, 2]] = lab.astype(np.int32)
+        rows = []
+        pair_index = {pr: i for i, pr in enumerate(pk.pairs)}
+        for a in cand:
+            for b in cand[a]:
+                for cid, c in cand[a][b].items():
+                    rows.append([pair_index[(a, b)], int(cid), c["N_discordants"], c["N_splits"], c["N_contigs"],
+                                 int(c["posA"]), int(c["posB"]), c["startA"], c["endA"], c["startB"], c["endB"],
+                                 len(c["positions_A"]["start"])])
+        key = "c%d_" % case
+        for f in ("seg_off", "posA", "posB", "span", "name_id", "flags", "same_chrom"):
+            out[key + f] = getattr(pk, f)
+        out[key + "labels"] = labels
+        out[key + "expected"] = np.array(rows, dtype=np.int64).reshape(-1, 12)
+        out[key + "params"] = np.array([sc["max_ins_len"], int(sc["is_mp"]), sc["min_reads"], sc["eps"], sc["m"]])
+    out["n_cases"] = np.array(len(scenarios))
+    np.savez_compressed(os.path.join(HERE, "aggregate_cases.npz"), **out)
+
+
 if __name__ == "__main__":
     config1_cov()
     dbscan_cases()
     coverage_cases()
     gc_cases()
     cluster_cases()
+    aggregate_cases()
     print("golden vectors written to", HERE)

@@ -27,6 +27,7 @@ def test_cluster_main_fold_matches_reference(case, oracle, monkeypatch):
     a = exp["args"]
     monkeypatch.setattr(device_ops, "cluster_labels",
                         lambda posA, posB, seg_off, eps, m, max_pos=0: oracle.cluster_segments(posA, posB, seg_off, eps, m))
+    monkeypatch.setattr(device_ops, "cluster_aggregate", oracle.cluster_aggregate)
     got = tiddit_cluster.main(os.path.join(GOLDEN, "cluster_case%d" % case), a["chromosomes"], a["contig_length"],
                               a["samples"], a["is_mp"], a["epsilon"], a["m"], a["max_ins_len"], a["min_contig"],
                               a["skip_assembly"], a["min_reads"])

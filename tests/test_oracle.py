@@ -82,3 +82,21 @@ def test_oracle_vs_compiled_reference(oracle, ref):
             cov.update_coverage(int(s[i]), int(e[i]), z, a, ebs)
         oracle.update_coverage_batch(s, e, z, b, ebs)
         assert np.array_equal(a, b)
+
+
+def test_aggregate_golden(oracle):
+    """tiddit_cluster.pyx:156-336: the oracle's candidate rows against the rows of the real tiddit_cluster.main
+    (14 random scenarios reaching every branch of :265-330), and its labels against the real DBSCAN.main."""
+    import os
+    from conftest import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "aggregate_cases.npz"))
+    rules = set()
+    for c in range(int(z["n_cases"])):
+        k = "c%d_" % c
+        mil, is_mp, mr, eps, m = z[k + "params"].tolist()
+        assert np.array_equal(oracle.cluster_segments(z[k + "posA"], z[k + "posB"], z[k + "seg_off"], eps, m), z[k + "labels"])
+        rows, mem = oracle.cluster_aggregate(z[k + "labels"], z[k + "posA"], z[k + "posB"], z[k + "span"], z[k + "name_id"],
+                                             z[k + "flags"], z[k + "seg_off"], z[k + "same_chrom"], mil, is_mp, mr)
+        assert np.array_equal(rows[:, [0, 1, 5, 6, 7, 8, 9, 10, 11, 12, 13, 4]], z[k + "expected"]), c
+        rules |= set(rows[:, 14].tolist())
+    assert rules == {0, 1, 2, 3, 4}

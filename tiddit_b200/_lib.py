@@ -29,6 +29,9 @@ SIGNATURES = {
     "tdt_dbscan_main": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _i32, _p, _p, _sz, _p]),
     "tdt_xpass_labels": (ctypes.c_int, [_p, _i64, _i32, _i32, _p, _p, _p, _sz, _p]),
     "tdt_ypass_labels": (ctypes.c_int, [_p, _i64, _i32, _i32, _i32, _p, _p, _p, _sz, _p]),
+    "tdt_aggregate_workspace_bytes": (_sz, [_i64, _i32]),
+    "tdt_cluster_aggregate": (ctypes.c_int, [_p, _p, _p, _p, _p, _p, _p, _p, _i64, _i32, _i32, _i32, _i32, _i32, _i32,
+                                             _p, _p, _p, _p, _sz, _p]),
     "tdt_coverage_accumulate": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _p, _i64, _p, _p]),
     "tdt_coverage_accumulate_contigs": (ctypes.c_int, [_p, _p, _i64, _p, _p, _p, _i32, _i32, _p, _i64, _p, _p]),
     "tdt_gc_bins": (ctypes.c_int, [_p, _i64, _i32, _dbl, _p, _p]),

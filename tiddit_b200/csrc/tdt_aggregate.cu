@@ -1,0 +1,649 @@
+// tdt_aggregate.cu -- candidate aggregation on B200 (sm_100a): cluster labels -> per-candidate statistics.
+//
+// Replaces the per-signal Python fold of tiddit/tiddit_cluster.pyx:156-254 and the per-candidate
+// statistics of :258-336 for ALL (chrA,chrB) pairs in one call.  Per candidate the reference keeps
+//   N_discordants / N_splits / N_contigs   sizes of the SETS of read names                       (:261-263)
+//   posA, posB                             Counter(...).most_common(1) of the split / contig / discordant
+//                                          positions (first-inserted value wins ties) or the orientation-aware
+//                                          min / max of the discordant positions                 (:265-330)
+//   startA, endA, startB, endB             min / max over all members                            (:332-336)
+// and numbers candidates by DBSCAN id, noise surviving only as short intra-chromosomal assembly contigs with
+// fresh ids len(pair) + k (:162-168).  Candidates are reported in the reference's dict insertion order (first
+// appearance in insertion order), the order tiddit_variant numbers SVs by.
+//
+// Pipeline (no host synchronisation, data-dependent sizes stay on the device):
+//   agg_survivor_scan    chained scan: rank of every surviving noise contig inside its pair
+//   agg_key              candidate key per signal (DBSCAN id | len(pair)+rank | dropped)
+//   segsort #1           signals grouped by (pair, candidate key), stable => members in insertion order
+//   agg_mark_scan        chained scan over the sorted order: group heads, compaction of the kept signals
+//   agg_rank_scan        chained scan over insertion order: rank of every candidate by first appearance
+//   agg_gather           per member: (kind,posA) (kind,posB) (kind,name) sort keys; min/max/orientation sums by a
+//                        segmented warp reduction, one atomic per (candidate, warp)
+//   segsort #2..#4       inside every candidate by (kind,posA), (kind,posB), (kind,name)   [tiny-segment path]
+//   agg_runs             runs of equal keys: mode with first-inserted tie-break (64-bit atomicMax of
+//                        count:~first), distinct-name counts
+//   agg_finalize         the branch logic of :265-330, one 16-int row per candidate
+#include "tdt_common.cuh"
+#include "tdt_segsort.cuh"
+
+namespace tdt {
+
+constexpr int AG_THREADS = 256;
+constexpr int AG_ITEMS = 8;
+constexpr int AG_TILE = AG_THREADS * AG_ITEMS;
+constexpr int AG_ACC = 12;    // int32 accumulators per candidate
+constexpr int AG_MODES = 6;   // u64 (count:~first) per side x kind
+enum { AG_ERR_LABEL = 8, AG_ERR_POS = 9, AG_ERR_NAME = 10 };
+
+struct AggDims {
+    int64_t n, nseg;
+};
+
+struct AggSmall {                // one 256-byte aligned record of device-side scalars
+    AggDims d1;                  // {n, P}
+    AggDims d2;                  // {members kept, candidates}
+    u32 ticket[4];
+    int err;
+    int pad[3];
+};
+
+struct AggParams {
+    // inputs
+    const int32_t *labels, *posA, *posB, *name_id;
+    const int4 *span;
+    const uint8_t *flags, *same_chrom;
+    const int64_t *seg_off;
+    int64_t n;
+    int32_t P, max_ins_len, is_mp, min_reads;
+    int pos_bits, name_bits;
+    u32 sentinel;
+    // scratch
+    AggSmall *small;
+    u32 *surv_excl;      // [n]   rank of a surviving noise contig among all survivors (only written for survivors)
+    u32 *pair_base;      // [P]   survivors before the pair
+    u32 *pair_heads;     // bit j: j is the first signal of a pair
+    u32 *key1, *key1s;   // [n]   candidate keys, insertion / sorted order
+    int32_t *val1s;      // [n]   insertion index in sorted order
+    int32_t *gfirst;     // [n]   (group + 1) at the insertion index of a group's first member, else 0
+    int32_t *c_grp;      // [M]   group of every kept signal (sorted order)
+    int64_t *goff;       // [G+1] group offsets into the compact order
+    int32_t *gpair, *gcid, *slot;   // [G]
+    u32 *keyA, *keyB, *keyN;        // [M] sub-sort keys
+    int32_t *acc;        // [G][AG_ACC]
+    u64 *modes;          // [G][AG_MODES]
+    u32 *ncnt;           // [G][4]
+    u64 *status1, *status2, *status3;
+    // outputs
+    int32_t *cand_out, *member_idx;
+    int64_t *counts_out;
+};
+
+struct ScanSmem {
+    int tile;
+    u32 warpA[AG_THREADS / 32], warpB[AG_THREADS / 32];
+    u32 exA, exB;
+};
+
+__device__ __forceinline__ int take_tile(ScanSmem &s, u32 *ticket) {
+    if (threadIdx.x == 0) s.tile = (int)atomicAdd(ticket, 1u);
+    __syncthreads();
+    return s.tile;
+}
+
+// (sumA, sumB): the thread's own totals.  Returns the exclusive prefixes over all earlier threads of all earlier
+// tiles in (preA, preB).  All threads of the CTA must call.
+__device__ __forceinline__ void block_scan2(ScanSmem &s, u64 *status, int tile, u32 sumA, u32 sumB, u32 &preA, u32 &preB) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u32 incA = sumA, incB = sumB;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(0xffffffffu, incA, o);
+        const u32 b = __shfl_up_sync(0xffffffffu, incB, o);
+        if (lane >= o) {
+            incA += a;
+            incB += b;
+        }
+    }
+    if (lane == 31) {
+        s.warpA[warp] = incA;
+        s.warpB[warp] = incB;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const u32 wa = lane < AG_THREADS / 32 ? s.warpA[lane] : 0u;
+        const u32 wb = lane < AG_THREADS / 32 ? s.warpB[lane] : 0u;
+        u32 ia = wa, ib = wb;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, ia, o);
+            const u32 b = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) {
+                ia += a;
+                ib += b;
+            }
+        }
+        const u32 aggA = __shfl_sync(0xffffffffu, ia, 31), aggB = __shfl_sync(0xffffffffu, ib, 31);
+        if (lane < AG_THREADS / 32) {
+            s.warpA[lane] = ia - wa;
+            s.warpB[lane] = ib - wb;
+        }
+        u32 exA, exB;
+        lookback(status, tile, aggA, aggB, exA, exB);
+        if (lane == 0) {
+            s.exA = exA;
+            s.exB = exB;
+        }
+    }
+    __syncthreads();
+    preA = s.exA + s.warpA[warp] + (incA - sumA);
+    preB = s.exB + s.warpB[warp] + (incB - sumB);
+}
+
+// largest p with seg_off[p] <= i (i < seg_off[P]): the non-empty pair that owns element i
+__device__ __forceinline__ int find_pair(const int64_t *__restrict__ off, int P, int64_t i) {
+    int lo = 0, hi = P;  // invariant: off[lo] <= i < off[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (off[mid] <= i) lo = mid; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void agg_setup_kernel(AggParams a) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s == 0) {
+        a.small->d1.n = a.n;
+        a.small->d1.nseg = a.P;
+    }
+    if (s < a.P) {
+        const int64_t q = a.seg_off[s];
+        if (a.seg_off[s + 1] > q) atomicOr(a.pair_heads + (q >> 5), 1u << (q & 31));
+    }
+}
+
+// ---- scan 1: surviving noise contigs (tiddit_cluster.pyx:163-168) --------------------------------------------------
+__device__ __forceinline__ bool survives(const AggParams &a, int64_t i, int p) {
+    return a.labels[i] == -1 && (a.flags[i] & 3) == 2 && a.same_chrom[p] &&
+           ((int64_t)a.posB[i] - (int64_t)a.posA[i]) < 2 * (int64_t)a.max_ins_len;
+}
+
+__global__ void __launch_bounds__(AG_THREADS) agg_survivor_scan_kernel(AggParams a) {
+    __shared__ ScanSmem s;
+    const int tile = take_tile(s, &a.small->ticket[0]);
+    const int64_t i0 = (int64_t)tile * AG_TILE + (int64_t)threadIdx.x * AG_ITEMS;
+    u32 f = 0, cnt = 0;
+    int p = 0;
+    if (i0 < a.n) {
+        p = find_pair(a.seg_off, a.P, i0);
+#pragma unroll
+        for (int k = 0; k < AG_ITEMS; k++) {
+            const int64_t i = i0 + k;
+            if (i < a.n) {
+                while (i >= a.seg_off[p + 1]) p++;
+                if (survives(a, i, p)) {
+                    f |= 1u << k;
+                    cnt++;
+                }
+            }
+        }
+    }
+    u32 pre, unused;
+    block_scan2(s, a.status1, tile, cnt, 0u, pre, unused);
+    if (i0 < a.n) {
+        p = find_pair(a.seg_off, a.P, i0);
+#pragma unroll
+        for (int k = 0; k < AG_ITEMS; k++) {
+            const int64_t i = i0 + k;
+            if (i < a.n) {
+                while (i >= a.seg_off[p + 1]) p++;
+                if (i == a.seg_off[p]) a.pair_base[p] = pre;
+                if (f & (1u << k)) {
+                    a.surv_excl[i] = pre;
+                    pre++;
+                }
+            }
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) agg_key_kernel(AggParams a) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    const int p = find_pair(a.seg_off, a.P, i);
+    const int64_t np = a.seg_off[p + 1] - a.seg_off[p];
+    const int32_t lab = a.labels[i];
+    u32 key = a.sentinel;
+    if (lab >= 0) {
+        if (lab >= np) atomicMax(&a.small->err, (int)AG_ERR_LABEL);   // DBSCAN ids are < len(pair)
+        else key = (u32)lab;
+    } else if (lab != -1) {
+        atomicMax(&a.small->err, (int)AG_ERR_LABEL);
+    } else if (survives(a, i, p)) {
+        key = (u32)(np + (int64_t)(a.surv_excl[i] - a.pair_base[p]));
+    }
+    a.key1[i] = key;
+}
+
+// ---- scan 2: group heads + compaction over the (pair, key)-sorted order ----------------------------------------------
+__global__ void __launch_bounds__(AG_THREADS) agg_mark_scan_kernel(AggParams a) {
+    __shared__ ScanSmem s;
+    const int tile = take_tile(s, &a.small->ticket[1]);
+    const int64_t j0 = (int64_t)tile * AG_TILE + (int64_t)threadIdx.x * AG_ITEMS;
+    u32 keys[AG_ITEMS];
+    u32 headm = 0, keptm = 0;
+    if (j0 < a.n) {
+        u32 prev = j0 > 0 ? a.key1s[j0 - 1] : 0u;
+#pragma unroll
+        for (int k = 0; k < AG_ITEMS; k++) {
+            const int64_t j = j0 + k;
+            if (j < a.n) {
+                const u32 key = a.key1s[j];
+                keys[k] = key;
+                const bool ph = (a.pair_heads[j >> 5] >> (j & 31)) & 1u;
+                if (key != a.sentinel) {
+                    keptm |= 1u << k;
+                    if (ph || key != prev) headm |= 1u << k;
+                }
+                prev = key;
+            }
+        }
+    }
+    u32 preH, preK;
+    block_scan2(s, a.status2, tile, (u32)__popc(headm), (u32)__popc(keptm), preH, preK);
+    if (j0 < a.n) {
+        int p = -1;
+#pragma unroll
+        for (int k = 0; k < AG_ITEMS; k++) {
+            const int64_t j = j0 + k;
+            if (j < a.n) {
+                if (keptm & (1u << k)) {
+                    const int32_t idx = a.val1s[j];
+                    if (headm & (1u << k)) {
+                        if (p < 0) p = find_pair(a.seg_off, a.P, j);
+                        while (j >= a.seg_off[p + 1]) p++;
+                        a.goff[preH] = (int64_t)preK;
+                        a.gpair[preH] = p;
+                        a.gcid[preH] = (int32_t)keys[k];
+                        a.gfirst[idx] = (int32_t)preH + 1;
+                        preH++;
+                    }
+                    a.member_idx[preK] = idx;
+                    a.c_grp[preK] = (int32_t)preH - 1;
+                    preK++;
+                }
+                if (j == a.n - 1) {   // totals
+                    a.goff[preH] = (int64_t)preK;
+                    a.small->d2.n = (int64_t)preK;
+                    a.small->d2.nseg = (int64_t)preH;
+                    a.counts_out[0] = (int64_t)preH;
+                    a.counts_out[1] = (int64_t)preK;
+                }
+            }
+        }
+    }
+}
+
+// ---- scan 3: candidates ranked by first appearance (dict insertion order) ---------------------------------------------
+__global__ void __launch_bounds__(AG_THREADS) agg_rank_scan_kernel(AggParams a) {
+    __shared__ ScanSmem s;
+    const int tile = take_tile(s, &a.small->ticket[2]);
+    const int64_t i0 = (int64_t)tile * AG_TILE + (int64_t)threadIdx.x * AG_ITEMS;
+    int32_t g[AG_ITEMS];
+    u32 cnt = 0;
+#pragma unroll
+    for (int k = 0; k < AG_ITEMS; k++) {
+        const int64_t i = i0 + k;
+        g[k] = i < a.n ? a.gfirst[i] : 0;
+        cnt += g[k] != 0;
+    }
+    u32 pre, unused;
+    block_scan2(s, a.status3, tile, cnt, 0u, pre, unused);
+#pragma unroll
+    for (int k = 0; k < AG_ITEMS; k++)
+        if (g[k]) a.slot[g[k] - 1] = (int32_t)pre++;
+}
+
+// ---- accumulators ------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) agg_init_kernel(AggParams a) {
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t G = a.small->d2.nseg;
+    if (t >= G) return;
+    int32_t *acc = a.acc + t * AG_ACC;
+#pragma unroll
+    for (int k = 0; k < 8; k++) acc[k] = (k & 1) ? (int32_t)0x80000000 : 0x7fffffff;   // even: min, odd: max
+#pragma unroll
+    for (int k = 8; k < AG_ACC; k++) acc[k] = 0;
+    u64 *md = a.modes + t * AG_MODES;
+#pragma unroll
+    for (int k = 0; k < AG_MODES; k++) md[k] = 0ull;
+    *(uint4 *)(a.ncnt + t * 4) = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__device__ __forceinline__ int32_t seg_min(int32_t v, int32_t g, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t w = __shfl_up_sync(0xffffffffu, v, o);
+        const int32_t h = __shfl_up_sync(0xffffffffu, g, o);
+        if (lane >= o && h == g) v = min(v, w);
+    }
+    return v;
+}
+__device__ __forceinline__ int32_t seg_max(int32_t v, int32_t g, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t w = __shfl_up_sync(0xffffffffu, v, o);
+        const int32_t h = __shfl_up_sync(0xffffffffu, g, o);
+        if (lane >= o && h == g) v = max(v, w);
+    }
+    return v;
+}
+__device__ __forceinline__ u32 seg_add(u32 v, int32_t g, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 w = __shfl_up_sync(0xffffffffu, v, o);
+        const int32_t h = __shfl_up_sync(0xffffffffu, g, o);
+        if (lane >= o && h == g) v += w;
+    }
+    return v;
+}
+
+__global__ void __launch_bounds__(256) agg_gather_kernel(AggParams a) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t M = a.small->d2.n;
+    const int lane = threadIdx.x & 31;
+    if (c - lane >= M) return;   // whole warp beyond the end
+    const bool live = c < M;
+    int32_t g = -1;
+    int32_t sA = 0x7fffffff, eA = (int32_t)0x80000000, sB = 0x7fffffff, eB = (int32_t)0x80000000;
+    int32_t dAmin = 0x7fffffff, dAmax = (int32_t)0x80000000, dBmin = 0x7fffffff, dBmax = (int32_t)0x80000000;
+    u32 ori = 0;   // four 8-bit counters: revA, fwdA, revB, fwdB (a warp adds at most 32 to each)
+    if (live) {
+        const int32_t idx = a.member_idx[c];
+        g = a.c_grp[c];
+        const u32 f = a.flags[idx];
+        const u32 kind = f & 3u;
+        const int32_t x = a.posA[idx], y = a.posB[idx], nm = a.name_id[idx];
+        const int4 sp = a.span[idx];
+        if (kind == 3u) atomicMax(&a.small->err, (int)AG_ERR_LABEL);
+        if (x < 0 || y < 0 || (a.pos_bits < 31 && ((x >> a.pos_bits) || (y >> a.pos_bits))))
+            atomicMax(&a.small->err, (int)AG_ERR_POS);
+        if (nm < 0 || (nm >> a.name_bits)) atomicMax(&a.small->err, (int)AG_ERR_NAME);
+        a.keyA[c] = (kind << a.pos_bits) | (u32)x;
+        a.keyB[c] = (kind << a.pos_bits) | (u32)y;
+        a.keyN[c] = (kind << a.name_bits) | (u32)nm;
+        sA = sp.x; eA = sp.y; sB = sp.z; eB = sp.w;
+        if (kind == 0u) {
+            dAmin = dAmax = x;
+            dBmin = dBmax = y;
+            ori = ((f >> 2) & 1u) | (((f >> 3) & 1u) << 8) | (((f >> 4) & 1u) << 16) | (((f >> 5) & 1u) << 24);
+        }
+    }
+    sA = seg_min(sA, g, lane); eA = seg_max(eA, g, lane);
+    sB = seg_min(sB, g, lane); eB = seg_max(eB, g, lane);
+    dAmin = seg_min(dAmin, g, lane); dAmax = seg_max(dAmax, g, lane);
+    dBmin = seg_min(dBmin, g, lane); dBmax = seg_max(dBmax, g, lane);
+    ori = seg_add(ori, g, lane);
+    const int32_t gnext = __shfl_down_sync(0xffffffffu, g, 1);
+    if (live && (lane == 31 || gnext != g)) {   // last lane of the candidate's run inside this warp
+        int32_t *acc = a.acc + (int64_t)g * AG_ACC;
+        atomicMin(acc + 0, sA); atomicMax(acc + 1, eA);
+        atomicMin(acc + 2, sB); atomicMax(acc + 3, eB);
+        if (dAmin <= dAmax) {
+            atomicMin(acc + 4, dAmin); atomicMax(acc + 5, dAmax);
+            atomicMin(acc + 6, dBmin); atomicMax(acc + 7, dBmax);
+            if (ori & 0xffu) atomicAdd(acc + 8, (int)(ori & 0xffu));
+            if ((ori >> 8) & 0xffu) atomicAdd(acc + 9, (int)((ori >> 8) & 0xffu));
+            if ((ori >> 16) & 0xffu) atomicAdd(acc + 10, (int)((ori >> 16) & 0xffu));
+            if (ori >> 24) atomicAdd(acc + 11, (int)(ori >> 24));
+        }
+    }
+}
+
+// ---- runs of equal keys inside every candidate (after the sub-sort) -----------------------------------------------------
+// WHAT 0 / 1: mode of (kind, posA) / (kind, posB); 2: distinct (kind, name)
+template <int WHAT>
+__global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *__restrict__ keys,
+                                                       const int32_t *__restrict__ vals) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t M = a.small->d2.n;
+    if (c >= M) return;
+    const int32_t g = a.c_grp[c];
+    const int64_t lo = a.goff[g];
+    const u32 key = keys[c];
+    if (c > lo && keys[c - 1] == key) return;   // not a run head
+    if (WHAT == 2) {
+        atomicAdd(a.ncnt + (int64_t)g * 4 + (key >> a.name_bits), 1u);
+        return;
+    }
+    // run end: gallop, then bisect (keys ascend inside the candidate)
+    const int64_t hi = a.goff[g + 1];
+    int64_t left = c, step = 1;            // keys[left] == key
+    int64_t right = hi;                    // keys[right] > key (or right == hi)
+    while (left + step < hi) {
+        if (keys[left + step] == key) {
+            left += step;
+            step <<= 1;
+        } else {
+            right = left + step;
+            break;
+        }
+    }
+    while (right - left > 1) {
+        const int64_t mid = (left + right) >> 1;
+        if (keys[mid] == key) left = mid; else right = mid;
+    }
+    const u64 count = (u64)(right - c);
+    const u32 first = (u32)vals[c];        // compact position of the first occurrence (the sort is stable)
+    const u32 kind = key >> a.pos_bits;
+    atomicMax(a.modes + (int64_t)g * AG_MODES + WHAT * 3 + kind, (count << 32) | (u64)(0xffffffffu - first));
+}
+
+// ---- one row per candidate (tiddit_cluster.pyx:258-336) ------------------------------------------------------------------
+__global__ void __launch_bounds__(256) agg_finalize_kernel(AggParams a) {
+    const int64_t g = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t G = a.small->d2.nseg;
+    if (g >= G) return;
+    const int32_t *acc = a.acc + g * AG_ACC;
+    const u64 *md = a.modes + g * AG_MODES;
+    const uint4 nc = *(const uint4 *)(a.ncnt + g * 4);
+    const int64_t lo = a.goff[g], hi = a.goff[g + 1];
+    int32_t row[16];
+    row[0] = a.gpair[g];
+    row[1] = a.gcid[g];
+    row[2] = a.member_idx[lo];
+    row[3] = (int32_t)lo;
+    row[4] = (int32_t)(hi - lo);
+    row[5] = (int32_t)nc.x;
+    row[6] = (int32_t)nc.y;
+    row[7] = (int32_t)nc.z;
+    int use_kind = -1, rule;
+    if (nc.y && (int64_t)a.min_reads <= (int64_t)nc.y) { use_kind = 1; rule = 0; }
+    else if (nc.z) { use_kind = 2; rule = 1; }
+    else if (nc.y) { use_kind = 1; rule = 2; }
+    else {
+        const int64_t revA = acc[8], fwdA = acc[9], revB = acc[10], fwdB = acc[11];
+        if ((revA >= 5 * fwdA || revA * 5 <= fwdA) && (revB >= 5 * fwdB || revB * 5 <= fwdB)) {
+            const bool A_rev = revA > fwdA, B_rev = revB > fwdB;
+            const bool maxA = a.is_mp ? A_rev : !A_rev, maxB = a.is_mp ? B_rev : !B_rev;
+            row[8] = maxA ? acc[5] : acc[4];
+            row[9] = maxB ? acc[7] : acc[6];
+            rule = 3;
+        } else {
+            use_kind = 0;
+            rule = 4;
+        }
+    }
+    if (use_kind >= 0) {
+        const u32 fa = 0xffffffffu - (u32)md[use_kind];
+        const u32 fb = 0xffffffffu - (u32)md[3 + use_kind];
+        row[8] = a.posA[a.member_idx[fa]];
+        row[9] = a.posB[a.member_idx[fb]];
+    }
+    row[10] = acc[0]; row[11] = acc[1]; row[12] = acc[2]; row[13] = acc[3];
+    row[14] = rule;
+    row[15] = 0;
+    int4 *out = (int4 *)(a.cand_out + (int64_t)a.slot[g] * 16);
+    out[0] = make_int4(row[0], row[1], row[2], row[3]);
+    out[1] = make_int4(row[4], row[5], row[6], row[7]);
+    out[2] = make_int4(row[8], row[9], row[10], row[11]);
+    out[3] = make_int4(row[12], row[13], row[14], row[15]);
+}
+
+__global__ void agg_status_kernel(AggParams a) {
+    a.counts_out[2] = (int64_t)a.small->err;
+}
+
+// ---- workspace -----------------------------------------------------------------------------------------------------------
+struct AggPlan {
+    size_t sort, total;
+    int64_t tiles;
+};
+
+static AggPlan agg_plan(int64_t n, int32_t P) {
+    AggPlan pl;
+    const int64_t nseg = n > P ? n : P;
+    pl.sort = segsort_temp_bytes(n, nseg);
+    pl.tiles = (n + AG_TILE - 1) / AG_TILE + 1;
+    auto al = [](size_t b) { return (b + 255) & ~(size_t)255; };
+    size_t t = 0;
+    t += al(sizeof(AggSmall));
+    t += 3 * al((size_t)pl.tiles * 8);                 // scan status
+    t += al((size_t)(P + 1) * 4);                      // pair_base
+    t += al((size_t)(n / 32 + 2) * 4);                 // pair_heads
+    t += 11 * al((size_t)(n + 4) * 4);                 // key1 key1s val1s tmpK tmpV c_grp keyA keyB keyN gfirst(slot alias no) gpair
+    t += 2 * al((size_t)(n + 4) * 4);                  // gcid slot
+    t += al((size_t)(n + 2) * 8);                      // goff
+    t += al((size_t)n * AG_ACC * 4) + al((size_t)n * AG_MODES * 8) + al((size_t)n * 16);
+    t += pl.sort + 256;
+    pl.total = t;
+    return pl;
+}
+
+static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t st) {
+    const int64_t n = a.n;
+    const int32_t P = a.P;
+    const AggPlan pl = agg_plan(n, P);
+    if (ws == nullptr || ws_bytes < pl.total)
+        return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
+    Arena ar(ws, ws_bytes);
+    a.small = ar.take<AggSmall>(1);
+    a.status1 = ar.take<u64>(pl.tiles);
+    a.status2 = ar.take<u64>(pl.tiles);
+    a.status3 = ar.take<u64>(pl.tiles);
+    a.pair_heads = ar.take<u32>(n / 32 + 2);
+    a.gfirst = ar.take<int32_t>(n + 4);
+    char *zero_end = ar.base + ar.off;               // everything up to here is zeroed by one memset
+    a.pair_base = ar.take<u32>(P + 1);
+    a.key1 = ar.take<u32>(n + 4);
+    a.key1s = ar.take<u32>(n + 4);
+    a.val1s = ar.take<int32_t>(n + 4);
+    u32 *tmpK = ar.take<u32>(n + 4);
+    int32_t *tmpV = ar.take<int32_t>(n + 4);
+    a.c_grp = ar.take<int32_t>(n + 4);
+    a.keyA = ar.take<u32>(n + 4);
+    a.keyB = ar.take<u32>(n + 4);
+    a.keyN = ar.take<u32>(n + 4);
+    a.gpair = ar.take<int32_t>(n + 4);
+    a.gcid = ar.take<int32_t>(n + 4);
+    a.slot = ar.take<int32_t>(n + 4);
+    a.goff = ar.take<int64_t>(n + 2);
+    a.acc = ar.take<int32_t>((size_t)n * AG_ACC);
+    a.modes = ar.take<u64>((size_t)n * AG_MODES);
+    a.ncnt = ar.take<u32>((size_t)n * 4);
+    void *sort_temp = ar.take<char>(pl.sort);
+    if (!sort_temp) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
+    a.surv_excl = tmpK;   // consumed by agg_key before the first sort touches its scratch
+
+    TDT_CUDA(cudaMemsetAsync(ws, 0, (size_t)(zero_end - (char *)ws), st));
+    TDT_CUDA(cudaMemsetAsync(a.counts_out, 0, 4 * sizeof(int64_t), st));
+    const unsigned tiles = (unsigned)((n + AG_TILE - 1) / AG_TILE);
+    const unsigned per_elem = (unsigned)((n + 255) / 256);
+    {
+        ProfScope ps("agg_keys", st);
+        TDT_LAUNCH(agg_setup_kernel, (unsigned)((P + 256) / 256), 256, 0, st, a);
+        TDT_LAUNCH(agg_survivor_scan_kernel, tiles, AG_THREADS, 0, st, a);
+        TDT_LAUNCH(agg_key_kernel, per_elem, 256, 0, st, a);
+    }
+    {
+        ProfScope ps("agg_sort_groups", st);
+        const int key_bits = bit_width_u32(a.sentinel);
+        int rc = segsort_pairs(a.key1, nullptr, a.key1s, a.val1s, tmpK, tmpV, a.seg_off, (const int64_t *)&a.small->d1,
+                               nullptr, n, P, key_bits, sort_temp, pl.sort, &a.small->err, st);
+        if (rc) return rc;
+    }
+    {
+        ProfScope ps("agg_groups", st);
+        TDT_LAUNCH(agg_mark_scan_kernel, tiles, AG_THREADS, 0, st, a);
+        TDT_LAUNCH(agg_rank_scan_kernel, tiles, AG_THREADS, 0, st, a);
+        TDT_LAUNCH(agg_init_kernel, per_elem, 256, 0, st, a);
+    }
+    {
+        ProfScope ps("agg_gather", st);
+        TDT_LAUNCH(agg_gather_kernel, per_elem, 256, 0, st, a);
+    }
+    const int64_t nseg_max = n;
+    for (int what = 0; what < 3; what++) {
+        ProfScope ps(what == 0 ? "agg_mode_A" : (what == 1 ? "agg_mode_B" : "agg_names"), st);
+        const u32 *kin = what == 0 ? a.keyA : (what == 1 ? a.keyB : a.keyN);
+        const int bits = (what == 2 ? a.name_bits : a.pos_bits) + 2;
+        int rc = segsort_pairs(kin, nullptr, a.key1s, a.val1s, tmpK, tmpV, a.goff, (const int64_t *)&a.small->d2,
+                               a.c_grp, n, nseg_max, bits, sort_temp, pl.sort, &a.small->err, st);
+        if (rc) return rc;
+        if (what == 0) TDT_LAUNCH(agg_runs_kernel<0>, per_elem, 256, 0, st, a, a.key1s, a.val1s);
+        else if (what == 1) TDT_LAUNCH(agg_runs_kernel<1>, per_elem, 256, 0, st, a, a.key1s, a.val1s);
+        else TDT_LAUNCH(agg_runs_kernel<2>, per_elem, 256, 0, st, a, a.key1s, a.val1s);
+    }
+    {
+        ProfScope ps("agg_finalize", st);
+        TDT_LAUNCH(agg_finalize_kernel, per_elem, 256, 0, st, a);
+        TDT_LAUNCH(agg_status_kernel, 1, 1, 0, st, a);
+    }
+    return TDT_OK;
+}
+
+}  // namespace tdt
+
+using namespace tdt;
+
+extern "C" {
+
+size_t tdt_aggregate_workspace_bytes(int64_t n, int32_t P) {
+    if (n <= 0) return 0;
+    return agg_plan(n, P < 1 ? 1 : P).total;
+}
+
+int tdt_cluster_aggregate(const int32_t *labels, const int32_t *posA, const int32_t *posB, const int32_t *span,
+                          const int32_t *name_id, const uint8_t *flags, const int64_t *seg_off,
+                          const uint8_t *same_chrom, int64_t n, int32_t P, int32_t max_ins_len, int32_t is_mp,
+                          int32_t min_reads, int32_t max_pos, int32_t n_names, int32_t *cand_out,
+                          int32_t *member_idx_out, int64_t *counts_out, void *ws, size_t ws_bytes, void *stream) {
+    if (n < 0) return fail(TDT_E_ARG, "n = %lld is negative", (long long)n);
+    if (n >= (1LL << 30)) return fail(TDT_E_ARG, "n = %lld exceeds the 2^30 signals one call supports", (long long)n);
+    if (!counts_out) return fail(TDT_E_ARG, "counts_out is null");
+    if (max_pos < 0 || n_names < 0) return fail(TDT_E_ARG, "max_pos / n_names must not be negative");
+    if (max_pos >= (1 << 30)) return fail(TDT_E_ARG, "max_pos = %d: positions must stay below 2^30", max_pos);
+    if (n == 0) {
+        TDT_CUDA(cudaMemsetAsync(counts_out, 0, 4 * sizeof(int64_t), (cudaStream_t)stream));
+        return TDT_OK;
+    }
+    if (P < 1) return fail(TDT_E_ARG, "P = %d pairs for %lld signals", P, (long long)n);
+    if (!labels || !posA || !posB || !span || !name_id || !flags || !seg_off || !same_chrom || !cand_out ||
+        !member_idx_out)
+        return fail(TDT_E_ARG, "null pointer argument");
+    if (((uintptr_t)span & 15) || ((uintptr_t)cand_out & 15))
+        return fail(TDT_E_ARG, "span and cand_out must be 16-byte aligned");
+    AggParams a = {};
+    a.labels = labels; a.posA = posA; a.posB = posB; a.name_id = name_id;
+    a.span = (const int4 *)span;
+    a.flags = flags; a.same_chrom = same_chrom; a.seg_off = seg_off;
+    a.n = n; a.P = P; a.max_ins_len = max_ins_len; a.is_mp = is_mp != 0; a.min_reads = min_reads;
+    a.pos_bits = max_pos ? bit_width_u32((uint32_t)max_pos) : 30;
+    a.name_bits = n_names ? bit_width_u32((uint32_t)n_names) : 30;
+    if (a.pos_bits < 1) a.pos_bits = 1;
+    if (a.name_bits < 1) a.name_bits = 1;
+    a.sentinel = (1u << bit_width_u32((uint32_t)(2 * n))) - 1u;
+    a.cand_out = cand_out; a.member_idx = member_idx_out; a.counts_out = counts_out;
+    return aggregate_impl(a, ws, ws_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -22,6 +22,7 @@
 //   group_extra_scan/bases       DBSCAN.py:113-122 id arithmetic per x-run
 //   final_labels                 reference ids scattered back to insertion order
 #include "tdt_common.cuh"
+#define TDT_SEGSORT_IMPL
 #include "tdt_segsort.cuh"
 
 namespace tdt {

@@ -122,6 +122,14 @@ __device__ __forceinline__ uint32_t ss_digit(uint32_t key, int pass, int bits) {
     return (key >> (pass * bits)) & ((1u << bits) - 1u);
 }
 
+// Sorts every segment [off[s], off[s+1]) of keys_in/vals_in by key (stable) into keys_out/vals_out; defined in the
+// one translation unit that sets TDT_SEGSORT_IMPL (tdt_cluster.cu), declared for the others (tdt_aggregate.cu).
+int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *keys_out, int32_t *vals_out,
+                  uint32_t *keys_tmp, int32_t *vals_tmp, const int64_t *off, const int64_t *dims, const int32_t *segid,
+                  int64_t n_max, int64_t nseg_max, int key_bits, void *temp, size_t temp_bytes, int *err,
+                  cudaStream_t st);
+
+#ifdef TDT_SEGSORT_IMPL
 // ---- classification: windows of the small segments, tile ranges of the large ones -----------------
 __global__ void segsort_classify_kernel(SSArgs a) {
     const int64_t nseg = a.dims[1];
@@ -651,7 +659,7 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
 // n_max / nseg_max: host-side upper bounds that size the grids; the actual n / nseg are read on the device
 // from dims[0] / dims[1].  keys_tmp / vals_tmp: scratch of n_max elements (only touched for large segments).
 // segid (optional): segment index of every element; enables the counting path for segments of <= 32 elements.
-static int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *keys_out, int32_t *vals_out,
+int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *keys_out, int32_t *vals_out,
                          uint32_t *keys_tmp, int32_t *vals_tmp, const int64_t *off, const int64_t *dims,
                          const int32_t *segid, int64_t n_max, int64_t nseg_max, int key_bits, void *temp,
                          size_t temp_bytes, int *err, cudaStream_t st) {
@@ -713,5 +721,6 @@ static int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32
     }
     return TDT_OK;
 }
+#endif  // TDT_SEGSORT_IMPL
 
 }  // namespace tdt

@@ -123,6 +123,55 @@ def ypass_device(y, epsilon, m, labels_io, cluster_id_io, max_pos=0):
     return labels_io, cluster_id_io
 
 
+def cluster_aggregate_device(labels, posA, posB, span, name_id, flags, seg_off, same_chrom, P, max_ins_len, is_mp,
+                             min_reads, max_pos=0, n_names=0, cand_out=None, member_out=None, counts_out=None):
+    """tiddit_cluster.pyx:156-336 for all pairs: CUDA tensors in -> (rows int32 [n,16], member_idx int32 [n],
+    counts int64 [4] = {candidates, kept signals, data error, 0}), all on the device; nothing synchronises."""
+    torch = _lib.torch_cuda()
+    L = _lib.lib()
+    n = int(labels.numel())
+    dev = labels.device
+    if cand_out is None:
+        cand_out = torch.empty((max(n, 1), 16), dtype=torch.int32, device=dev)
+    if member_out is None:
+        member_out = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    if counts_out is None:
+        counts_out = torch.zeros(4, dtype=torch.int64, device=dev)
+    need = L.tdt_aggregate_workspace_bytes(n, int(P))
+    ws = _lib.workspace(torch, need, tag="aggregate") if n else None
+    rc = L.tdt_cluster_aggregate(_lib.ptr(labels), _lib.ptr(posA), _lib.ptr(posB), _lib.ptr(span), _lib.ptr(name_id),
+                                 _lib.ptr(flags), _lib.ptr(seg_off), _lib.ptr(same_chrom), n, int(P), int(max_ins_len),
+                                 int(bool(is_mp)), int(min_reads), int(max_pos), int(n_names), _lib.ptr(cand_out),
+                                 _lib.ptr(member_out), _lib.ptr(counts_out), _lib.ptr(ws), ws.numel() if n else 0,
+                                 _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return cand_out, member_out, counts_out
+
+
+def check_aggregate_status(code):
+    if code:
+        what = {1: "a sort key is out of range", 8: "a label is outside [-1, len(pair)) or a kind is not D/S/A",
+                9: "a position is negative or above max_pos", 10: "a name id is negative or above n_names"}
+        raise _lib.TdtError(_lib.TDT_E_RANGE, what.get(int(code), "data error %d" % int(code)))
+
+
+def cluster_aggregate(labels, posA, posB, span, name_id, flags, seg_off, same_chrom, max_ins_len, is_mp, min_reads,
+                      max_pos=0, n_names=0):
+    """Host front end: numpy arrays in -> (rows int32 [C,16] in dict insertion order, member_idx int32 [M])."""
+    torch = _lib.torch_cuda()
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+    P = len(seg_off) - 1
+    d = lambda a, t: _lib.to_device(torch, a, t)
+    span = np.ascontiguousarray(span, dtype=np.int32).reshape(-1, 4)
+    rows, mem, counts = cluster_aggregate_device(d(labels, np.int32), d(posA, np.int32), d(posB, np.int32), d(span, np.int32),
+                                                 d(name_id, np.int32), d(flags, np.uint8), d(seg_off, np.int64),
+                                                 d(same_chrom, np.uint8), P, max_ins_len, is_mp, min_reads, max_pos,
+                                                 n_names)
+    C, M, err, _ = (int(v) for v in counts.cpu().tolist())
+    check_aggregate_status(err)
+    return rows[:C].cpu().numpy(), mem[:M].cpu().numpy()
+
+
 def segsort_device(keys, vals, off, key_bits, segid=None):
     """Test hook: every segment [off[s], off[s+1]) of (keys uint32-as-int32, vals int32 or None) sorted by key,
     stable -> (keys_out, vals_out) CUDA tensors."""

@@ -151,3 +151,32 @@ def fasta_sequence(length, seed=9, gc=0.41):
     mid = length // 2
     seq[mid:mid + cen] = ord("N")
     return seq
+
+
+def signal_records(posA, posB, seg_off, seed=11, split_frac=0.18, contig_frac=0.02, dup_names=0.3, contigs=GRCH38):
+    """The remaining record fields (tiddit_cluster.pyx:72,101,134) for a signal set: kind (D / S / A), read-name ids
+    (a share of the names occurs on several records, like reads with supplementary alignments), orientation bits
+    drawn with a per-region bias (so that both the orientation rule and the mode rule of :284-329 occur), and
+    (startA, endA, startB, endB) around the breakpoints.  Assembly contigs on intra-chromosomal pairs get
+    posB close to posA now and then, so that noise contigs survive as singleton candidates (:163-168).
+    -> dict(span int32 [n,4], name_id int32, flags uint8, same_chrom uint8 [P], n_names)."""
+    rng = np.random.default_rng(seed)
+    n = len(posA)
+    pairs = populated_pairs(contigs)
+    P = len(seg_off) - 1
+    same = np.array([ia == ib for ia, ib in pairs[:P]], dtype=np.uint8) if P == len(pairs) else np.ones(P, dtype=np.uint8)
+    r = rng.random(n)
+    kind = np.where(r < contig_frac, 2, np.where(r < contig_frac + split_frac, 1, 0)).astype(np.uint8)
+    # orientation bias by 4 kb region of posA / posB: 0.03, 0.5 or 0.97
+    bias = np.array([0.03, 0.5, 0.97])
+    pa = bias[(posA.astype(np.int64) >> 12) * 2654435761 % 3]
+    pb = bias[(posB.astype(np.int64) >> 12) * 40503 % 3]
+    ta, tb = rng.random(n) < pa, rng.random(n) < pb
+    flags = kind | np.where(ta, 0x04, 0x08).astype(np.uint8) | np.where(tb, 0x10, 0x20).astype(np.uint8)
+    name_id = np.arange(n, dtype=np.int64)
+    dup = rng.random(n) < dup_names
+    name_id[dup] = np.maximum(name_id[dup] - rng.integers(1, 40, int(dup.sum())), 0)   # shares a name with an earlier record
+    la, lb = rng.integers(30, 151, n), rng.integers(30, 151, n)
+    span = np.stack([posA - la, posA.astype(np.int64), posB.astype(np.int64), posB + lb], axis=1)
+    return {"span": np.ascontiguousarray(span, dtype=np.int32), "name_id": name_id.astype(np.int32), "flags": flags,
+            "same_chrom": same, "n_names": n}
