@@ -154,6 +154,20 @@ TDT_API int tdt_coverage_accumulate_contigs(const int32_t *start, const int32_t 
                                     int64_t *first_bad, void *stream);
 
 /* --------------------------------------------------------------------------------------------
+ * Masked coverage medians.  Replaces the bin loops of tiddit/tiddit_coverage_analysis.pyx:14-29
+ * (determine_ploidy): for every contig c the numpy.median of bins[i] over bin_off[c] <= i < bin_off[c+1] with
+ * bins[i] > 0 and gc[i] != -1 (:17-22), and the same over all bins (:26-27).  bins / gc are the coverage and GC
+ * arrays of all contigs back to back (same bin size), bin_off[C+1] (device int64) delimits them.
+ * medians_out[C+1] (float64): contigs, then the genome-wide median; NaN where nothing qualifies (numpy.median([])).
+ * counts_out[C+1] (int64): qualifying bins.  Exact (radix select on the bit patterns; even counts average the two
+ * middle values like numpy).  Does not synchronise.
+ * ------------------------------------------------------------------------------------------ */
+TDT_API size_t tdt_coverage_medians_workspace_bytes(int32_t C);
+
+TDT_API int tdt_coverage_medians(const double *bins, const int8_t *gc, const int64_t *bin_off, int32_t C, int64_t n_bins,
+                                 double *medians_out, int64_t *counts_out, void *ws, size_t ws_bytes, void *stream);
+
+/* --------------------------------------------------------------------------------------------
  * GC bins.  Replaces tiddit/tiddit_gc.pyx:6-33 (binned_gc) on a contig sequence resident in HBM
  * (one byte per base, as pysam.FastaFile.fetch returns it): out[b] (int8) = -1 if
  * #N/bin_size > n_cutoff else rint(100 * #GC / #chars), ceil(len / bin_size) bins.

@@ -11,6 +11,7 @@ repository, only the compiled extension modules are kept):
     oracle/_ref/tiddit/tiddit_cluster.*.so   <- /root/reference/tiddit/tiddit_cluster.pyx
     oracle/_ref/tiddit/tiddit_coverage.*.so  <- /root/reference/tiddit/tiddit_coverage.pyx
     oracle/_ref/tiddit/tiddit_gc.*.so        <- /root/reference/tiddit/tiddit_gc.pyx
+    oracle/_ref/tiddit/tiddit_coverage_analysis.*.so <- /root/reference/tiddit/tiddit_coverage_analysis.pyx
     oracle/_ref/tiddit/__init__.py           (empty, generated)
     oracle/_ref/pysam.py                     (copy of oracle/ref_shims/pysam.py -- our FastaFile stand-in)
 
@@ -32,7 +33,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("TIDDIT_REFERENCE", "/root/reference")
 OUT = os.path.join(HERE, "_ref")
 MODULES = [("DBSCAN", "DBSCAN.py"), ("tiddit_cluster", "tiddit_cluster.pyx"),
-           ("tiddit_coverage", "tiddit_coverage.pyx"), ("tiddit_gc", "tiddit_gc.pyx")]
+           ("tiddit_coverage", "tiddit_coverage.pyx"), ("tiddit_gc", "tiddit_gc.pyx"),
+           ("tiddit_coverage_analysis", "tiddit_coverage_analysis.pyx")]
 
 
 def have_ref():

@@ -50,6 +50,9 @@ def lib():
         L.tdt_oracle_aggregate.restype = ctypes.c_int64
         L.tdt_oracle_aggregate.argtypes = [i32p, i32p, i32p, i32p, i32p, u8p, i64p, u8p, ctypes.c_int64, ctypes.c_int32,
                                            ctypes.c_int32, ctypes.c_int32, i32p, i32p, i64p]
+        L.tdt_oracle_masked_medians.restype = None
+        L.tdt_oracle_masked_medians.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int8), i64p,
+                                                ctypes.c_int64, ctypes.POINTER(ctypes.c_double), i64p]
         _lib = L
     return _lib
 
@@ -175,3 +178,17 @@ def gc_bins(seq, bin_size, n_cutoff):
     if nbins:
         lib().tdt_oracle_gc(_p(buf, ctypes.c_uint8), len(buf), int(bin_size), float(n_cutoff), _p(out, ctypes.c_int8))
     return out
+
+
+def coverage_medians(bins, gc, bin_off):
+    """tiddit_coverage_analysis.pyx:14-27 -> (medians float64 [C+1], counts int64 [C+1]); same contract as
+    tiddit_b200.device_ops.coverage_medians."""
+    bins = np.ascontiguousarray(bins, dtype=np.float64)
+    gc = np.ascontiguousarray(gc, dtype=np.int8)
+    bin_off = np.ascontiguousarray(bin_off, dtype=np.int64)
+    C = len(bin_off) - 1
+    med = np.zeros(C + 1, dtype=np.float64)
+    cnt = np.zeros(C + 1, dtype=np.int64)
+    lib().tdt_oracle_masked_medians(_p(bins, ctypes.c_double), _p(gc, ctypes.c_int8), _p(bin_off, ctypes.c_int64), C,
+                                    _p(med, ctypes.c_double), _p(cnt, ctypes.c_int64))
+    return med, cnt

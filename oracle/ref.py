@@ -32,5 +32,6 @@ def load():
     ns.tiddit_coverage = importlib.import_module("tiddit.tiddit_coverage")
     ns.tiddit_cluster = importlib.import_module("tiddit.tiddit_cluster")
     ns.tiddit_gc = importlib.import_module("tiddit.tiddit_gc")
+    ns.tiddit_coverage_analysis = importlib.import_module("tiddit.tiddit_coverage_analysis")
     _ns = ns
     return ns

@@ -332,6 +332,44 @@ def aggregate_cases():
     np.savez_compressed(os.path.join(HERE, "aggregate_cases.npz"), **out)
 
 
+def ploidy_cases():
+    """tiddit_coverage_analysis.determine_ploidy (the REAL one) on synthetic coverage / GC bins: library values and
+    the ploidies.tab text."""
+    import tempfile
+    rng = np.random.default_rng(31)
+    cases = []
+    tmp = tempfile.mkdtemp(prefix="tdt_ploidy_")
+    for k in range(6):
+        names = ["chr%d" % (i + 1) for i in range(int(rng.integers(2, 7)))]
+        cov, gc = {}, {}
+        for i, nm in enumerate(names):
+            nb = int(rng.integers(1, 1500))
+            base = float(rng.choice([10, 30, 15, 60]))
+            v = np.round(rng.gamma(20, base / 20, nb) * 50) / 50.0          # multiples of 1/50 with many ties
+            v[rng.random(nb) < 0.1] = 0.0
+            g = rng.integers(20, 70, nb).astype(np.int8)
+            g[rng.random(nb) < 0.05] = -1
+            if k == 2 and i == 1:
+                v[:] = 0.0                                                 # nothing qualifies -> nan -> 0
+            if k == 3 and i == 0:
+                nb2 = 2 * (nb // 2) + 2                                    # even count, all distinct
+                v = rng.permutation(nb2).astype(np.float64) + 1.5
+                g = np.full(nb2, 40, dtype=np.int8)
+            cov[nm], gc[nm] = v, g
+        c = 0 if k != 4 else 27.5
+        contigs = names[::-1] + ["not_there"]
+        prefix = os.path.join(tmp, "case%d" % k)
+        lib = R.tiddit_coverage_analysis.determine_ploidy(dict(cov), contigs, {"x": 1}, 2, prefix, c, "ref.fa", 50,
+                                                          {"SQ": []}, dict(gc))
+        cases.append({"names": names, "contigs": contigs, "c": c, "ploidy": 2,
+                      "cov": {n: cov[n].tolist() for n in names}, "gc": {n: gc[n].tolist() for n in names},
+                      "library": {kk: (float(v) if not isinstance(v, int) else v) for kk, v in lib.items()},
+                      "library_types": {kk: type(v).__name__ for kk, v in lib.items()},
+                      "tab": open(prefix + ".ploidies.tab").read()})
+    with open(os.path.join(HERE, "ploidy_cases.json"), "w") as f:
+        json.dump(cases, f, separators=(",", ":"))
+
+
 if __name__ == "__main__":
     config1_cov()
     dbscan_cases()
@@ -339,4 +377,5 @@ if __name__ == "__main__":
     gc_cases()
     cluster_cases()
     aggregate_cases()
+    ploidy_cases()
     print("golden vectors written to", HERE)

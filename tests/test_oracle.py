@@ -100,3 +100,19 @@ def test_aggregate_golden(oracle):
         assert np.array_equal(rows[:, [0, 1, 5, 6, 7, 8, 9, 10, 11, 12, 13, 4]], z[k + "expected"]), c
         rules |= set(rows[:, 14].tolist())
     assert rules == {0, 1, 2, 3, 4}
+
+
+def test_masked_medians_golden(oracle):
+    """tiddit_coverage_analysis.pyx:14-27: the oracle's medians against the library the real determine_ploidy built."""
+    from conftest import load_json
+    for c in load_json("ploidy_cases.json"):
+        names = c["names"]
+        cov = np.concatenate([np.array(c["cov"][n], dtype=np.float64) for n in names])
+        gc = np.concatenate([np.array(c["gc"][n], dtype=np.int8) for n in names])
+        off = np.concatenate([[0], np.cumsum([len(c["cov"][n]) for n in names])])
+        med, cnt = oracle.coverage_medians(cov, gc, off)
+        for i, n in enumerate(names):
+            want = c["library"]["avg_coverage_" + n]
+            assert (np.isnan(med[i]) and want == 0 and cnt[i] == 0) or med[i] == want
+        if not c["c"]:
+            assert med[-1] == c["library"]["avg_coverage"]

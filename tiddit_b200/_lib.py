@@ -34,6 +34,8 @@ SIGNATURES = {
                                              _p, _p, _p, _p, _sz, _p]),
     "tdt_coverage_accumulate": (ctypes.c_int, [_p, _p, _i64, _i32, _i32, _p, _i64, _p, _p]),
     "tdt_coverage_accumulate_contigs": (ctypes.c_int, [_p, _p, _i64, _p, _p, _p, _i32, _i32, _p, _i64, _p, _p]),
+    "tdt_coverage_medians_workspace_bytes": (_sz, [_i32]),
+    "tdt_coverage_medians": (ctypes.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _p, _sz, _p]),
     "tdt_gc_bins": (ctypes.c_int, [_p, _i64, _i32, _dbl, _p, _p]),
     "tdt_debug_segsort": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
 }

@@ -10,7 +10,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtdt_b200.so")
-SOURCES = ["tdt_api.cu", "tdt_cluster.cu", "tdt_aggregate.cu", "tdt_coverage.cu", "tdt_gc.cu"]
+SOURCES = ["tdt_api.cu", "tdt_cluster.cu", "tdt_aggregate.cu", "tdt_coverage.cu", "tdt_ploidy.cu", "tdt_gc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

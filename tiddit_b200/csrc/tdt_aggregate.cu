@@ -12,8 +12,7 @@
 // appearance in insertion order), the order tiddit_variant numbers SVs by.
 //
 // Pipeline (no host synchronisation, data-dependent sizes stay on the device):
-//   agg_survivor_scan    chained scan: rank of every surviving noise contig inside its pair
-//   agg_key              candidate key per signal (DBSCAN id | len(pair)+rank | dropped)
+//   agg_key              candidate key per signal (DBSCAN id | surviving noise contig | dropped)
 //   segsort #1           signals grouped by (pair, candidate key), stable => members in insertion order
 //   agg_mark_scan        chained scan over the sorted order: group heads, compaction of the kept signals
 //   agg_rank_scan        chained scan over insertion order: rank of every candidate by first appearance
@@ -59,8 +58,7 @@ struct AggParams {
     u32 sentinel;
     // scratch
     AggSmall *small;
-    u32 *surv_excl;      // [n]   rank of a surviving noise contig among all survivors (only written for survivors)
-    u32 *pair_base;      // [P]   survivors before the pair
+    u32 *pair_base;      // [P]   first survivor group of the pair
     u32 *pair_heads;     // bit j: j is the first signal of a pair
     u32 *key1, *key1s;   // [n]   candidate keys, insertion / sorted order
     int32_t *val1s;      // [n]   insertion index in sorted order
@@ -161,49 +159,12 @@ __global__ void agg_setup_kernel(AggParams a) {
     }
 }
 
-// ---- scan 1: surviving noise contigs (tiddit_cluster.pyx:163-168) --------------------------------------------------
+// ---- candidate keys; surviving noise contigs (tiddit_cluster.pyx:163-168) share one key below the sentinel: the stable
+// sort keeps them in insertion order behind the pair's clusters, each becomes a group, and its id len(pair) + k follows
+// from its rank among the pair's survivor groups -----------------------------------------------------------------------
 __device__ __forceinline__ bool survives(const AggParams &a, int64_t i, int p) {
     return a.labels[i] == -1 && (a.flags[i] & 3) == 2 && a.same_chrom[p] &&
            ((int64_t)a.posB[i] - (int64_t)a.posA[i]) < 2 * (int64_t)a.max_ins_len;
-}
-
-__global__ void __launch_bounds__(AG_THREADS) agg_survivor_scan_kernel(AggParams a) {
-    __shared__ ScanSmem s;
-    const int tile = take_tile(s, &a.small->ticket[0]);
-    const int64_t i0 = (int64_t)tile * AG_TILE + (int64_t)threadIdx.x * AG_ITEMS;
-    u32 f = 0, cnt = 0;
-    int p = 0;
-    if (i0 < a.n) {
-        p = find_pair(a.seg_off, a.P, i0);
-#pragma unroll
-        for (int k = 0; k < AG_ITEMS; k++) {
-            const int64_t i = i0 + k;
-            if (i < a.n) {
-                while (i >= a.seg_off[p + 1]) p++;
-                if (survives(a, i, p)) {
-                    f |= 1u << k;
-                    cnt++;
-                }
-            }
-        }
-    }
-    u32 pre, unused;
-    block_scan2(s, a.status1, tile, cnt, 0u, pre, unused);
-    if (i0 < a.n) {
-        p = find_pair(a.seg_off, a.P, i0);
-#pragma unroll
-        for (int k = 0; k < AG_ITEMS; k++) {
-            const int64_t i = i0 + k;
-            if (i < a.n) {
-                while (i >= a.seg_off[p + 1]) p++;
-                if (i == a.seg_off[p]) a.pair_base[p] = pre;
-                if (f & (1u << k)) {
-                    a.surv_excl[i] = pre;
-                    pre++;
-                }
-            }
-        }
-    }
 }
 
 __global__ void __launch_bounds__(256) agg_key_kernel(AggParams a) {
@@ -219,7 +180,7 @@ __global__ void __launch_bounds__(256) agg_key_kernel(AggParams a) {
     } else if (lab != -1) {
         atomicMax(&a.small->err, (int)AG_ERR_LABEL);
     } else if (survives(a, i, p)) {
-        key = (u32)(np + (int64_t)(a.surv_excl[i] - a.pair_base[p]));
+        key = a.sentinel - 1u;   // every survivor is its own candidate; its id is assigned from its rank in the pair
     }
     a.key1[i] = key;
 }
@@ -230,7 +191,7 @@ __global__ void __launch_bounds__(AG_THREADS) agg_mark_scan_kernel(AggParams a) 
     const int tile = take_tile(s, &a.small->ticket[1]);
     const int64_t j0 = (int64_t)tile * AG_TILE + (int64_t)threadIdx.x * AG_ITEMS;
     u32 keys[AG_ITEMS];
-    u32 headm = 0, keptm = 0;
+    u32 headm = 0, keptm = 0, firstsurv = 0;
     if (j0 < a.n) {
         u32 prev = j0 > 0 ? a.key1s[j0 - 1] : 0u;
 #pragma unroll
@@ -242,7 +203,8 @@ __global__ void __launch_bounds__(AG_THREADS) agg_mark_scan_kernel(AggParams a) 
                 const bool ph = (a.pair_heads[j >> 5] >> (j & 31)) & 1u;
                 if (key != a.sentinel) {
                     keptm |= 1u << k;
-                    if (ph || key != prev) headm |= 1u << k;
+                    if (ph || key != prev || key == a.sentinel - 1u) headm |= 1u << k;
+                    if (key == a.sentinel - 1u && (ph || key != prev)) firstsurv |= 1u << k;
                 }
                 prev = key;
             }
@@ -264,6 +226,7 @@ __global__ void __launch_bounds__(AG_THREADS) agg_mark_scan_kernel(AggParams a) 
                         a.goff[preH] = (int64_t)preK;
                         a.gpair[preH] = p;
                         a.gcid[preH] = (int32_t)keys[k];
+                        if (firstsurv & (1u << k)) a.pair_base[p] = preH;   // first survivor group of the pair
                         a.gfirst[idx] = (int32_t)preH + 1;
                         preH++;
                     }
@@ -290,12 +253,16 @@ __global__ void __launch_bounds__(AG_THREADS) agg_rank_scan_kernel(AggParams a) 
     const int64_t i0 = (int64_t)tile * AG_TILE + (int64_t)threadIdx.x * AG_ITEMS;
     int32_t g[AG_ITEMS];
     u32 cnt = 0;
+    if (i0 + AG_ITEMS <= a.n) {
+        const int4 v0 = *(const int4 *)(a.gfirst + i0), v1 = *(const int4 *)(a.gfirst + i0 + 4);
+        g[0] = v0.x; g[1] = v0.y; g[2] = v0.z; g[3] = v0.w;
+        g[4] = v1.x; g[5] = v1.y; g[6] = v1.z; g[7] = v1.w;
+    } else {
 #pragma unroll
-    for (int k = 0; k < AG_ITEMS; k++) {
-        const int64_t i = i0 + k;
-        g[k] = i < a.n ? a.gfirst[i] : 0;
-        cnt += g[k] != 0;
+        for (int k = 0; k < AG_ITEMS; k++) g[k] = i0 + k < a.n ? a.gfirst[i0 + k] : 0;
     }
+#pragma unroll
+    for (int k = 0; k < AG_ITEMS; k++) cnt += g[k] != 0;
     u32 pre, unused;
     block_scan2(s, a.status3, tile, cnt, 0u, pre, unused);
 #pragma unroll
@@ -305,18 +272,15 @@ __global__ void __launch_bounds__(AG_THREADS) agg_rank_scan_kernel(AggParams a) 
 
 // ---- accumulators ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) agg_init_kernel(AggParams a) {
-    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t G = a.small->d2.nseg;
-    if (t >= G) return;
-    int32_t *acc = a.acc + t * AG_ACC;
-#pragma unroll
-    for (int k = 0; k < 8; k++) acc[k] = (k & 1) ? (int32_t)0x80000000 : 0x7fffffff;   // even: min, odd: max
-#pragma unroll
-    for (int k = 8; k < AG_ACC; k++) acc[k] = 0;
-    u64 *md = a.modes + t * AG_MODES;
-#pragma unroll
-    for (int k = 0; k < AG_MODES; k++) md[k] = 0ull;
-    *(uint4 *)(a.ncnt + t * 4) = make_uint4(0u, 0u, 0u, 0u);
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const int64_t t0 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (int64_t t = t0; t < G * AG_ACC; t += stride) {
+        const int k = (int)(t % AG_ACC);
+        a.acc[t] = k >= 8 ? 0 : ((k & 1) ? (int32_t)0x80000000 : 0x7fffffff);   // even: min, odd: max, then sums
+    }
+    for (int64_t t = t0; t < G * AG_MODES; t += stride) a.modes[t] = 0ull;
+    for (int64_t t = t0; t < G; t += stride) ((uint4 *)a.ncnt)[t] = make_uint4(0u, 0u, 0u, 0u);
 }
 
 __device__ __forceinline__ int32_t seg_min(int32_t v, int32_t g, int lane) {
@@ -406,15 +370,35 @@ __global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *_
                                                        const int32_t *__restrict__ vals) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t M = a.small->d2.n;
-    if (c >= M) return;
-    const int32_t g = a.c_grp[c];
-    const int64_t lo = a.goff[g];
-    const u32 key = keys[c];
-    if (c > lo && keys[c - 1] == key) return;   // not a run head
+    const int lane = threadIdx.x & 31;
+    if (c - lane >= M) return;   // whole warp beyond the end
+    const bool live = c < M;
+    int32_t g = 0;
+    int64_t lo = 0;
+    u32 key = 0;
+    bool head = false;
+    if (live) {
+        g = a.c_grp[c];
+        lo = a.goff[g];
+        key = keys[c];
+        head = c == lo || keys[c - 1] != key;   // first element of a run of equal keys
+    }
     if (WHAT == 2) {
-        atomicAdd(a.ncnt + (int64_t)g * 4 + (key >> a.name_bits), 1u);
+        // distinct names per (candidate, kind): run heads counted per warp, one atomic per (candidate, kind, warp)
+        const u32 kind = key >> a.name_bits;
+        const u32 ck = live ? (((u32)g << 2) | kind) : (0xffffffffu - (u32)lane);
+        const u32 prevk = __shfl_up_sync(0xffffffffu, ck, 1);
+        const u32 nextk = __shfl_down_sync(0xffffffffu, ck, 1);
+        const u32 bnd = __ballot_sync(0xffffffffu, lane == 0 || prevk != ck);
+        const u32 heads = __ballot_sync(0xffffffffu, head);
+        if (live && (lane == 31 || nextk != ck)) {
+            const int start = 31 - __clz(bnd & lanemask_le());
+            const u32 cnt = __popc(heads & lanemask_le() & ~((1u << start) - 1u));
+            if (cnt) atomicAdd(a.ncnt + (int64_t)g * 4 + kind, cnt);
+        }
         return;
     }
+    if (!head) return;
     // run end: gallop, then bisect (keys ascend inside the candidate)
     const int64_t hi = a.goff[g + 1];
     int64_t left = c, step = 1;            // keys[left] == key
@@ -448,8 +432,11 @@ __global__ void __launch_bounds__(256) agg_finalize_kernel(AggParams a) {
     const uint4 nc = *(const uint4 *)(a.ncnt + g * 4);
     const int64_t lo = a.goff[g], hi = a.goff[g + 1];
     int32_t row[16];
-    row[0] = a.gpair[g];
-    row[1] = a.gcid[g];
+    const int p = a.gpair[g];
+    row[0] = p;
+    row[1] = (u32)a.gcid[g] == a.sentinel - 1u
+                 ? (int32_t)(a.seg_off[p + 1] - a.seg_off[p] + (g - (int64_t)a.pair_base[p]))   // len(pair) + k (:166)
+                 : a.gcid[g];
     row[2] = a.member_idx[lo];
     row[3] = (int32_t)lo;
     row[4] = (int32_t)(hi - lo);
@@ -552,7 +539,6 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
     a.ncnt = ar.take<u32>((size_t)n * 4);
     void *sort_temp = ar.take<char>(pl.sort);
     if (!sort_temp) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
-    a.surv_excl = tmpK;   // consumed by agg_key before the first sort touches its scratch
 
     TDT_CUDA(cudaMemsetAsync(ws, 0, (size_t)(zero_end - (char *)ws), st));
     TDT_CUDA(cudaMemsetAsync(a.counts_out, 0, 4 * sizeof(int64_t), st));
@@ -561,7 +547,6 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
     {
         ProfScope ps("agg_keys", st);
         TDT_LAUNCH(agg_setup_kernel, (unsigned)((P + 256) / 256), 256, 0, st, a);
-        TDT_LAUNCH(agg_survivor_scan_kernel, tiles, AG_THREADS, 0, st, a);
         TDT_LAUNCH(agg_key_kernel, per_elem, 256, 0, st, a);
     }
     {
@@ -575,7 +560,7 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
         ProfScope ps("agg_groups", st);
         TDT_LAUNCH(agg_mark_scan_kernel, tiles, AG_THREADS, 0, st, a);
         TDT_LAUNCH(agg_rank_scan_kernel, tiles, AG_THREADS, 0, st, a);
-        TDT_LAUNCH(agg_init_kernel, per_elem, 256, 0, st, a);
+        TDT_LAUNCH(agg_init_kernel, 148 * 8, 256, 0, st, a);
     }
     {
         ProfScope ps("agg_gather", st);

@@ -221,6 +221,32 @@ def coverage_accumulate_contigs_device(start, end, read_off, bin_off, end_bin_si
     return bins
 
 
+def coverage_medians_device(bins, gc, bin_off, C, medians_out=None, counts_out=None):
+    """tiddit_coverage_analysis.pyx:14-27 on CUDA tensors (float64 bins, int8 gc, int64 bin_off[C+1]) ->
+    (float64 [C+1] medians: contigs then genome-wide, int64 [C+1] qualifying bins); nothing synchronises."""
+    torch = _lib.torch_cuda()
+    L = _lib.lib()
+    if medians_out is None:
+        medians_out = torch.empty(C + 1, dtype=torch.float64, device="cuda")
+    if counts_out is None:
+        counts_out = torch.empty(C + 1, dtype=torch.int64, device="cuda")
+    ws = _lib.workspace(torch, L.tdt_coverage_medians_workspace_bytes(int(C)), tag="medians")
+    rc = L.tdt_coverage_medians(_lib.ptr(bins), _lib.ptr(gc), _lib.ptr(bin_off), int(C), int(bins.numel()),
+                                _lib.ptr(medians_out), _lib.ptr(counts_out), _lib.ptr(ws), ws.numel(),
+                                _lib.stream_ptr(torch))
+    _lib.check(rc)
+    return medians_out, counts_out
+
+
+def coverage_medians(bins, gc, bin_off):
+    """Host front end: numpy float64 bins / int8 gc of all contigs back to back + int64 bin_off -> numpy (medians, counts)."""
+    torch = _lib.torch_cuda()
+    bin_off = np.ascontiguousarray(bin_off, dtype=np.int64)
+    med, cnt = coverage_medians_device(_lib.to_device(torch, bins, np.float64), _lib.to_device(torch, gc, np.int8),
+                                       _lib.to_device(torch, bin_off, np.int64), len(bin_off) - 1)
+    return med.cpu().numpy(), cnt.cpu().numpy()
+
+
 # ---------------------------------------------------------------------------------------------
 # GC
 # ---------------------------------------------------------------------------------------------
