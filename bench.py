@@ -305,6 +305,136 @@ def coverage_leg(torch, args, hbm_peak, flush):
 
 
 # ---------------------------------------------------------------------------------------------------
+# candidate aggregation + ploidy medians legs (N = 1; the SURVEY 8(f) rows built so far)
+# ---------------------------------------------------------------------------------------------------
+def aggregate_leg(torch, args, posA, posB, seg_off, L, eps, m, hbm_peak, flush):
+    """tdt_cluster_aggregate on the step's own labels: candidates/s, stage times, CPU port on a bounded sample."""
+    from tiddit_b200 import device_ops, synth, _lib
+    n, P = len(posA), len(seg_off) - 1
+    rec = synth.signal_records(posA, posB, seg_off)
+    d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    A, B, O = d(posA), d(posB), d(seg_off)
+    span, name, flags, same = d(rec["span"]), d(rec["name_id"]), d(rec["flags"]), d(rec["same_chrom"])
+    labels = device_ops.cluster_labels_device(A, B, O, P, eps, m, L)
+    rows = torch.empty((n, 16), dtype=torch.int32, device="cuda")
+    mem = torch.empty(n, dtype=torch.int32, device="cuda")
+    counts = torch.zeros(4, dtype=torch.int64, device="cuda")
+    max_ins, is_mp, min_reads = 5000, False, 3
+    run = lambda: device_ops.cluster_aggregate_device(labels, A, B, span, name, flags, O, same, P, max_ins, is_mp,
+                                                      min_reads, L, n, rows, mem, counts)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    times, stages = [], {}
+    c0 = _lib.launch_count()
+    run()
+    launches = _lib.launch_count() - c0
+    for it in range(args.warmup + args.steps):
+        flush()
+        ev[0].record()
+        run()
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            times.append(ev[0].elapsed_time(ev[1]))
+    for _ in range(3):
+        flush()
+        torch.cuda.synchronize()
+        _lib.profile_begin()
+        run()
+        for k, v in _lib.profile_end():
+            stages[k] = stages.get(k, 0.0) + v / 3
+    ms = float(np.mean(times))
+    C, M, err, _ = (int(v) for v in counts.cpu().tolist())
+    alg = 33.0 * n + 4.0 * M + 64.0 * C
+    out = {"signals": n, "candidates": C, "members": M, "ms_per_step": ms, "signals_per_sec": n / ms * 1e3,
+           "candidates_per_sec": C / ms * 1e3, "gpu_launches_per_step": int(launches), "data_error": err,
+           "stages_ms": {k: round(v, 4) for k, v in stages.items()},
+           "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg / ms / 1e6 / hbm_peak,
+                        "algorithmic_bytes": "33 B/signal in (label, posA, posB, 4 x span, name id, flags) + 4 B/member "
+                                             "+ 64 B/candidate out; the four sorts are implementation traffic"}}
+    if not args.no_cpu:
+        from oracle import oracle
+        k = int(np.searchsorted(seg_off, 2_000_000, side="right"))          # whole pairs, about 2M signals
+        k = max(k, 1)
+        hi = int(seg_off[k])
+        lab_h = labels[:hi].cpu().numpy()
+        a = (lab_h, posA[:hi], posB[:hi], rec["span"][:hi], rec["name_id"][:hi], rec["flags"][:hi], seg_off[:k + 1],
+             rec["same_chrom"][:k], max_ins, is_mp, min_reads)
+        t0 = time.perf_counter()
+        want_rows, want_mem = oracle.cluster_aggregate(*a)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": hi / dt, "unit": "signals/s", "cores": 1, "kind": "port",
+                               "sample": "the first %d pairs (%d signals) through the C restatement of "
+                                         "tiddit_cluster.pyx:156-336, %.2f s; the reference itself does this fold in "
+                                         "interpreted Python per signal" % (k, hi, dt)}
+        got_rows = rows[:C].cpu().numpy()
+        sel = got_rows[:, 0] < k
+        keep = [c for c in range(16) if c != 3]
+        out["verified"] = bool(np.array_equal(got_rows[sel][:, keep], want_rows[:, keep]))
+    return out
+
+
+def medians_leg(torch, args, hbm_peak, flush):
+    """tdt_coverage_medians on 61.8 M bins (GRCh38, bin size 50: the arrays determine_ploidy walks in --sv runs)."""
+    from tiddit_b200 import device_ops, synth
+    lens = np.array([ln for _, ln in synth.GRCH38], dtype=np.int64)
+    nb = (lens + 49) // 50
+    off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+    n = int(off[-1])
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    cov = torch.round(torch.rand(n, device="cuda", generator=g, dtype=torch.float64) * 3000) / 50.0
+    cov[torch.rand(n, device="cuda", generator=g) < 0.08] = 0.0
+    gc = torch.randint(-1, 80, (n,), device="cuda", generator=g, dtype=torch.int8)
+    off_d = torch.from_numpy(off).cuda()
+    med = torch.empty(len(nb) + 1, dtype=torch.float64, device="cuda")
+    cnt = torch.empty(len(nb) + 1, dtype=torch.int64, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    times = []
+    for it in range(args.warmup + args.steps):
+        flush()
+        ev[0].record()
+        device_ops.coverage_medians_device(cov, gc, off_d, len(nb), med, cnt)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            times.append(ev[0].elapsed_time(ev[1]))
+    ms = float(np.mean(times))
+    out = {"bins": n, "contigs": len(nb), "ms_per_step": ms, "bins_per_sec": n / ms * 1e3, "gpu_launches_per_step": 18,
+           "roofline": {"bound": "hbm", "achieved": 9.0 * n / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": 9.0 * n / ms / 1e6 / hbm_peak,
+                        "algorithmic_bytes": "9 B/bin (float64 coverage + int8 GC), read once; the radix select "
+                                             "streams them 9 times (8 digit passes + the upper-median pass)"}}
+    if not args.no_cpu:
+        R = _ref_modules()
+        lo, hi = int(off[20]), int(off[22])                                  # chr21 + chr22: 1.95 M bins
+        cov_h, gc_h = cov[lo:hi].cpu().numpy(), gc[lo:hi].cpu().numpy()
+        names = ["chr21", "chr22"]
+        cd = {nm: cov_h[int(off[20 + i]) - lo:int(off[21 + i]) - lo] for i, nm in enumerate(names)}
+        gd = {nm: gc_h[int(off[20 + i]) - lo:int(off[21 + i]) - lo] for i, nm in enumerate(names)}
+        import tempfile
+        t0 = time.perf_counter()
+        if R is not None and hasattr(R, "tiddit_coverage_analysis"):
+            lib = R.tiddit_coverage_analysis.determine_ploidy(cd, names, {}, 2, os.path.join(tempfile.mkdtemp(), "p"), 0,
+                                                              "", 50, {"SQ": []}, gd)
+            want = [lib["avg_coverage_chr21"], lib["avg_coverage_chr22"]]
+            kind = "reference"
+        else:
+            from oracle import oracle
+            m_, _ = oracle.coverage_medians(cov_h, gc_h, off[20:23] - off[20])
+            want = m_[:2].tolist()
+            kind = "port"
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": (hi - lo) / dt, "unit": "bins/s", "cores": 1, "kind": kind,
+                               "sample": "determine_ploidy on chr21 + chr22 (%d bins), %.1f s" % (hi - lo, dt)}
+        got = med.cpu().numpy()
+        out["verified"] = bool(got[20] == want[0] and got[21] == want[1])
+    del cov, gc
+    torch.cuda.empty_cache()
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # main (our arm)
 # ---------------------------------------------------------------------------------------------------
 def main():
@@ -320,6 +450,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true", help="issue the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--chunks", type=int, default=6, help="pair chunks of the pipelined host path (e2e, N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
+    ap.add_argument("--no-extra", action="store_true", help="skip the candidate-aggregation and ploidy-median legs")
     ap.add_argument("--ref-crops-per-core", type=int, default=1, help="--impl reference: 50k-signal crops per core per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -379,19 +510,16 @@ def main():
         if world > 1:
             dist.all_gather_into_tensor(gathered, labels_d)
 
-    pipe = engine.HostPipeline(n_total, n_chunks=args.chunks) if world == 1 else None
+    # e2e: every rank pipelines ITS shard (pinned host arrays -> H2D | kernels | D2H of the shard's labels into the
+    # rank's own pinned buffer, chunked over three streams); with N > 1 the labels are then all-gathered on the device
+    # like in the device-resident step, so every GPU ends up with every label.
+    pipe = engine.HostPipeline(max(pad, n_mine, 1), n_chunks=args.chunks if world == 1 else max(2, args.chunks // 2))
+    shard_pin = out_pin if world == 1 else torch.empty(max(n_mine, 1), dtype=torch.int32).pin_memory()
 
-    def step_e2e(a_dev, b_dev, off_dev):
-        if world == 1:       # chunked: H2D / kernels / D2H overlap on three streams
-            pipe.run(a_pin, b_pin, off_h, eps, m, L, out_pin)
-            return
-        a_dev.copy_(a_pin, non_blocking=True)
-        b_dev.copy_(b_pin, non_blocking=True)
-        off_dev.copy_(off_pin, non_blocking=True)
-        device_ops.cluster_labels_device(a_dev, b_dev, off_dev, P_mine, eps, m, L, labels_out=labels_d[:n_mine])
-        dist.all_gather_into_tensor(gathered, labels_d)
-        if rank == 0:
-            out_pin.copy_(gathered, non_blocking=True)
+    def step_e2e():
+        pipe.run(a_pin, b_pin, off_h, eps, m, L, shard_pin)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, pipe.lab_d[:pad])
 
     def barrier():
         if world > 1:
@@ -427,8 +555,7 @@ def main():
         if runner is not None:
             runner.check()
             launches = launches_per_call   # replayed launches are not re-issued through the library's counter
-        a2, b2, off2 = torch.empty_like(a_d), torch.empty_like(b_d), torch.empty_like(off_d)
-        ms_e2e = timed(lambda: step_e2e(a2, b2, off2), max(3, args.steps // 2), 2)
+        ms_e2e = timed(step_e2e, max(3, args.steps // 2), 3)
     clocks = clk.summary()
 
     # per-stage device times of one more (untimed) pass -> roofline of the eps-range-query kernel
@@ -475,29 +602,41 @@ def main():
                        "launch": "eager" if args.no_graph else "CUDA-graph replay of the ABI call's kernels"},
             "e2e": {"value": n_total / ms_e2e * 1e3, "unit": UNIT, "ms_per_step": ms_e2e,
                     "path": "engine.HostPipeline: %d tapered pair chunks, H2D | CUDA-graph replay of the chunk kernels | D2H on 3 streams, one host sync" % args.chunks
-                    if world == 1 else "per-rank H2D, kernels, all-gather, rank-0 D2H",
-                    "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + off_h.nbytes),
-                    "d2h_bytes_per_step": int(out_pin.numel() * 4) if rank == 0 else 0},
+                    if world == 1 else "per rank: engine.HostPipeline over its shard (H2D | kernels | D2H of the shard's "
+                    "labels to the rank's pinned buffer), then the device all-gather of all labels",
+                    "h2d_bytes_per_step": int(a_h.nbytes + b_h.nbytes + off_h.nbytes) * (1 if world == 1 else 1),
+                    "d2h_bytes_per_step": int(n_mine * 4),
+                    "bytes_note": "per rank (rank 0 shown)" if world > 1 else "whole job"},
             "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
             "clocks": clocks, "roofline": roofline}
 
     # result check of what the timed paths produced (the oracle as checker, bounded to the sample pairs' cost)
     torch.cuda.synchronize()
+    if world > 1:
+        shard_ok = bool(torch.equal(shard_pin[:n_mine], labels_d[:n_mine].cpu()))   # e2e shard == device-resident shard
+        out_pin.copy_(gathered)          # the all-gathered labels of the last e2e step
+        torch.cuda.synchronize()
     if rank == 0:
         from oracle import oracle
         got_all = out_pin.numpy()[plan.gather_index()] if world > 1 else out_pin.numpy()
         want_all = oracle.cluster_segments(posA, posB, seg_off, eps, m)
-        line["verified"] = bool(np.array_equal(got_all, want_all))
+        line["verified"] = bool(np.array_equal(got_all, want_all)) and (world == 1 or shard_ok)
     if world == 1 and rank == 0:
         if not args.no_cpu:
             line["cpu_baseline"] = cpu_cluster_baseline(posA, posB, seg_off, eps, m)
         if not args.no_coverage:
-            del a2, b2, off2
             torch.cuda.empty_cache()
             try:
                 line["coverage"] = coverage_leg(torch, args, hbm_peak, flush)
             except torch.cuda.OutOfMemoryError as exc:
                 line["coverage"] = {"error": "out of memory: %s" % exc}
+        if not args.no_extra:
+            _lib.release_workspaces()
+            torch.cuda.empty_cache()
+            line["aggregate"] = aggregate_leg(torch, args, posA, posB, seg_off, L, eps, m, hbm_peak, flush)
+            _lib.release_workspaces()
+            torch.cuda.empty_cache()
+            line["ploidy_medians"] = medians_leg(torch, args, hbm_peak, flush)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

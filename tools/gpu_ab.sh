@@ -7,7 +7,7 @@ for v in ${VARIANTS:-base:}; do
   echo "== variant $name  defs: $defs"
   TDT_NVCC_DEFS="$defs" python -m tiddit_b200.build --force > gpurun_out/ab_build_$name.log 2>&1 || { echo build failed; tail -5 gpurun_out/ab_build_$name.log; continue; }
   timeout 600 python -m pytest tests/test_gpu_segsort.py tests/test_gpu_cluster.py -m gpu -q -x --timeout 300 2>&1 | tail -2
-  timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu --no-coverage ${BENCH_ARGS} > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+  timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu --no-coverage --no-extra ${BENCH_ARGS} > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
   python - <<PY
 import json
 try:
