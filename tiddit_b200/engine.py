@@ -239,3 +239,101 @@ def sharded_labels(posA, posB, seg_off, epsilon, m, max_pos=0, group=None, label
     recv = torch.empty(world * plan.pad, dtype=torch.int32, device=dev)
     dist.all_gather_into_tensor(recv, send, group=group)
     return recv.cpu().numpy()[plan.gather_index()]
+
+
+# ---------------------------------------------------------------------------------------------
+# multi-GPU: coverage by read slices, GC by contig
+# ---------------------------------------------------------------------------------------------
+def read_slices(read_off, world, rank):
+    """Rank `rank`'s contiguous share of every contig's reads -> list of (lo, hi) per contig.  Every contig is cut
+    into `world` nearly equal slices, so the ranks stay balanced whatever the contig sizes are."""
+    read_off = np.asarray(read_off, dtype=np.int64)
+    out = []
+    for c in range(len(read_off) - 1):
+        lo, hi = int(read_off[c]), int(read_off[c + 1])
+        k = hi - lo
+        out.append((lo + k * rank // world, lo + k * (rank + 1) // world))
+    return out
+
+
+def sharded_coverage(start, end, read_off, lengths, bin_size, group=None, accumulate_fn=None):
+    """Coverage bins of ALL contigs (numpy float64, contigs back to back) on every rank; each rank accumulates its
+    slice of every contig's reads (tiddit_coverage.pyx:48-74 per read) and ONE all-reduce(sum) adds the partial bins.
+    Every addend is a float32 quotient or 1.0 and bin totals stay far below 2^53 units of the smallest addend, so
+    float64 sums are exact in ANY order: the all-reduce -- ring, tree or in-switch -- returns bins
+    bit-identical to the sequential loop.
+
+    start / end: int32 host arrays of all reads, grouped by contig (read_off[C+1]); lengths[C]: contig lengths.
+    accumulate_fn(start, end, read_off, bin_off, end_bin_size, bin_size, n_bins) -> float64 bins: the per-rank
+    kernel front end; defaults to the GPU path.  The gloo tests inject the oracle."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    lengths = np.asarray(lengths, dtype=np.int64)
+    nb = np.ceil(lengths / float(bin_size)).astype(np.int64)
+    bin_off = np.concatenate([[0], np.cumsum(nb)]).astype(np.int64)
+    ebs = (lengths - (nb - 1) * bin_size).astype(np.int32)
+    sl = read_slices(read_off, world, rank)
+    s = np.concatenate([start[lo:hi] for lo, hi in sl]) if sl else np.zeros(0, dtype=np.int32)
+    e = np.concatenate([end[lo:hi] for lo, hi in sl]) if sl else np.zeros(0, dtype=np.int32)
+    my_off = np.concatenate([[0], np.cumsum([hi - lo for lo, hi in sl])]).astype(np.int64)
+    on_gpu = dist.get_backend(group) == "nccl"
+    if accumulate_fn is None:
+        accumulate_fn = _coverage_contigs_gpu
+    bins = accumulate_fn(np.ascontiguousarray(s, dtype=np.int32), np.ascontiguousarray(e, dtype=np.int32), my_off, bin_off,
+                         ebs, int(bin_size), int(bin_off[-1]))
+    if isinstance(bins, np.ndarray):
+        bins = torch.from_numpy(bins)
+        if on_gpu:
+            bins = bins.cuda()
+    dist.all_reduce(bins, op=dist.ReduceOp.SUM, group=group)
+    return bins.cpu().numpy(), bin_off
+
+
+def _coverage_contigs_gpu(s, e, read_off, bin_off, ebs, bin_size, n_bins):
+    torch = _lib.torch_cuda()
+    bins = torch.zeros(n_bins, dtype=torch.float64, device="cuda")
+    bad = device_ops.new_first_bad(torch)
+    if len(s):
+        device_ops.coverage_accumulate_contigs_device(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda(),
+                                                      torch.from_numpy(read_off).cuda(), torch.from_numpy(bin_off).cuda(),
+                                                      torch.from_numpy(ebs).cuda(), bin_size, bins, bad)
+    if int(bad.item()) != device_ops.FIRST_BAD_NONE:
+        raise IndexError("Out of bounds on buffer access (axis 0)")
+    return bins
+
+
+def sharded_gc(sequences, bin_size, n_cutoff, group=None, gc_fn=None):
+    """GC bins of ALL contigs ({name: int8 ndarray}) on every rank; contigs are dealt to ranks longest-first and the
+    int8 bins all-gathered once (tiddit_gc.pyx:35-42 fans contigs out over joblib processes the same way).
+    sequences: {name: uint8 array / bytes}; gc_fn(seq, bin_size, n_cutoff) -> int8 bins defaults to the GPU path."""
+    import torch
+    import torch.distributed as dist
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    names = list(sequences)
+    lens = [len(sequences[n]) for n in names]
+    owner = lpt_assign(lens, world)
+    nb = [int(-(-ln // bin_size)) for ln in lens]
+    mine = [i for i in range(len(names)) if owner[i] == rank]
+    per_rank = [sum(nb[i] for i in range(len(names)) if owner[i] == r) for r in range(world)]
+    pad = max(per_rank) if per_rank else 0
+    if gc_fn is None:
+        from . import tiddit_gc
+        gc_fn = tiddit_gc.gc_bins
+    on_gpu = dist.get_backend(group) == "nccl"
+    dev = torch.device("cuda", torch.cuda.current_device()) if on_gpu else torch.device("cpu")
+    send = torch.zeros(max(pad, 1), dtype=torch.int8, device=dev)
+    pos = 0
+    for i in mine:
+        if nb[i]:
+            send[pos:pos + nb[i]] = torch.from_numpy(np.asarray(gc_fn(sequences[names[i]], bin_size, n_cutoff), dtype=np.int8)).to(dev)
+        pos += nb[i]
+    recv = torch.empty(world * max(pad, 1), dtype=torch.int8, device=dev)
+    dist.all_gather_into_tensor(recv, send, group=group)
+    recv = recv.cpu().numpy()
+    out, cursor = {}, [r * max(pad, 1) for r in range(world)]
+    for i, name in enumerate(names):
+        r = int(owner[i])
+        out[name] = recv[cursor[r]:cursor[r] + nb[i]].copy()
+        cursor[r] += nb[i]
+    return out
