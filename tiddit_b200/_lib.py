@@ -76,7 +76,7 @@ def profile_begin():
 
 def profile_end():
     """-> list of (stage, milliseconds) in call order since profile_begin()."""
-    buf = ctypes.create_string_buffer(1 << 16)
+    buf = ctypes.create_string_buffer(1 << 18)
     n = lib().tdt_profile_end(buf, len(buf))
     if n < 0:
         check(n)

@@ -12,9 +12,10 @@
 // appearance in insertion order), the order tiddit_variant numbers SVs by.
 //
 // Pipeline (no host synchronisation, data-dependent sizes stay on the device):
-//   agg_key              candidate key per signal (DBSCAN id | surviving noise contig | dropped)
-//   segsort #1           signals grouped by (pair, candidate key), stable => members in insertion order
-//   agg_mark_scan        chained scan over the sorted order: group heads, compaction of the kept signals
+//   agg_key_scan         chained scan over insertion order: candidate key per signal (DBSCAN id | surviving noise
+//                        contig | dropped), the kept signals compacted (noise never reaches the sort)
+//   segsort #1           kept signals grouped by (pair, candidate key), stable => members in insertion order
+//   agg_mark_scan        chained scan over the sorted order: group heads, group offsets
 //   agg_rank_scan        chained scan over insertion order: rank of every candidate by first appearance
 //   agg_gather           per member: (kind,posA) (kind,posB) (kind,name) sort keys; min/max/orientation sums by a
 //                        segmented warp reduction, one atomic per (candidate, warp)
@@ -39,7 +40,7 @@ struct AggDims {
 };
 
 struct AggSmall {                // one 256-byte aligned record of device-side scalars
-    AggDims d1;                  // {n, P}
+    AggDims d1;                  // {kept signals, P}
     AggDims d2;                  // {members kept, candidates}
     u32 ticket[4];
     int err;
@@ -59,9 +60,11 @@ struct AggParams {
     // scratch
     AggSmall *small;
     u32 *pair_base;      // [P]   first survivor group of the pair
-    u32 *pair_heads;     // bit j: j is the first signal of a pair
-    u32 *key1, *key1s;   // [n]   candidate keys, insertion / sorted order
-    int32_t *val1s;      // [n]   insertion index in sorted order
+    u32 *pair_heads;     // bit j: kept signal j is the first of its pair
+    u32 *key1, *key1s;   // [M]   candidate keys of the kept signals, insertion / sorted order
+    int32_t *val1;       // [M]   insertion index of the kept signals (sorted order: member_idx)
+    int32_t *val1s;      // [M]   sub-sort values
+    int64_t *coff;       // [P+1] pair offsets into the kept signals
     int32_t *gfirst;     // [n]   (group + 1) at the insertion index of a group's first member, else 0
     int32_t *c_grp;      // [M]   group of every kept signal (sorted order)
     int64_t *goff;       // [G+1] group offsets into the compact order
@@ -147,99 +150,152 @@ __device__ __forceinline__ int find_pair(const int64_t *__restrict__ off, int P,
     return lo;
 }
 
-__global__ void agg_setup_kernel(AggParams a) {
-    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (s == 0) {
-        a.small->d1.n = a.n;
-        a.small->d1.nseg = a.P;
-    }
-    if (s < a.P) {
-        const int64_t q = a.seg_off[s];
-        if (a.seg_off[s + 1] > q) atomicOr(a.pair_heads + (q >> 5), 1u << (q & 31));
-    }
-}
-
-// ---- candidate keys; surviving noise contigs (tiddit_cluster.pyx:163-168) share one key below the sentinel: the stable
-// sort keeps them in insertion order behind the pair's clusters, each becomes a group, and its id len(pair) + k follows
-// from its rank among the pair's survivor groups -----------------------------------------------------------------------
-__device__ __forceinline__ bool survives(const AggParams &a, int64_t i, int p) {
-    return a.labels[i] == -1 && (a.flags[i] & 3) == 2 && a.same_chrom[p] &&
-           ((int64_t)a.posB[i] - (int64_t)a.posA[i]) < 2 * (int64_t)a.max_ins_len;
-}
-
-__global__ void __launch_bounds__(256) agg_key_kernel(AggParams a) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= a.n) return;
-    const int p = find_pair(a.seg_off, a.P, i);
-    const int64_t np = a.seg_off[p + 1] - a.seg_off[p];
+// ---- candidate keys + compaction (scan 1, insertion order).  Noise is dropped here, before the sort; surviving noise
+// contigs (tiddit_cluster.pyx:163-168) share one key below the sentinel: the stable sort keeps them in insertion
+// order behind the pair's clusters, each becomes a group of its own, and its id len(pair) + k follows from its rank
+// among the pair's survivor groups. -------------------------------------------------------------------------------------
+__device__ __forceinline__ u32 candidate_key(const AggParams &a, int64_t i, int p, int64_t np) {
     const int32_t lab = a.labels[i];
-    u32 key = a.sentinel;
     if (lab >= 0) {
-        if (lab >= np) atomicMax(&a.small->err, (int)AG_ERR_LABEL);   // DBSCAN ids are < len(pair)
-        else key = (u32)lab;
-    } else if (lab != -1) {
-        atomicMax(&a.small->err, (int)AG_ERR_LABEL);
-    } else if (survives(a, i, p)) {
-        key = a.sentinel - 1u;   // every survivor is its own candidate; its id is assigned from its rank in the pair
+        if (lab >= np) {   // DBSCAN ids are < len(pair)
+            atomicMax(&a.small->err, (int)AG_ERR_LABEL);
+            return a.sentinel;
+        }
+        return (u32)lab;
     }
-    a.key1[i] = key;
+    if (lab != -1) {
+        atomicMax(&a.small->err, (int)AG_ERR_LABEL);
+        return a.sentinel;
+    }
+    if ((a.flags[i] & 3) == 2 && a.same_chrom[p] &&
+        ((int64_t)a.posB[i] - (int64_t)a.posA[i]) < 2 * (int64_t)a.max_ins_len)
+        return a.sentinel - 1u;
+    return a.sentinel;
 }
 
-// ---- scan 2: group heads + compaction over the (pair, key)-sorted order ----------------------------------------------
+__global__ void __launch_bounds__(AG_THREADS) agg_key_scan_kernel(AggParams a) {
+    __shared__ ScanSmem s;
+    __shared__ int s_p0;
+    const int tile = take_tile(s, &a.small->ticket[0]);
+    const int64_t t0 = (int64_t)tile * AG_TILE;
+    if (threadIdx.x == 0) s_p0 = find_pair(a.seg_off, a.P, t0);
+    __syncthreads();
+    const int64_t i0 = t0 + (int64_t)threadIdx.x * AG_ITEMS;
+    u32 keys[AG_ITEMS];
+    u32 keptm = 0;
+    int p = s_p0;
+    if (i0 < a.n) {
+        // the pair of the thread's first signal: a short walk from the tile's pair, a bisection when pairs are tiny
+        int steps = 0;
+        while (i0 >= a.seg_off[p + 1] && steps < 8) {
+            p++;
+            steps++;
+        }
+        if (i0 >= a.seg_off[p + 1]) p = find_pair(a.seg_off, a.P, i0);
+        int q = p;
+        int64_t qend = a.seg_off[q + 1], qn = qend - a.seg_off[q];
+#pragma unroll
+        for (int k = 0; k < AG_ITEMS; k++) {
+            const int64_t i = i0 + k;
+            if (i < a.n) {
+                while (i >= qend) {
+                    q++;
+                    qend = a.seg_off[q + 1];
+                    qn = qend - a.seg_off[q];
+                }
+                keys[k] = candidate_key(a, i, q, qn);
+                if (keys[k] != a.sentinel) keptm |= 1u << k;
+            }
+        }
+    }
+    u32 pre, unused;
+    block_scan2(s, a.status1, tile, (u32)__popc(keptm), 0u, pre, unused);
+    if (i0 < a.n) {
+        int q = p;
+#pragma unroll
+        for (int k = 0; k < AG_ITEMS; k++) {
+            const int64_t i = i0 + k;
+            if (i < a.n) {
+                while (i >= a.seg_off[q + 1]) q++;
+                if (i == a.seg_off[q]) {   // first signal of pair q (and of the empty pairs right before it)
+                    for (int e = q; e >= 0 && a.seg_off[e] == i; e--) a.coff[e] = (int64_t)pre;
+                }
+                if (keptm & (1u << k)) {
+                    a.key1[pre] = keys[k];
+                    a.val1[pre] = (int32_t)i;
+                    pre++;
+                }
+                if (i == a.n - 1) {   // totals; trailing empty pairs
+                    for (int e = a.P; e > q; e--) a.coff[e] = (int64_t)pre;
+                    a.small->d1.n = (int64_t)pre;
+                    a.small->d1.nseg = a.P;
+                    a.small->d2.n = (int64_t)pre;
+                    a.counts_out[1] = (int64_t)pre;
+                }
+            }
+        }
+    }
+}
+
+__global__ void agg_heads_kernel(AggParams a) {
+    const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < a.P) {
+        const int64_t q = a.coff[s];
+        if (a.coff[s + 1] > q) atomicOr(a.pair_heads + (q >> 5), 1u << (q & 31));
+    }
+}
+
+// ---- scan 2: group heads over the (pair, key)-sorted kept signals ------------------------------------------------------
 __global__ void __launch_bounds__(AG_THREADS) agg_mark_scan_kernel(AggParams a) {
     __shared__ ScanSmem s;
     const int tile = take_tile(s, &a.small->ticket[1]);
+    const int64_t M = a.small->d2.n;
     const int64_t j0 = (int64_t)tile * AG_TILE + (int64_t)threadIdx.x * AG_ITEMS;
+    if ((int64_t)tile * AG_TILE >= M) {
+        if (M == 0 && tile == 0 && threadIdx.x == 0) a.goff[0] = 0;
+        return;   // nobody waits on a tile behind the last signal
+    }
     u32 keys[AG_ITEMS];
-    u32 headm = 0, keptm = 0, firstsurv = 0;
-    if (j0 < a.n) {
+    u32 headm = 0, firstsurv = 0;
+    if (j0 < M) {
         u32 prev = j0 > 0 ? a.key1s[j0 - 1] : 0u;
+        u32 hw = a.pair_heads[j0 >> 5] >> (j0 & 31);   // j0 is a multiple of 8: the 8 bits sit in one word
 #pragma unroll
         for (int k = 0; k < AG_ITEMS; k++) {
             const int64_t j = j0 + k;
-            if (j < a.n) {
+            if (j < M) {
                 const u32 key = a.key1s[j];
                 keys[k] = key;
-                const bool ph = (a.pair_heads[j >> 5] >> (j & 31)) & 1u;
-                if (key != a.sentinel) {
-                    keptm |= 1u << k;
-                    if (ph || key != prev || key == a.sentinel - 1u) headm |= 1u << k;
-                    if (key == a.sentinel - 1u && (ph || key != prev)) firstsurv |= 1u << k;
-                }
+                const bool ph = (hw >> k) & 1u;
+                if (ph || key != prev || key == a.sentinel - 1u) headm |= 1u << k;
+                if (key == a.sentinel - 1u && (ph || key != prev)) firstsurv |= 1u << k;
                 prev = key;
             }
         }
     }
-    u32 preH, preK;
-    block_scan2(s, a.status2, tile, (u32)__popc(headm), (u32)__popc(keptm), preH, preK);
-    if (j0 < a.n) {
+    u32 preH, unused;
+    block_scan2(s, a.status2, tile, (u32)__popc(headm), 0u, preH, unused);
+    if (j0 < M) {
         int p = -1;
 #pragma unroll
         for (int k = 0; k < AG_ITEMS; k++) {
             const int64_t j = j0 + k;
-            if (j < a.n) {
-                if (keptm & (1u << k)) {
-                    const int32_t idx = a.val1s[j];
-                    if (headm & (1u << k)) {
-                        if (p < 0) p = find_pair(a.seg_off, a.P, j);
-                        while (j >= a.seg_off[p + 1]) p++;
-                        a.goff[preH] = (int64_t)preK;
-                        a.gpair[preH] = p;
-                        a.gcid[preH] = (int32_t)keys[k];
-                        if (firstsurv & (1u << k)) a.pair_base[p] = preH;   // first survivor group of the pair
-                        a.gfirst[idx] = (int32_t)preH + 1;
-                        preH++;
-                    }
-                    a.member_idx[preK] = idx;
-                    a.c_grp[preK] = (int32_t)preH - 1;
-                    preK++;
+            if (j < M) {
+                if (headm & (1u << k)) {
+                    if (p < 0) p = find_pair(a.coff, a.P, j);
+                    while (j >= a.coff[p + 1]) p++;
+                    a.goff[preH] = j;
+                    a.gpair[preH] = p;
+                    a.gcid[preH] = (int32_t)keys[k];
+                    if (firstsurv & (1u << k)) a.pair_base[p] = preH;   // first survivor group of the pair
+                    a.gfirst[a.member_idx[j]] = (int32_t)preH + 1;
+                    preH++;
                 }
-                if (j == a.n - 1) {   // totals
-                    a.goff[preH] = (int64_t)preK;
-                    a.small->d2.n = (int64_t)preK;
+                a.c_grp[j] = (int32_t)preH - 1;
+                if (j == M - 1) {   // totals
+                    a.goff[preH] = M;
                     a.small->d2.nseg = (int64_t)preH;
                     a.counts_out[0] = (int64_t)preH;
-                    a.counts_out[1] = (int64_t)preK;
                 }
             }
         }
@@ -496,6 +552,8 @@ static AggPlan agg_plan(int64_t n, int32_t P) {
     t += al(sizeof(AggSmall));
     t += 3 * al((size_t)pl.tiles * 8);                 // scan status
     t += al((size_t)(P + 1) * 4);                      // pair_base
+    t += al((size_t)(P + 2) * 8);                      // coff
+    t += al((size_t)(n + 4) * 4);                      // val1
     t += al((size_t)(n / 32 + 2) * 4);                 // pair_heads
     t += 11 * al((size_t)(n + 4) * 4);                 // key1 key1s val1s tmpK tmpV c_grp keyA keyB keyN gfirst(slot alias no) gpair
     t += 2 * al((size_t)(n + 4) * 4);                  // gcid slot
@@ -521,6 +579,8 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
     a.gfirst = ar.take<int32_t>(n + 4);
     char *zero_end = ar.base + ar.off;               // everything up to here is zeroed by one memset
     a.pair_base = ar.take<u32>(P + 1);
+    a.coff = ar.take<int64_t>(P + 2);
+    a.val1 = ar.take<int32_t>(n + 4);
     a.key1 = ar.take<u32>(n + 4);
     a.key1s = ar.take<u32>(n + 4);
     a.val1s = ar.take<int32_t>(n + 4);
@@ -546,13 +606,13 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
     const unsigned per_elem = (unsigned)((n + 255) / 256);
     {
         ProfScope ps("agg_keys", st);
-        TDT_LAUNCH(agg_setup_kernel, (unsigned)((P + 256) / 256), 256, 0, st, a);
-        TDT_LAUNCH(agg_key_kernel, per_elem, 256, 0, st, a);
+        TDT_LAUNCH(agg_key_scan_kernel, tiles, AG_THREADS, 0, st, a);
+        TDT_LAUNCH(agg_heads_kernel, (unsigned)((P + 255) / 256), 256, 0, st, a);
     }
     {
         ProfScope ps("agg_sort_groups", st);
         const int key_bits = bit_width_u32(a.sentinel);
-        int rc = segsort_pairs(a.key1, nullptr, a.key1s, a.val1s, tmpK, tmpV, a.seg_off, (const int64_t *)&a.small->d1,
+        int rc = segsort_pairs(a.key1, a.val1, a.key1s, a.member_idx, tmpK, tmpV, a.coff, (const int64_t *)&a.small->d1,
                                nullptr, n, P, key_bits, sort_temp, pl.sort, &a.small->err, st);
         if (rc) return rc;
     }

@@ -1,5 +1,6 @@
 // tdt_api.cu -- error reporting, launch counter, version (libtdt_b200.so, sm_100a).
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "tdt_common.cuh"
 
@@ -21,11 +22,27 @@ struct ProfStage {
     cudaEvent_t a, b;
 };
 static bool g_prof_on = false;
+static bool g_prof_detail = false;   // TDT_PROF_DETAIL=1: one entry per kernel launch instead of per stage
 static int g_prof_n = 0;
-static ProfStage g_prof[256];
+constexpr int PROF_MAX = 2048;
+static ProfStage g_prof[PROF_MAX];
+
+void prof_kernel_begin(const char *name, cudaStream_t st) {
+    if (!g_prof_on || !g_prof_detail || g_prof_n >= PROF_MAX) return;
+    ProfStage &s = g_prof[g_prof_n];
+    s.name = name;
+    if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
+    cudaEventRecord(s.a, st);
+}
+
+void prof_kernel_end(cudaStream_t st) {
+    if (!g_prof_on || !g_prof_detail || g_prof_n >= PROF_MAX) return;
+    cudaEventRecord(g_prof[g_prof_n].b, st);
+    g_prof_n++;
+}
 
 void prof_stage_begin(const char *name, cudaStream_t st) {
-    if (!g_prof_on || g_prof_n >= 256) return;
+    if (!g_prof_on || g_prof_detail || g_prof_n >= PROF_MAX) return;
     ProfStage &s = g_prof[g_prof_n];
     s.name = name;
     if (cudaEventCreate(&s.a) != cudaSuccess || cudaEventCreate(&s.b) != cudaSuccess) return;
@@ -33,7 +50,7 @@ void prof_stage_begin(const char *name, cudaStream_t st) {
 }
 
 void prof_stage_end(cudaStream_t st) {
-    if (!g_prof_on || g_prof_n >= 256) return;
+    if (!g_prof_on || g_prof_detail || g_prof_n >= PROF_MAX) return;
     cudaEventRecord(g_prof[g_prof_n].b, st);
     g_prof_n++;
 }
@@ -43,6 +60,8 @@ void prof_stage_end(cudaStream_t st) {
 extern "C" {
 
 void tdt_profile_begin(void) {
+    const char *d = getenv("TDT_PROF_DETAIL");
+    tdt::g_prof_detail = d && d[0] == '1';
     tdt::g_prof_on = true;
     tdt::g_prof_n = 0;
 }

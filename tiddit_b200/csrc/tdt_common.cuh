@@ -28,13 +28,17 @@ int fail(int code, const char *fmt, ...);
 // every kernel launch goes through this so that tdt_launch_count() is honest
 #define TDT_LAUNCH(kernel, grid, block, smem, stream, ...)                                          \
     do {                                                                                            \
+        tdt::prof_kernel_begin(#kernel, (stream));                                                  \
         kernel<<<(grid), (block), (smem), (stream)>>>(__VA_ARGS__);                                 \
+        tdt::prof_kernel_end((stream));                                                             \
         tdt::g_launches.fetch_add(1, std::memory_order_relaxed);                                    \
         TDT_CUDA(cudaGetLastError());                                                               \
     } while (0)
 
 // optional per-stage timing (tdt_profile_begin / tdt_profile_end): CUDA events on the caller's stream around
 // each stage of a call; off by default, not thread-safe (one profiled caller at a time)
+void prof_kernel_begin(const char *name, cudaStream_t st);   // per-launch timing (TDT_PROF_DETAIL=1)
+void prof_kernel_end(cudaStream_t st);
 void prof_stage_begin(const char *name, cudaStream_t st);
 void prof_stage_end(cudaStream_t st);
 struct ProfScope {

@@ -482,25 +482,28 @@ __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
 // ---- large segments --------------------------------------------------------------------------------
 __global__ void __launch_bounds__(SS_THREADS) segsort_hist_kernel(SSArgs a) {
     __shared__ uint32_t h[SS_MAX_PASSES][256];
-    const int tile = blockIdx.x;
-    if (tile >= a.L.cnt->n_tiles) return;
-    for (int i = threadIdx.x; i < SS_MAX_PASSES * 256; i += SS_THREADS) (&h[0][0])[i] = 0u;
-    __syncthreads();
-    const int seg = a.L.tile_seg[tile];
-    const SSLarge L = a.L.large[seg];
-    const int64_t t0 = L.start + (int64_t)(tile - L.tile_base) * SS_TILE;
-    const int64_t rem = L.start + L.size - t0;
-    const int cnt = rem < SS_TILE ? (int)rem : SS_TILE;
-    for (int e = threadIdx.x; e < cnt; e += SS_THREADS) {
-        const uint32_t key = a.keys_in[t0 + e];
-        if (a.key_bits < 32 && (key >> a.key_bits)) atomicMax(a.err, SS_ERR_KEY_RANGE);
-        for (int p = 0; p < a.n_passes; p++) atomicAdd(&h[p][ss_digit(key, p, a.bits_per_pass)], 1u);
-    }
-    __syncthreads();
-    uint32_t *g = a.L.ghist + (size_t)seg * SS_MAX_PASSES * 256;
-    for (int i = threadIdx.x; i < a.n_passes * 256; i += SS_THREADS) {
-        const uint32_t v = (&h[0][0])[i];
-        if (v) atomicAdd(g + i, v);
+    const int n_tiles = a.L.cnt->n_tiles;
+    // the grid is capped at the resident-CTA count (ss_grid): a CTA walks tiles blockIdx.x, +gridDim.x, ...
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int i = threadIdx.x; i < SS_MAX_PASSES * 256; i += SS_THREADS) (&h[0][0])[i] = 0u;
+        __syncthreads();
+        const int seg = a.L.tile_seg[tile];
+        const SSLarge L = a.L.large[seg];
+        const int64_t t0 = L.start + (int64_t)(tile - L.tile_base) * SS_TILE;
+        const int64_t rem = L.start + L.size - t0;
+        const int cnt = rem < SS_TILE ? (int)rem : SS_TILE;
+        for (int e = threadIdx.x; e < cnt; e += SS_THREADS) {
+            const uint32_t key = a.keys_in[t0 + e];
+            if (a.key_bits < 32 && (key >> a.key_bits)) atomicMax(a.err, SS_ERR_KEY_RANGE);
+            for (int p = 0; p < a.n_passes; p++) atomicAdd(&h[p][ss_digit(key, p, a.bits_per_pass)], 1u);
+        }
+        __syncthreads();
+        uint32_t *g = a.L.ghist + (size_t)seg * SS_MAX_PASSES * 256;
+        for (int i = threadIdx.x; i < a.n_passes * 256; i += SS_THREADS) {
+            const uint32_t v = (&h[0][0])[i];
+            if (v) atomicAdd(g + i, v);
+        }
+        __syncthreads();
     }
 }
 
@@ -567,8 +570,12 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
     uint32_t *bin = (uint32_t *)p; p += 256 * 4;
     int64_t *gbase = (int64_t *)p;
 
-    const int tile = blockIdx.x;
-    if (tile >= a.L.cnt->n_tiles) return;
+    const int n_tiles = a.L.cnt->n_tiles;
+    // Persistent CTAs: the grid is capped at the number of CTAs the device keeps resident (ss_grid), CTA b takes tiles
+    // b, b + gridDim.x, ...  A tile only waits on tiles with a smaller index; those belong to CTAs that are resident
+    // too and are at the same or an earlier round, so the chained scan always makes progress -- and a sort with few
+    // (or no) large segments no longer pays for thousands of empty CTAs.
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
     for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) {
         (&wh[0][0])[i] = 0u;
         if (SS_MM) (&mm[0][0])[i] = 0u;
@@ -652,6 +659,8 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
         dst_k[g] = k;
         dst_v[g] = V2[i];
     }
+    __syncthreads();   // K2 / V2 / gbase are rewritten by the next tile
+    }
 }
 
 // ---- host launcher ---------------------------------------------------------------------------------
@@ -706,8 +715,19 @@ int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *key
     int64_t nwin = (n_max + SS_WINDOW - 1) / SS_WINDOW;
     if (nwin > 148 * 4) nwin = 148 * 4;
     TDT_LAUNCH(segsort_local_kernel, (unsigned)nwin, SS_LTHREADS, SS_LOCAL_SMEM, st, a);
-    const unsigned tiles = (unsigned)a.L.tiles_max;
-    TDT_LAUNCH(segsort_hist_kernel, tiles, SS_THREADS, 0, st, a);
+    static thread_local int pass_cap = 0, hist_cap = 0;   // resident CTAs of the two tile kernels on this device
+    if (!pass_cap) {
+        int dev = 0, sms = 0, per_sm = 0;
+        TDT_CUDA(cudaGetDevice(&dev));
+        TDT_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+        TDT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, segsort_pass_kernel, SS_THREADS, SS_PASS_SMEM));
+        pass_cap = sms * (per_sm > 0 ? per_sm : 1);
+        TDT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, segsort_hist_kernel, SS_THREADS, 0));
+        hist_cap = sms * (per_sm > 0 ? per_sm : 1);
+    }
+    const unsigned tiles = (unsigned)(a.L.tiles_max < pass_cap ? a.L.tiles_max : pass_cap);
+    const unsigned htiles = (unsigned)(a.L.tiles_max < hist_cap ? a.L.tiles_max : hist_cap);
+    TDT_LAUNCH(segsort_hist_kernel, htiles, SS_THREADS, 0, st, a);
     const int64_t scan_warps = a.L.nlarge_max * SS_MAX_PASSES;
     TDT_LAUNCH(segsort_scan_hist_kernel, (unsigned)((scan_warps * 32 + 255) / 256), 256, 0, st, a);
     // ping-pong so that the LAST pass lands in keys_out / vals_out
