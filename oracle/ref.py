@@ -1,7 +1,7 @@
 """Loader for the REAL reference modules compiled into oracle/_ref/ (see build_ref.py).
 
 TEST INFRASTRUCTURE ONLY.  `load()` returns a namespace with DBSCAN, tiddit_cluster,
-tiddit_coverage, tiddit_gc -- the unmodified upstream code -- or None when oracle/_ref/ has not
+tiddit_coverage, tiddit_gc, tiddit_coverage_analysis, tiddit_signal -- the unmodified upstream code -- or None when oracle/_ref/ has not
 been built (then callers fall back to the golden fixtures / the C restatement).
 """
 import importlib
@@ -33,5 +33,9 @@ def load():
     ns.tiddit_cluster = importlib.import_module("tiddit.tiddit_cluster")
     ns.tiddit_gc = importlib.import_module("tiddit.tiddit_gc")
     ns.tiddit_coverage_analysis = importlib.import_module("tiddit.tiddit_coverage_analysis")
+    try:    # compiled against the pysam stand-in (oracle/ref_shims/pysam); needs joblib at import time
+        ns.tiddit_signal = importlib.import_module("tiddit.tiddit_signal")
+    except ImportError:
+        ns.tiddit_signal = None
     _ns = ns
     return ns

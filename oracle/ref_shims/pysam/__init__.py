@@ -1,4 +1,5 @@
-"""Stand-in for the two `pysam.FastaFile` methods the reference's GC module calls.
+"""Stand-in `pysam` package for the compiled reference modules: `FastaFile` (two methods, GC module) here,
+`AlignmentFile` / `AlignedSegment` (signal worker) in libcalignmentfile.pyx.
 
 TEST INFRASTRUCTURE ONLY.  The real pysam (htslib bindings) is not installed in this
 image; `tiddit/tiddit_gc.pyx:1,7-8,15` only needs `FastaFile(path)`,
@@ -6,6 +7,7 @@ image; `tiddit/tiddit_gc.pyx:1,7-8,15` only needs `FastaFile(path)`,
 our own code (nothing from the reference); `oracle/build_ref.py` copies it next to the
 compiled reference modules so that `import pysam` inside `tiddit_gc` resolves here.
 """
+from .libcalignmentfile import AlignedSegment, AlignmentFile  # noqa: F401  (compiled by oracle/build_ref.py)
 
 
 class FastaFile:

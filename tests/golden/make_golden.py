@@ -332,6 +332,37 @@ def aggregate_cases():
     np.savez_compressed(os.path.join(HERE, "aggregate_cases.npz"), **out)
 
 
+def signal_cases():
+    """tiddit_signal.main (the REAL one, compiled against the pysam stand-in of oracle/ref_shims -- pysam itself is
+    not installed here) on synthetic BAMs from our writer that reach every branch of the worker loop: expected
+    discordants / splits tab files, clips fasta and the 50-bp coverage of every contig."""
+    import shutil
+    import tempfile
+    from tiddit_b200 import bamio, synth
+    signal = R.tiddit_signal
+    assert signal is not None, "tiddit_signal was not compiled"
+    cases = [dict(contigs=[("chr2", 400000), ("chr10", 300000), ("chr1", 250000), ("tiny", 4000), ("chrX", 120000)],
+                  n=2500, seed=13, min_q=10, max_ins=600, min_contig=5000, min_anchor_len=40, min_clip_len=20),
+             dict(contigs=[("b", 90000), ("a", 150000), ("c", 60000)],
+                  n=1500, seed=14, min_q=30, max_ins=450, min_contig=0, min_anchor_len=60, min_clip_len=4)]
+    tmp = tempfile.mkdtemp(prefix="tdt_sig_")
+    for k, c in enumerate(cases):
+        bam = os.path.join(HERE, "signal_case%d.bam" % k)
+        bamio.write_bam(bam, c["contigs"], synth.sv_bam_reads(c["contigs"], c["n"], seed=c["seed"], max_ins=c["max_ins"]))
+        prefix = os.path.join(tmp, "case%d" % k)
+        os.makedirs(prefix + "_tiddit/clips")
+        cov = signal.main(bam, "", prefix, c["min_q"], c["max_ins"], "S", 1, c["min_contig"], True,
+                          c["min_anchor_len"], c["min_clip_len"])
+        out = os.path.join(HERE, "signal_case%d_expected" % k)
+        os.makedirs(out, exist_ok=True)
+        for name in ("discordants_S.tab", "splits_S.tab", "clips_S.fa"):
+            shutil.copy(os.path.join(prefix + "_tiddit", name), os.path.join(out, name))
+        np.savez_compressed(os.path.join(out, "coverage.npz"), order=np.array(list(cov), dtype=str),
+                            **{"cov_" + n: v for n, v in cov.items()})
+        with open(os.path.join(out, "args.json"), "w") as f:
+            json.dump({kk: v for kk, v in c.items() if kk not in ("contigs", "n", "seed")}, f)
+
+
 def ploidy_cases():
     """tiddit_coverage_analysis.determine_ploidy (the REAL one) on synthetic coverage / GC bins: library values and
     the ploidies.tab text."""
@@ -371,11 +402,9 @@ def ploidy_cases():
 
 
 if __name__ == "__main__":
-    config1_cov()
-    dbscan_cases()
-    coverage_cases()
-    gc_cases()
-    cluster_cases()
-    aggregate_cases()
-    ploidy_cases()
+    steps = [config1_cov, dbscan_cases, coverage_cases, gc_cases, cluster_cases, aggregate_cases, signal_cases, ploidy_cases]
+    only = set(sys.argv[1:])          # e.g. `make_golden.py signal_cases` regenerates one family
+    for step in steps:
+        if not only or step.__name__ in only:
+            step()
     print("golden vectors written to", HERE)

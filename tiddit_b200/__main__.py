@@ -1,7 +1,7 @@
 """`python -m tiddit_b200 --cov ...`: the reference's coverage command (tiddit/__main__.py:210-247) on the GPU path.
 
-Same flags, same output files (byte-identical bed / wig).  Reads are decoded on the host (pysam when installed,
-the built-in BAM reader otherwise), buffered per contig and accumulated in batches by the coverage kernel.
+Same flags, same output files (byte-identical bed / wig).  Reads are decoded on the host by libtdt_bam.so (BGZF inflated on all cores, records as
+columns) and accumulated batch by batch by the coverage kernel.
 `--sv` needs the reference's own stages (signal extraction, assembly, variant calling, all built on pysam and bwa);
 when the `tiddit` package is importable it is run with this package's clustering / coverage / GC modules swapped in.
 """
@@ -24,28 +24,26 @@ def run_cov(argv):
         print("error,  could not find the bam file")
         return 1
     from . import bamio, tiddit_coverage
-    samfile = bamio.open_alignment_file(args.bam, reference_filename=args.ref)
-    bam_header = samfile.header
-    cov = tiddit_coverage.DeviceCoverage(bam_header, args.z)
-    names, starts, ends = [], [], []
-    current = None
-
-    def flush():
-        if starts:
-            cov.add_reads(current, starts, ends)
-            del starts[:], ends[:]
-
-    for read in samfile.fetch(until_eof=True):
-        if read.is_unmapped or read.is_duplicate:
-            continue
-        if read.mapq >= args.q:
-            name = read.reference_name
-            if name != current or len(starts) >= 1 << 20:
-                flush()
-                current = name
-            starts.append(read.reference_start)
-            ends.append(read.reference_end)
-    flush()
+    import numpy as np
+    # the reference's loop (__main__.py:229-242) on whole batches: libtdt_bam.so decodes the records into columns,
+    # the (start, end) columns of the reads that count go to the coverage kernel contig by contig
+    with bamio.ColumnReader(args.bam) as reader:
+        bam_header = reader.header
+        cov = tiddit_coverage.DeviceCoverage(bam_header, args.z)
+        for b in reader.batches():
+            keep = np.flatnonzero(((b.flag & (0x4 | 0x400)) == 0) & (b.mapq >= args.q))
+            if not len(keep):
+                continue
+            if np.any(b.ref_id[keep] < 0) or np.any(b.end[keep] < 0):
+                raise TypeError("a mapped read without reference or CIGAR")   # the reference fails on these too
+            rid = b.ref_id[keep]
+            if np.any(rid[1:] < rid[:-1]):
+                keep = keep[np.argsort(rid, kind="stable")]
+                rid = b.ref_id[keep]
+            cuts = np.flatnonzero(rid[1:] != rid[:-1]) + 1
+            for lo, hi in zip(np.concatenate([[0], cuts]), np.concatenate([cuts, [len(keep)]])):
+                sel = keep[lo:hi]
+                cov.add_reads(reader.references[rid[lo]], b.pos[sel], b.end[sel])
     coverage_data, _ = cov.to_host()
     if args.w:
         tiddit_coverage.print_coverage(coverage_data, bam_header, args.z, "wig", args.o + ".wig")

@@ -1,14 +1,24 @@
-"""Minimal BAM access for the coverage path.
+"""BAM access for the coverage / signal path.
 
-The reference reads alignments through pysam (`AlignmentFile(...).fetch(until_eof=True)`,
-`__main__.py:225-242`).  pysam / htslib are not part of this image, so `open_alignment_file` returns
-the real `pysam.AlignmentFile` when it is importable and otherwise this pure-Python reader, which offers
-the attributes the two coverage loops touch: header["SQ"], fetch(until_eof=True), and per read
-is_unmapped, is_duplicate, is_secondary, is_supplementary, mapq / mapping_quality, reference_start,
-reference_end, reference_name, query_name, flag.  `write_bam` produces small BGZF-compressed BAM files for
-tests and benchmarks.
+The reference reads alignments through pysam (`AlignmentFile(...).fetch(...)`, `__main__.py:225-242`,
+`tiddit_signal.pyx:156-221`).  pysam / htslib are not part of this image.  Two readers replace it:
+
+  * `ColumnReader` -- the product path: libtdt_bam.so (include/tdt_bam.h, csrc/tdt_bam.cpp) inflates BGZF
+    blocks on all host cores and decodes whole batches of records into numpy columns (reference id, start,
+    end, flag, mapq, mate, template length, first / last CIGAR word, "has SA"); the start / end columns go to
+    the GPU coverage kernel batch by batch and only signal-carrying reads are materialised (`record(k)`).
+  * `AlignmentFile` -- a small pure-Python sequential reader with pysam's attribute names, used by tests as an
+    independent cross-check of the scanner and by `open_alignment_file` when pysam is absent.
+
+`AlignedRead` offers the pysam attributes the two reference loops touch: is_unmapped, is_duplicate,
+is_secondary, is_supplementary, is_paired, is_reverse, mate_is_unmapped, mapq / mapping_quality,
+reference_start, reference_end, reference_name, next_reference_name, isize / template_length, cigartuples,
+query_name, query_sequence, query_alignment_start / _end, has_tag, get_tag.  `write_bam` produces small
+BGZF-compressed BAM files for tests and benchmarks.
 """
+import ctypes
 import gzip
+import os
 import struct
 import zlib
 
@@ -16,43 +26,162 @@ import numpy as np
 
 _CIGAR_REF = (1, 0, 1, 1, 0, 0, 0, 1, 1)   # M I D N S H P = X : consumes reference?
 _BGZF_EOF = bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000")
+_SEQ_CODE = "=ACMGRSVTWYHKDBN"
+_CORE = struct.Struct("<iiBBHHHiiii")
+_AUX_FIXED = {"A": 1, "c": 1, "C": 1, "s": 2, "S": 2, "i": 4, "I": 4, "f": 4}
+_AUX_FMT = {"c": "<b", "C": "<B", "s": "<h", "S": "<H", "i": "<i", "I": "<I", "f": "<f"}
 
 
 class AlignedRead:
-    __slots__ = ("query_name", "flag", "reference_id", "reference_start", "reference_end", "mapping_quality",
-                 "reference_name", "cigartuples", "next_reference_id", "next_reference_start", "template_length")
+    """One BAM record (the bytes after its block_size word), decoded on demand, pysam attribute names."""
+    __slots__ = ("_rec", "_refs", "reference_id", "reference_start", "mapping_quality", "flag", "next_reference_id",
+                 "next_reference_start", "template_length", "_l_name", "_n_cigar", "_l_seq", "_cigar", "_tags")
+
+    def __init__(self, rec, references):
+        self._rec, self._refs = rec, references
+        (self.reference_id, self.reference_start, self._l_name, self.mapping_quality, _bin, self._n_cigar, self.flag,
+         self._l_seq, self.next_reference_id, self.next_reference_start, self.template_length) = _CORE.unpack_from(rec, 0)
+        self._cigar = None
+        self._tags = None
+
+    # ---- names / flags ---------------------------------------------------------------------------------
+    @property
+    def query_name(self):
+        return bytes(self._rec[32:32 + self._l_name - 1]).decode("ascii")
 
     @property
     def mapq(self):
         return self.mapping_quality
 
     @property
-    def is_unmapped(self):
-        return bool(self.flag & 0x4)
+    def isize(self):
+        return self.template_length
 
     @property
-    def is_duplicate(self):
-        return bool(self.flag & 0x400)
+    def reference_name(self):
+        return self._refs[self.reference_id] if self.reference_id >= 0 else None
 
     @property
-    def is_secondary(self):
-        return bool(self.flag & 0x100)
+    def next_reference_name(self):
+        return self._refs[self.next_reference_id] if self.next_reference_id >= 0 else None
+
+    is_paired = property(lambda self: bool(self.flag & 0x1))
+    is_unmapped = property(lambda self: bool(self.flag & 0x4))
+    mate_is_unmapped = property(lambda self: bool(self.flag & 0x8))
+    is_reverse = property(lambda self: bool(self.flag & 0x10))
+    is_secondary = property(lambda self: bool(self.flag & 0x100))
+    is_duplicate = property(lambda self: bool(self.flag & 0x400))
+    is_supplementary = property(lambda self: bool(self.flag & 0x800))
+
+    # ---- alignment -------------------------------------------------------------------------------------
+    @property
+    def cigartuples(self):
+        """[(op, len)], or None for a record without CIGAR (pysam)."""
+        if self._cigar is None:
+            ops = struct.unpack_from("<%dI" % self._n_cigar, self._rec, 32 + self._l_name) if self._n_cigar else ()
+            self._cigar = [(o & 0xF, o >> 4) for o in ops]
+        return self._cigar or None
 
     @property
-    def is_supplementary(self):
-        return bool(self.flag & 0x800)
+    def reference_end(self):
+        cig = self.cigartuples
+        if self.flag & 0x4 or not cig:
+            return None
+        return self.reference_start + sum(n for op, n in cig if op < 9 and _CIGAR_REF[op])
 
     @property
-    def is_reverse(self):
-        return bool(self.flag & 0x10)
+    def query_alignment_start(self):
+        """Leading soft clip (hard clips skipped), like pysam's getQueryStart."""
+        start = 0
+        for op, n in self.cigartuples or ():
+            if op == 5:
+                continue
+            if op == 4:
+                start += n
+            else:
+                break
+        return start
 
     @property
-    def is_paired(self):
-        return bool(self.flag & 0x1)
+    def query_alignment_end(self):
+        """pysam's getQueryEnd: sequence length minus the trailing soft clip."""
+        end = self._l_seq
+        cig = self.cigartuples or ()
+        if end == 0:
+            for op, n in cig:
+                if op in (0, 1, 7, 8) or (op == 4 and end == 0):
+                    end += n
+            return end
+        for op, n in reversed(cig[1:]):
+            if op == 5:
+                continue
+            if op == 4:
+                end -= n
+            else:
+                break
+        return end
+
+    @property
+    def query_sequence(self):
+        if self._l_seq == 0:
+            return None
+        at = 32 + self._l_name + 4 * self._n_cigar
+        packed = np.frombuffer(self._rec, dtype=np.uint8, count=(self._l_seq + 1) // 2, offset=at)
+        codes = np.empty(2 * len(packed), dtype=np.uint8)
+        codes[0::2], codes[1::2] = packed >> 4, packed & 15
+        return "".join(_SEQ_CODE[c] for c in codes[:self._l_seq])
+
+    # ---- aux fields ------------------------------------------------------------------------------------
+    def _aux(self):
+        if self._tags is None:
+            rec, tags = self._rec, {}
+            p = 32 + self._l_name + 4 * self._n_cigar + (self._l_seq + 1) // 2 + self._l_seq
+            end = len(rec)
+            while p + 3 <= end:
+                tag, typ = bytes(rec[p:p + 2]).decode("ascii"), chr(rec[p + 2])
+                p += 3
+                if typ == "A":
+                    val = chr(rec[p])
+                    p += 1
+                elif typ in _AUX_FMT:
+                    val = struct.unpack_from(_AUX_FMT[typ], rec, p)[0]
+                    p += _AUX_FIXED[typ]
+                elif typ in "ZH":
+                    z = p
+                    while rec[z]:
+                        z += 1
+                    val = bytes(rec[p:z]).decode("ascii")
+                    p = z + 1
+                elif typ == "B":
+                    sub, cnt = chr(rec[p]), struct.unpack_from("<I", rec, p + 1)[0]
+                    val = list(struct.unpack_from("<%d%s" % (cnt, _AUX_FMT[sub][1]), rec, p + 5))
+                    p += 5 + cnt * _AUX_FIXED[sub]
+                else:
+                    raise ValueError("unknown aux type %r" % typ)
+                tags.setdefault(tag, val)
+            self._tags = tags
+        return self._tags
+
+    def has_tag(self, tag):
+        return tag in self._aux()
+
+    def get_tag(self, tag):
+        try:
+            return self._aux()[tag]
+        except KeyError:
+            raise KeyError("tag '%s' not present" % tag)
+
+
+def _parse_header_text(text, references, lengths):
+    header = {"HD": {}, "SQ": [{"SN": n, "LN": l} for n, l in zip(references, lengths)], "RG": []}
+    for line in text.splitlines():
+        if line.startswith("@RG"):
+            header["RG"].append(dict(f.split(":", 1) for f in line.split("\t")[1:] if ":" in f))
+    return header
 
 
 class AlignmentFile:
-    """Sequential BAM reader (no index, no CRAM)."""
+    """Sequential pure-Python BAM reader (no index, no CRAM)."""
 
     def __init__(self, path, mode="r", reference_filename=None, **_):
         self._fh = gzip.open(path, "rb")      # BGZF is a series of gzip members
@@ -68,35 +197,20 @@ class AlignmentFile:
             self.references.append(self._fh.read(l_name)[:-1].decode("ascii"))
             self.lengths.append(struct.unpack("<i", self._fh.read(4))[0])
         self.text = text
-        self.header = {"HD": {}, "SQ": [{"SN": n, "LN": l} for n, l in zip(self.references, self.lengths)], "RG": []}
-        for line in text.splitlines():
-            if line.startswith("@RG"):
-                self.header["RG"].append(dict(f.split(":", 1) for f in line.split("\t")[1:] if ":" in f))
+        self.header = _parse_header_text(text, self.references, self.lengths)
 
     def fetch(self, contig=None, until_eof=False, **_):
-        if contig is not None:
-            raise NotImplementedError("the pure-Python BAM reader is sequential: use fetch(until_eof=True)")
+        """All records in file order; with `contig`, the records placed on it (a linear scan: there is no index)."""
+        want = None if contig is None else self.references.index(contig)
         read_block = self._fh.read
-        unpack = struct.Struct("<iiBBHHHiiii").unpack_from
         while True:
             raw = read_block(4)
             if len(raw) < 4:
                 return
             size, = struct.unpack("<i", raw)
-            rec = read_block(size)
-            ref_id, pos, l_name, mapq, _bin, n_cigar, flag, l_seq, next_ref, next_pos, tlen = unpack(rec, 0)
-            r = AlignedRead()
-            r.query_name = rec[32:32 + l_name - 1].decode("ascii")
-            r.flag, r.reference_id, r.reference_start, r.mapping_quality = flag, ref_id, pos, mapq
-            r.next_reference_id, r.next_reference_start, r.template_length = next_ref, next_pos, tlen
-            r.reference_name = self.references[ref_id] if ref_id >= 0 else None
-            ops = struct.unpack_from("<%dI" % n_cigar, rec, 32 + l_name) if n_cigar else ()
-            r.cigartuples = [(o & 0xF, o >> 4) for o in ops]
-            if flag & 0x4 or not ops:
-                r.reference_end = None
-            else:
-                r.reference_end = pos + sum(n for op, n in r.cigartuples if op < 9 and _CIGAR_REF[op])
-            yield r
+            r = AlignedRead(read_block(size), self.references)
+            if want is None or r.reference_id == want:
+                yield r
 
     def close(self):
         self._fh.close()
@@ -117,6 +231,112 @@ def open_alignment_file(path, reference_filename=None):
         return AlignmentFile(path, "r", reference_filename=reference_filename)
 
 
+# ---------------------------------------------------------------------------------------------------------
+# the native scanner
+# ---------------------------------------------------------------------------------------------------------
+_BAM_LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libtdt_bam.so")
+_vp, _i32, _i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+BAM_SIGNATURES = {
+    "tdt_bam_last_error": (ctypes.c_char_p, []),
+    "tdt_bam_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_int, ctypes.POINTER(_vp)]),
+    "tdt_bam_close": (None, [_vp]),
+    "tdt_bam_header_text": (_vp, [_vp, ctypes.POINTER(_i64)]),
+    "tdt_bam_n_ref": (_i32, [_vp]),
+    "tdt_bam_ref_name": (ctypes.c_char_p, [_vp, _i32]),
+    "tdt_bam_ref_len": (_i32, [_vp, _i32]),
+    "tdt_bam_read_columns": (_i64, [_vp, _i64] + [_vp] * 12),
+    "tdt_bam_batch_data": (_vp, [_vp, ctypes.POINTER(_i64)]),
+}
+_bam_lib = None
+
+
+def bam_lib():
+    global _bam_lib
+    if _bam_lib is None:
+        if not os.path.exists(_BAM_LIB_PATH):
+            raise RuntimeError("%s is missing: build it with `python -m tiddit_b200.build`" % _BAM_LIB_PATH)
+        L = ctypes.CDLL(_BAM_LIB_PATH)
+        for name, (res, args) in BAM_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _bam_lib = L
+    return _bam_lib
+
+
+class ColumnBatch:
+    """Columns of one batch of records (numpy views, valid until the reader's next batch)."""
+    COLUMNS = (("ref_id", np.int32), ("pos", np.int32), ("end", np.int32), ("mate_ref", np.int32),
+               ("mate_pos", np.int32), ("tlen", np.int32), ("flag", np.uint16), ("mapq", np.uint8),
+               ("cig_first", np.uint32), ("cig_last", np.uint32), ("has_sa", np.uint8), ("rec_off", np.int64))
+
+    def __init__(self, n, cols, data, references):
+        self.n = n
+        for (name, _), col in zip(self.COLUMNS, cols):
+            setattr(self, name, col[:n])
+        self._data, self._refs = data, references
+
+    def __len__(self):
+        return self.n
+
+    def record(self, k):
+        """The k-th record of the batch as an AlignedRead (copies its bytes: it outlives the batch)."""
+        off = int(self.rec_off[k])
+        size = int(self._data[off:off + 4].view(np.int32)[0])
+        return AlignedRead(self._data[off + 4:off + 4 + size].tobytes(), self._refs)
+
+
+class ColumnReader:
+    """`pysam.AlignmentFile(path).fetch(until_eof=True)` as batches of columns (libtdt_bam.so)."""
+
+    def __init__(self, path, threads=0, batch_reads=1 << 20):
+        L = bam_lib()
+        h = _vp()
+        rc = L.tdt_bam_open(os.fsencode(path), int(threads), ctypes.byref(h))
+        if rc != 0:
+            msg = L.tdt_bam_last_error().decode("utf-8", "replace")
+            raise (FileNotFoundError if rc == -2 else ValueError)(msg)
+        self._h, self._L = h, L
+        n = _i64()
+        p = L.tdt_bam_header_text(h, ctypes.byref(n))
+        self.text = ctypes.string_at(p, n.value).decode("ascii", "replace")
+        self.references = [L.tdt_bam_ref_name(h, i).decode("ascii") for i in range(L.tdt_bam_n_ref(h))]
+        self.lengths = [L.tdt_bam_ref_len(h, i) for i in range(len(self.references))]
+        self.header = _parse_header_text(self.text, self.references, self.lengths)
+        self.batch_reads = int(batch_reads)
+        self._cols = [np.empty(self.batch_reads, dtype=dt) for _, dt in ColumnBatch.COLUMNS]
+
+    def batches(self):
+        L, h = self._L, self._h
+        ptrs = [c.ctypes.data_as(_vp) for c in self._cols]
+        while True:
+            n = L.tdt_bam_read_columns(h, self.batch_reads, *ptrs)
+            if n < 0:
+                raise ValueError(L.tdt_bam_last_error().decode("utf-8", "replace"))
+            if n == 0:
+                return
+            size = _i64()
+            base = L.tdt_bam_batch_data(h, ctypes.byref(size))
+            data = np.ctypeslib.as_array(ctypes.cast(base, ctypes.POINTER(ctypes.c_uint8)), shape=(size.value,))
+            yield ColumnBatch(int(n), self._cols, data, self.references)
+
+    def close(self):
+        if self._h:
+            self._L.tdt_bam_close(self._h)
+            self._h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 def _bgzf_block(data):
     comp = zlib.compressobj(6, zlib.DEFLATED, -15)
     body = comp.compress(data) + comp.flush()
@@ -127,7 +347,8 @@ def _bgzf_block(data):
 
 def write_bam(path, contigs, reads, header_text=None):
     """contigs: [(name, length)]; reads: iterable of dicts with keys name, flag, ref (index or -1), pos (0-based),
-    mapq, cigar [(op, len)] (op as in BAM: 0=M 1=I 2=D 3=N 4=S ...), optional seq_len."""
+    mapq, cigar [(op, len)] (op as in BAM: 0=M 1=I 2=D 3=N 4=S ...); optional seq_len or seq (ACGTN string),
+    next_ref / next_pos / tlen (mate), tags {"SA": "chr,pos,strand,CIGAR,mapq,NM;", "NM": 3} (str -> Z, int -> i)."""
     if header_text is None:
         header_text = "@HD\tVN:1.6\tSO:coordinate\n" + "".join("@SQ\tSN:%s\tLN:%d\n" % c for c in contigs)
     out = bytearray(b"BAM\x01")
@@ -139,7 +360,8 @@ def write_bam(path, contigs, reads, header_text=None):
     for rd in reads:
         nm = rd["name"].encode("ascii") + b"\0"
         cigar = rd.get("cigar") or []
-        l_seq = rd.get("seq_len", sum(n for op, n in cigar if op in (0, 1, 4, 7, 8)))
+        seq = rd.get("seq")
+        l_seq = len(seq) if seq is not None else rd.get("seq_len", sum(n for op, n in cigar if op in (0, 1, 4, 7, 8)))
         ref_len = sum(n for op, n in cigar if _CIGAR_REF[op])
         end = rd["pos"] + (ref_len or 1)
         # UCSC binning scheme (SAM spec 5.3)
@@ -151,9 +373,19 @@ def write_bam(path, contigs, reads, header_text=None):
         elif b >> 26 == e >> 26: bin_ = ((1 << 3) - 1) // 7 + (b >> 26)
         else: bin_ = 0
         body = struct.pack("<iiBBHHHiiii", rd["ref"], rd["pos"], len(nm), rd["mapq"], bin_, len(cigar), rd["flag"],
-                           l_seq, -1, -1, 0)
+                           l_seq, rd.get("next_ref", -1), rd.get("next_pos", -1), rd.get("tlen", 0))
         body += nm + b"".join(struct.pack("<I", (n << 4) | op) for op, n in cigar)
-        body += b"\xff" * ((l_seq + 1) // 2) + b"\xff" * l_seq
+        if seq is None:
+            body += b"\xff" * ((l_seq + 1) // 2)
+        else:
+            codes = [_SEQ_CODE.index(ch) for ch in seq.upper()] + [0]
+            body += bytes((codes[i] << 4) | codes[i + 1] for i in range(0, l_seq, 2))
+        body += b"\xff" * l_seq
+        for tag, val in (rd.get("tags") or {}).items():
+            if isinstance(val, str):
+                body += tag.encode("ascii") + b"Z" + val.encode("ascii") + b"\0"
+            else:
+                body += tag.encode("ascii") + b"i" + struct.pack("<i", int(val))
         out += struct.pack("<i", len(body)) + body
     with open(path, "wb") as f:
         for i in range(0, len(out), 0xff00):

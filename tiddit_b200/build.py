@@ -1,4 +1,5 @@
-"""Build libtdt_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a.
+"""Build libtdt_b200.so (the C-ABI CUDA library) in-tree with nvcc for sm_100a, and libtdt_bam.so (the host-side
+BAM scanner, include/tdt_bam.h) with g++ + zlib.
 
 `python -m tiddit_b200.build` or `tiddit_b200.build.build()`.  nvcc cross-compiles without a GPU.
 The built library is git-ignored but travels to the GPU box with the repository snapshot.
@@ -10,6 +11,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtdt_b200.so")
+BAM_LIB = os.path.join(HERE, "libtdt_bam.so")
 SOURCES = ["tdt_api.cu", "tdt_cluster.cu", "tdt_aggregate.cu", "tdt_coverage.cu", "tdt_ploidy.cu", "tdt_gc.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -26,11 +28,23 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "tdt_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "tdt_bam.cpp"] + [os.path.join(HERE, "..", "include", "tdt_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
+def build_bam(force=False):
+    """g++ -O3 -shared: the BGZF/BAM column scanner (host code only, links zlib)."""
+    src = os.path.join(CSRC, "tdt_bam.cpp")
+    hdr = os.path.join(HERE, "..", "include", "tdt_bam.h")
+    if not force and os.path.exists(BAM_LIB) and os.path.getmtime(BAM_LIB) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return BAM_LIB
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+                           "-Wall", "-o", BAM_LIB, src, "-lz", "-lpthread"])
+    return BAM_LIB
+
+
 def build(force=False, verbose=False):
+    build_bam(force)
     if not force and not _stale():
         return LIB
     objs = []

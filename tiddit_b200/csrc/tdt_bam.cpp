@@ -1,0 +1,342 @@
+// libtdt_bam.so -- BGZF/BAM scanner producing columns for the GPU coverage / signal path (include/tdt_bam.h).
+// Host code only (g++ + zlib).  The file is mapped, BGZF block boundaries are found by hopping over the BSIZE
+// fields, a window of blocks is inflated on a pool of threads straight into one contiguous buffer (every block
+// states its inflated size in its trailer, so the destinations are known up front), and records are decoded
+// from that buffer without copying.
+#include "../../include/tdt_bam.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+inline uint32_t le32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
+inline uint16_t le16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
+
+// does this CIGAR operation consume the reference?  M I D N S H P = X
+const uint8_t kConsumesRef[16] = {1, 0, 1, 1, 0, 0, 0, 1, 1, 0, 0, 0, 0, 0, 0, 0};
+
+struct Block {
+    const uint8_t *payload;  // raw deflate stream
+    uint32_t clen;           // its length
+    uint32_t isize;          // inflated size
+    uint32_t crc;
+    size_t dst;              // offset in the window buffer
+};
+
+}  // namespace
+
+struct tdt_bam_reader {
+    int fd = -1;
+    const uint8_t *map = nullptr;
+    size_t map_len = 0;
+    size_t cpos = 0;  // next compressed block
+    int threads = 1;
+    std::vector<uint8_t> buf;  // inflated window
+    size_t bpos = 0, bend = 0;
+    size_t window_blocks = 1024;  // blocks inflated per refill (<= 64 MiB inflated)
+    bool eof = false;
+    std::string text;
+    std::vector<std::string> ref_names;
+    std::vector<int32_t> ref_lens;
+    std::string path;
+};
+
+namespace {
+
+// Appends up to r->window_blocks inflated blocks after compacting the unread tail to the front.
+// Returns 1 if bytes were added, 0 at end of file, < 0 on error.
+int refill(tdt_bam_reader *r) {
+    if (r->bpos > 0) {
+        size_t left = r->bend - r->bpos;
+        if (left) memmove(r->buf.data(), r->buf.data() + r->bpos, left);
+        r->bpos = 0;
+        r->bend = left;
+    }
+    std::vector<Block> blocks;
+    size_t out = r->bend;
+    while (blocks.size() < r->window_blocks && r->cpos < r->map_len) {
+        const uint8_t *h = r->map + r->cpos;
+        size_t left = r->map_len - r->cpos;
+        if (left < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4))
+            return fail(TDT_BAM_E_FORMAT, "%s: not a BGZF block at offset %zu", r->path.c_str(), r->cpos);
+        uint32_t xlen = le16(h + 10);
+        if (left < 12 + (size_t)xlen) return fail(TDT_BAM_E_FORMAT, "%s: truncated BGZF header", r->path.c_str());
+        int64_t bsize = -1;
+        for (uint32_t x = 0; x + 4 <= xlen;) {
+            const uint8_t *sf = h + 12 + x;
+            uint32_t slen = le16(sf + 2);
+            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (int64_t)le16(sf + 4) + 1;
+            x += 4 + slen;
+        }
+        if (bsize < 0 || (size_t)bsize > left || (size_t)bsize < 12 + (size_t)xlen + 8)
+            return fail(TDT_BAM_E_FORMAT, "%s: bad BGZF block size at offset %zu", r->path.c_str(), r->cpos);
+        Block b;
+        b.payload = h + 12 + xlen;
+        b.clen = (uint32_t)(bsize - 12 - xlen - 8);
+        b.crc = le32(h + bsize - 8);
+        b.isize = le32(h + bsize - 4);
+        if (b.isize > 65536) return fail(TDT_BAM_E_FORMAT, "%s: BGZF block inflates to %u bytes", r->path.c_str(), b.isize);
+        b.dst = out;
+        out += b.isize;
+        r->cpos += (size_t)bsize;
+        if (b.isize) blocks.push_back(b);  // the EOF marker and other empty blocks carry nothing
+    }
+    if (blocks.empty()) {
+        r->eof = true;
+        return 0;
+    }
+    if (r->buf.size() < out) r->buf.resize(out + (out >> 2));
+    std::atomic<size_t> next(0);
+    std::atomic<int> bad(0);
+    uint8_t *base = r->buf.data();
+    auto work = [&]() {
+        z_stream zs;
+        memset(&zs, 0, sizeof zs);
+        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
+        for (;;) {
+            size_t i = next.fetch_add(1);
+            if (i >= blocks.size()) break;
+            const Block &b = blocks[i];
+            zs.next_in = const_cast<Bytef *>(b.payload);
+            zs.avail_in = b.clen;
+            zs.next_out = base + b.dst;
+            zs.avail_out = b.isize;
+            int rc = inflate(&zs, Z_FINISH);
+            if (rc != Z_STREAM_END || zs.avail_out != 0 ||
+                (uint32_t)crc32(crc32(0L, Z_NULL, 0), base + b.dst, b.isize) != b.crc)
+                bad = 1;
+            inflateReset(&zs);
+        }
+        inflateEnd(&zs);
+    };
+    int nt = (int)std::min<size_t>((size_t)r->threads, blocks.size());
+    if (nt <= 1) {
+        work();
+    } else {
+        std::vector<std::thread> pool;
+        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
+        work();
+        for (auto &t : pool) t.join();
+    }
+    if (bad) return fail(TDT_BAM_E_FORMAT, "%s: a BGZF block failed to inflate (corrupt data or CRC mismatch)", r->path.c_str());
+    r->bend = out;
+    return 1;
+}
+
+// at least n unread bytes in the window (used for the header only: it compacts the buffer)
+int ensure(tdt_bam_reader *r, size_t n) {
+    while (r->bend - r->bpos < n) {
+        int rc = refill(r);
+        if (rc < 0) return rc;
+        if (rc == 0) return fail(TDT_BAM_E_FORMAT, "%s: truncated BAM header", r->path.c_str());
+    }
+    return 1;
+}
+
+int read_header(tdt_bam_reader *r) {
+    int rc;
+    if ((rc = ensure(r, 12)) < 0) return rc;
+    const uint8_t *p = r->buf.data() + r->bpos;
+    if (memcmp(p, "BAM\1", 4) != 0) return fail(TDT_BAM_E_FORMAT, "%s is not a BAM file", r->path.c_str());
+    uint32_t l_text = le32(p + 4);
+    if ((rc = ensure(r, 12 + (size_t)l_text)) < 0) return rc;
+    p = r->buf.data() + r->bpos;
+    r->text.assign((const char *)p + 8, l_text);
+    size_t z = r->text.find('\0');
+    if (z != std::string::npos) r->text.resize(z);
+    uint32_t n_ref = le32(p + 8 + l_text);
+    r->bpos += 12 + (size_t)l_text;
+    for (uint32_t i = 0; i < n_ref; ++i) {
+        if ((rc = ensure(r, 4)) < 0) return rc;
+        uint32_t l_name = le32(r->buf.data() + r->bpos);
+        if ((rc = ensure(r, 8 + (size_t)l_name)) < 0) return rc;
+        p = r->buf.data() + r->bpos;
+        r->ref_names.emplace_back((const char *)p + 4, l_name ? strnlen((const char *)p + 4, l_name) : 0);
+        r->ref_lens.push_back((int32_t)le32(p + 4 + l_name));
+        r->bpos += 8 + (size_t)l_name;
+    }
+    return 0;
+}
+
+// "SA" among the aux fields [p, e)?  Walks the typed fields (SAM spec 4.2.4).
+bool aux_has_sa(const uint8_t *p, const uint8_t *e) {
+    while (p + 3 <= e) {
+        bool sa = p[0] == 'S' && p[1] == 'A';
+        uint8_t t = p[2];
+        p += 3;
+        if (sa) return true;
+        switch (t) {
+            case 'A': case 'c': case 'C': p += 1; break;
+            case 's': case 'S': p += 2; break;
+            case 'i': case 'I': case 'f': p += 4; break;
+            case 'Z': case 'H':
+                while (p < e && *p) ++p;
+                ++p;
+                break;
+            case 'B': {
+                if (p + 5 > e) return false;
+                uint8_t st = p[0];
+                uint32_t cnt = le32(p + 1);
+                size_t w = (st == 'c' || st == 'C') ? 1 : (st == 's' || st == 'S') ? 2 : 4;
+                p += 5 + (size_t)cnt * w;
+                break;
+            }
+            default: return false;  // unknown type: cannot walk further
+        }
+    }
+    return false;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *tdt_bam_last_error(void) { return g_err; }
+
+int tdt_bam_open(const char *path, int threads, tdt_bam_reader **out) {
+    if (!path || !out) return fail(TDT_BAM_E_ARG, "tdt_bam_open: null argument");
+    *out = nullptr;
+    int fd = open(path, O_RDONLY);
+    if (fd < 0) return fail(TDT_BAM_E_IO, "cannot open %s", path);
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size <= 0) {
+        close(fd);
+        return fail(TDT_BAM_E_IO, "%s is empty or cannot be examined", path);
+    }
+    void *m = mmap(nullptr, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    if (m == MAP_FAILED) {
+        close(fd);
+        return fail(TDT_BAM_E_IO, "cannot map %s", path);
+    }
+    madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+    tdt_bam_reader *r = new tdt_bam_reader;
+    r->fd = fd;
+    r->map = (const uint8_t *)m;
+    r->map_len = (size_t)st.st_size;
+    r->path = path;
+    if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
+    r->threads = std::max(1, threads);
+    int rc = read_header(r);
+    if (rc < 0) {
+        tdt_bam_close(r);
+        return rc;
+    }
+    *out = r;
+    return TDT_BAM_OK;
+}
+
+void tdt_bam_close(tdt_bam_reader *r) {
+    if (!r) return;
+    if (r->map) munmap(const_cast<uint8_t *>(r->map), r->map_len);
+    if (r->fd >= 0) close(r->fd);
+    delete r;
+}
+
+const char *tdt_bam_header_text(const tdt_bam_reader *r, int64_t *len) {
+    if (len) *len = (int64_t)r->text.size();
+    return r->text.c_str();
+}
+int32_t tdt_bam_n_ref(const tdt_bam_reader *r) { return (int32_t)r->ref_names.size(); }
+const char *tdt_bam_ref_name(const tdt_bam_reader *r, int32_t i) {
+    return (i >= 0 && (size_t)i < r->ref_names.size()) ? r->ref_names[i].c_str() : nullptr;
+}
+int32_t tdt_bam_ref_len(const tdt_bam_reader *r, int32_t i) {
+    return (i >= 0 && (size_t)i < r->ref_lens.size()) ? r->ref_lens[i] : -1;
+}
+
+int64_t tdt_bam_read_columns(tdt_bam_reader *r, int64_t max_reads, int32_t *ref_id, int32_t *pos, int32_t *end,
+                             int32_t *mate_ref, int32_t *mate_pos, int32_t *tlen, uint16_t *flag, uint8_t *mapq,
+                             uint32_t *cig_first, uint32_t *cig_last, uint8_t *has_sa, int64_t *rec_off) {
+    if (!r || max_reads < 0) return fail(TDT_BAM_E_ARG, "tdt_bam_read_columns: bad argument");
+    int64_t n = 0;
+    while (n == 0 && max_reads > 0) {
+        // a complete record at the read position?  otherwise bring in the next window (this is the only place
+        // the buffer moves, so the offsets handed out below stay valid until the next call)
+        size_t have = r->bend - r->bpos;
+        bool complete = have >= 4 && have >= 4 + (size_t)le32(r->buf.data() + r->bpos);
+        if (!complete) {
+            int rc = refill(r);
+            if (rc < 0) return rc;
+            if (rc == 0) {
+                if (r->bend - r->bpos != 0)
+                    return fail(TDT_BAM_E_FORMAT, "%s: truncated record at end of file", r->path.c_str());
+                return 0;
+            }
+        }
+        const uint8_t *base = r->buf.data();
+        while (n < max_reads) {
+            size_t avail = r->bend - r->bpos;
+            if (avail < 4) break;
+            const uint8_t *rec = base + r->bpos;
+            uint32_t bs = le32(rec);
+            if (bs < 32) return fail(TDT_BAM_E_FORMAT, "%s: record of %u bytes", r->path.c_str(), bs);
+            if (avail < 4 + (size_t)bs) break;
+            const uint8_t *c = rec + 4;
+            int32_t rid = (int32_t)le32(c), p0 = (int32_t)le32(c + 4);
+            uint32_t l_name = c[8];
+            uint32_t n_cig = le16(c + 12);
+            uint16_t fl = le16(c + 14);
+            uint32_t l_seq = le32(c + 16);
+            size_t fixed = 32 + (size_t)l_name + 4 * (size_t)n_cig;
+            size_t aux_at = fixed + ((size_t)l_seq + 1) / 2 + l_seq;
+            if (aux_at > bs) return fail(TDT_BAM_E_FORMAT, "%s: record fields exceed its size", r->path.c_str());
+            const uint8_t *cg = c + 32 + l_name;
+            if (ref_id) ref_id[n] = rid;
+            if (pos) pos[n] = p0;
+            if (end) {
+                if ((fl & 4) || n_cig == 0) {
+                    end[n] = -1;
+                } else {
+                    int64_t e = p0;
+                    for (uint32_t k = 0; k < n_cig; ++k) {
+                        uint32_t w = le32(cg + 4 * k);
+                        if (kConsumesRef[w & 15]) e += w >> 4;
+                    }
+                    end[n] = (int32_t)e;
+                }
+            }
+            if (mate_ref) mate_ref[n] = (int32_t)le32(c + 20);
+            if (mate_pos) mate_pos[n] = (int32_t)le32(c + 24);
+            if (tlen) tlen[n] = (int32_t)le32(c + 28);
+            if (flag) flag[n] = fl;
+            if (mapq) mapq[n] = c[9];
+            if (cig_first) cig_first[n] = n_cig ? le32(cg) : 0;
+            if (cig_last) cig_last[n] = n_cig ? le32(cg + 4 * (n_cig - 1)) : 0;
+            if (has_sa) has_sa[n] = aux_has_sa(c + aux_at, c + bs) ? 1 : 0;
+            if (rec_off) rec_off[n] = (int64_t)r->bpos;
+            r->bpos += 4 + (size_t)bs;
+            ++n;
+        }
+    }
+    return n;
+}
+
+const uint8_t *tdt_bam_batch_data(const tdt_bam_reader *r, int64_t *len) {
+    if (len) *len = (int64_t)r->bend;
+    return r->buf.data();
+}
+
+}  // extern "C"

@@ -180,3 +180,110 @@ def signal_records(posA, posB, seg_off, seed=11, split_frac=0.18, contig_frac=0.
     span = np.stack([posA - la, posA.astype(np.int64), posB.astype(np.int64), posB + lb], axis=1)
     return {"span": np.ascontiguousarray(span, dtype=np.int32), "name_id": name_id.astype(np.int32), "flags": flags,
             "same_chrom": same, "n_names": n}
+
+
+def sv_bam_reads(contigs, n_fragments=4000, seed=13, read_len=100, max_ins=600):
+    """Reads for bamio.write_bam that exercise every branch of the signal worker (tiddit_signal.pyx:169-221):
+    proper pairs, discordant pairs (far apart on one contig, across contigs, every orientation, mates that are
+    unmapped / filtered / low quality), split reads with SA tags (one or several entries, either strand, soft and
+    hard clips, SA on a smaller- or larger-named contig, quality below the threshold), soft-clipped reads,
+    duplicates, secondary and supplementary records.  Coordinate-sorted per contig like a real BAM."""
+    rng = np.random.default_rng(seed)
+    nc = len(contigs)
+    out = [[] for _ in contigs]
+    bases = np.array(list("ACGT"))
+
+    def seq(n):
+        return "".join(bases[rng.integers(0, 4, n)])
+
+    def place(ci, n):
+        return int(rng.integers(0, max(1, contigs[ci][1] - n - 1)))
+
+    def emit(ci, pos, name, flag, mapq, cigar, mate=(-1, -1), tlen=0, tags=None, with_seq=False):
+        rd = {"name": name, "flag": int(flag), "ref": ci, "pos": int(pos), "mapq": int(mapq), "cigar": cigar,
+              "next_ref": int(mate[0]), "next_pos": int(mate[1]), "tlen": int(tlen)}
+        if tags:
+            rd["tags"] = tags
+        if with_seq:
+            rd["seq"] = seq(sum(n for op, n in cigar if op in (0, 1, 4, 7, 8)))
+        out[ci].append(rd)
+
+    def mapq():
+        return 0 if rng.random() < 0.08 else int(rng.integers(5, 61))
+
+    for f in range(n_fragments):
+        name = "frag%d" % f
+        kind = rng.random()
+        ca = int(rng.integers(0, nc))
+        pa = place(ca, 2 * read_len + max_ins)
+        ra, rb = (int(rng.random() < 0.5) * 0x10), (int(rng.random() < 0.5) * 0x20)
+        extra = 0x400 if rng.random() < 0.03 else 0
+        if kind < 0.45:                                   # proper pair
+            ins = int(rng.integers(read_len, max_ins - 1))
+            emit(ca, pa, name, 0x1 | 0x2 | 0x40 | 0x20 | extra, mapq(), [(0, read_len)], (ca, pa + ins - read_len), ins)
+            emit(ca, pa + ins - read_len, name, 0x1 | 0x2 | 0x80 | 0x10 | extra, mapq(), [(0, read_len)], (ca, pa), -ins)
+        elif kind < 0.70:                                 # discordant pair
+            if rng.random() < 0.5:
+                cb, pb = ca, pa + int(rng.integers(max_ins, 30 * max_ins))
+                pb = min(pb, contigs[cb][1] - read_len - 1)
+            else:
+                cb = int(rng.integers(0, nc))
+                pb = place(cb, read_len)
+            tl = (pb + read_len - pa) if cb == ca else 0
+            fa = 0x1 | 0x40 | ra | (0x20 if rb else 0) | extra
+            fb = 0x1 | 0x80 | (0x10 if rb else 0) | (0x20 if ra else 0) | extra
+            u = rng.random()
+            if u < 0.08:
+                fa |= 0x8                                  # mate unmapped: never paired up
+                emit(ca, pa, name, fa, mapq(), [(0, read_len)], (ca, pa), 0)
+                out[ca].append({"name": name, "flag": 0x1 | 0x4 | 0x80, "ref": ca, "pos": pa, "mapq": 0, "cigar": [],
+                                "seq_len": read_len, "next_ref": ca, "next_pos": pa, "tlen": 0})
+                continue
+            emit(ca, pa, name, fa, mapq(), [(0, read_len)], (cb, pb), tl)
+            if u < 0.16:
+                continue                                   # the mate is missing from the file
+            emit(cb, pb, name, fb, mapq(), [(0, read_len - 10), (4, 10)] if u < 0.3 else [(0, read_len)], (ca, pa), -tl)
+            if u > 0.92:                                   # a third record under the same name (supplementary-free duplicate name)
+                emit(cb, min(pb + 50, contigs[cb][1] - read_len - 1), name, fb & ~0x400, mapq(), [(0, read_len)], (ca, pa), -tl)
+        elif kind < 0.88:                                 # split read: primary with SA (+ its supplementary record)
+            cb = ca if rng.random() < 0.5 else int(rng.integers(0, nc))
+            pb = place(cb, read_len)
+            k = int(rng.integers(20, read_len - 20))
+            before = rng.random() < 0.5                    # is the clipped part before the aligned part?
+            cigar = [(4, k), (0, read_len - k)] if before else [(0, read_len - k), (4, k)]
+            clipop = "H" if rng.random() < 0.3 else "S"
+            sa_cig = ("%dM%d%s" % (k, read_len - k, clipop)) if before else ("%d%s%dM" % (read_len - k, clipop, k))
+            if rng.random() < 0.2:
+                sa_cig = sa_cig.replace("M", "M2D3I", 1) if rng.random() < 0.5 else sa_cig
+            strand = "-" if rng.random() < 0.4 else "+"
+            sa_q = 0 if rng.random() < 0.1 else int(rng.integers(10, 61))
+            sa = "%s,%d,%s,%s,%d,%d;" % (contigs[cb][0], pb + 1, strand, sa_cig, sa_q, int(rng.integers(0, 4)))
+            if rng.random() < 0.25:                        # more SA entries: the reference only ever uses the first
+                cc = int(rng.integers(0, nc))
+                sa += "%s,%d,%s,%dM%dS,%d,0;" % (contigs[cc][0], place(cc, read_len) + 1, "+", 30, read_len - 30,
+                                                 int(rng.integers(0, 61)))
+            paired = rng.random() < 0.7
+            flag = (0x1 | 0x2 | 0x40 | 0x20 if paired else 0) | ra | extra
+            ins = int(rng.integers(read_len, max_ins - 1))
+            emit(ca, pa, name, flag, mapq(), cigar, (ca, pa + ins) if paired else (-1, -1), ins if paired else 0,
+                 {"NM": int(rng.integers(0, 5)), "SA": sa}, with_seq=True)
+            if rng.random() < 0.8:                         # the supplementary record itself (skipped by the worker)
+                back = "%s,%d,%s,%s,%d,0;" % (contigs[ca][0], pa + 1, "-" if ra else "+",
+                                               "".join("%d%s" % (n, "MIDNSHP=X"[op]) for op, n in cigar), 60)
+                emit(cb, pb, name, 0x800 | (0x10 if strand == "-" else 0), sa_q, [(5, read_len - k), (0, k)], tags={"SA": back})
+            if paired:
+                emit(ca, pa + ins, name, 0x1 | 0x2 | 0x80 | 0x10, mapq(), [(0, read_len)], (ca, pa), -ins)
+        else:                                             # soft-clipped reads (clips fasta), secondary noise
+            k = int(rng.integers(1, 60))
+            cigar = [(4, k), (0, read_len - k)] if rng.random() < 0.5 else [(0, read_len - k), (4, k)]
+            if rng.random() < 0.15:
+                cigar = [(4, k), (0, read_len - k - 5), (4, 5)]
+            ins = int(rng.integers(read_len, max_ins - 1))
+            emit(ca, pa, name, 0x1 | 0x2 | 0x40 | 0x20 | ra | extra, mapq(), cigar, (ca, pa + ins), ins, with_seq=True)
+            emit(ca, pa + ins, name, 0x1 | 0x2 | 0x80 | 0x10, mapq(), [(0, read_len)], (ca, pa), -ins)
+            if rng.random() < 0.2:
+                emit(ca, place(ca, read_len), name, 0x100 | ra, mapq(), [(0, read_len)])
+    reads = []
+    for ci in range(nc):
+        reads.extend(sorted(out[ci], key=lambda r: r["pos"]))   # stable: equal positions keep emission order
+    return reads

@@ -65,8 +65,12 @@ if os.path.exists(step_csv):
         f.write("# total %.1f us\n" % tot)
     print("wrote step launches, total %.1f us" % tot)
 
-if os.path.exists(full_rep):
-    raw = subprocess.run(["ncu", "-i", full_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+raw_csv = f"{ROOT}/gpurun_out/prof_{tag}_raw.csv"     # `ncu -i ... --page raw --csv` run on the box (the report is too big to bring back)
+if os.path.exists(full_rep) or os.path.exists(raw_csv):
+    if os.path.exists(raw_csv):
+        raw = open(raw_csv).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", full_rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
     want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
@@ -77,14 +81,14 @@ if os.path.exists(full_rep):
     idx = [hdr.index(w) for w in want if w in hdr]
     traffic = collections.OrderedDict()
     with open(f"{out}/{tag}_full_capture_summary.tsv", "w") as f:
-        f.write(f"# {tag} -- ncu --set full --clock-control none --import-source on, tools/profile_target.py "
-                "(20M-signal 30X set; 61.8M reads coverage; 250 Mbp GC)\n")
+        f.write(f"# {tag} -- ncu --set full --clock-control none, tools/profile_target.py (20M-signal 30X set: 3rd clustering pass "
+                "onwards; 61.8M reads coverage x2; 250 Mbp GC; candidate aggregation; 61.8M-bin ploidy medians)\n")
         f.write("\t".join(hdr[i] for i in idx) + "\n")
         for r in rows[2:]:
             f.write("\t".join((r[i][:60] + (" " + units[i] if units[i] else "")) for i in idx) + "\n")
             name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
             rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
-            scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1}
+            scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1, "Tbyte": 1e12}
             t = float(r[rd]) * scale[units[rd]] + float(r[wr]) * scale[units[wr]]
             traffic.setdefault(name, []).append(t)
     # per-launch DRAM traffic of the named kernels (first launch of each = the x-axis / big one)
