@@ -217,7 +217,11 @@ def ncu_traffic(kernel, note_only=False):
     files = sorted(glob.glob(os.path.join(ROOT, "profiles", "*_traffic.json")))
     if not files:
         return None
-    rec = json.load(open(files[-1])).get(kernel)
+    table = json.load(open(files[-1]))
+    rec = table.get(kernel)
+    if rec is None:       # template arguments are printed differently across captures: match on the prefix
+        hits = [v for k, v in table.items() if k.startswith(kernel)]
+        rec = hits[0] if hits else None
     if rec is None:
         return None
     if note_only:
@@ -301,6 +305,67 @@ def coverage_leg(torch, args, hbm_peak, flush):
     out["verified"] = bool(np.array_equal(dchk.cpu().numpy().view(np.uint64), chk.view(np.uint64)))
     del start, end, bins
     torch.cuda.empty_cache()
+    return out
+
+
+def bam_leg(torch, args):
+    """`--cov` from a BAM FILE: libtdt_bam.so (BGZF inflated on the host cores, records as columns)
+    + the coverage kernel batch by batch, host->device copies and the final device->host read of the bins included.
+    The synthetic BAM (150-bp reads with bases and qualities, coordinate-sorted) is written once, untimed."""
+    import tempfile
+    from tiddit_b200 import bamio, synth, __main__ as cli
+    contigs = synth.GRCH38[20:22]
+    s, e, roff, lens = synth.coverage_reads(args.bam_reads, contigs=contigs)
+    n = len(s)
+    rng = np.random.default_rng(17)
+    rid = np.repeat(np.arange(len(contigs)), np.diff(roff)).astype(np.int32)
+    s = np.minimum(s, (lens[rid] - 150).astype(np.int32))      # whole 150M reads inside the contig (order is kept)
+    flag = np.where(rng.random(n) < 0.02, 0x400, 0).astype(np.uint16)
+    mapq = rng.integers(0, 61, n).astype(np.uint8)
+    tmp = tempfile.mkdtemp(prefix="tdt_bench_bam_")
+    path = os.path.join(tmp, "reads.bam")
+    bamio.write_bam_columns(path, contigs, rid, s, flag, mapq)
+    z, q = 500, 20
+    times = []
+    for it in range(4):
+        t0 = time.perf_counter()
+        cov, header = cli.coverage_from_bam(path, z, q)
+        torch.cuda.synchronize()
+        if it:
+            times.append(time.perf_counter() - t0)
+    dt = float(np.median(times))
+    out = {"reads": n, "file_bytes": os.path.getsize(path), "bin_size": z, "min_q": q, "s_per_pass": dt,
+           "reads_per_sec": n / dt, "file_MB_per_sec": os.path.getsize(path) / dt / 1e6, "host_threads": os.cpu_count(),
+           "path": "tiddit_b200.__main__.coverage_from_bam: BGZF inflate (zlib) on all host cores + record decode -> numpy "
+                   "columns -> filters -> H2D -> tdt_coverage_accumulate_contigs per 1M-read batch -> bins D2H",
+           "bound": "host: zlib inflate of the BGZF blocks (the coverage kernel takes microseconds per batch)"}
+    from oracle import oracle
+    keep = ((flag & 0x400) == 0) & (mapq >= q)
+    ok = True
+    for ci, (name, ln) in enumerate(contigs):
+        sel = keep & (rid == ci)
+        want, ebs = oracle.create_coverage({"SQ": [{"SN": name, "LN": ln}]}, z, name)
+        oracle.update_coverage_batch(s[sel], np.minimum(s[sel] + 150, 2 ** 31 - 1).astype(np.int32), z, want, ebs)
+        ok = ok and np.array_equal(cov[name].view(np.uint64), want.view(np.uint64))
+    out["verified"] = bool(ok)
+    if not args.no_cpu:
+        R = _ref_modules()
+        k = min(n, 1_000_000)
+        name, ln = contigs[0]
+        sel = np.flatnonzero(keep & (rid == 0))[:k]
+        hs, he = s[sel].tolist(), (s[sel] + 150).tolist()
+        if R is not None:
+            c0, e0 = R.tiddit_coverage.create_coverage({"SQ": [{"SN": name, "LN": ln}]}, z, name)
+            upd = R.tiddit_coverage.update_coverage
+            t0 = time.perf_counter()
+            for a, b in zip(hs, he):
+                upd(a, b, z, c0, e0)
+            dtc = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": len(hs) / dtc, "unit": "reads/s", "cores": 1, "kind": "reference",
+                                   "sample": "%d reads: the reference's update_coverage call per read only (%.1f s); its BAM "
+                                             "iteration through pysam, absent here, comes on top, so this flatters the CPU" % (len(hs), dtc)}
+    import shutil
+    shutil.rmtree(tmp, ignore_errors=True)
     return out
 
 
@@ -447,6 +512,7 @@ def main():
     ap.add_argument("--signals", type=int, default=0, help="override the workload's signal count")
     ap.add_argument("--cov-reads", type=int, default=617_653_966, help="reads for the coverage leg (30X = 617653966)")
     ap.add_argument("--no-coverage", action="store_true")
+    ap.add_argument("--bam-reads", type=int, default=2_000_000, help="reads of the synthetic BAM of the bam_coverage leg")
     ap.add_argument("--no-graph", action="store_true", help="issue the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--chunks", type=int, default=6, help="pair chunks of the pipelined host path (e2e, N=1)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baselines")
@@ -575,10 +641,11 @@ def main():
     sx_ms = stage_ms.get("sort_x", float("nan"))
     sort_bytes = (4.0 + 16.0 * n_pass) * n_mine
     same_shape = world == 1 and args.workload == "wgs30x" and not args.signals   # the shape the ncu capture was taken on
-    roofline = {"bound": "hbm", "kernel": "window_runs_small_kernel<X> (eps-range query + run labelling, posA axis)",
+    roofline = {"bound": "hbm", "kernel": "window_runs_small_kernel<X, two-phase> (eps-range query + run labelling, posA axis; "
+                                            "its tile sums are scanned by wr_tile_scan_kernel = stage tile_scan_x)",
                 "achieved": alg / k_ms / 1e6, "peak": hbm_peak, "peak_source": peak_src, "unit": "GB/s",
                 "frac": alg / k_ms / 1e6 / hbm_peak,
-                "traffic": ncu_traffic("window_runs_small_kernel<0>") if same_shape else None,
+                "traffic": ncu_traffic("window_runs_small_kernel<0") if same_shape else None,
                 "traffic_source": "profiles/*_traffic.json: dram__bytes_read.sum + dram__bytes_write.sum of this kernel's "
                                   "launch in the committed ncu --set full capture of the same 20M-signal set",
                 "algorithmic_bytes_per_launch": alg, "ms_per_launch": k_ms,
@@ -637,6 +704,7 @@ def main():
             _lib.release_workspaces()
             torch.cuda.empty_cache()
             line["ploidy_medians"] = medians_leg(torch, args, hbm_peak, flush)
+            line["bam_coverage"] = bam_leg(torch, args)
     if rank == 0:
         print(json.dumps(line))
     if world > 1:

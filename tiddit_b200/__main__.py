@@ -10,28 +10,17 @@ import os
 import sys
 
 
-def run_cov(argv):
-    parser = argparse.ArgumentParser("""tiddit --cov --bam inputfile [-o prefix]""")
-    parser.add_argument('--cov', help="generate a coverage bed/wig file", required=False, action="store_true")
-    parser.add_argument('--bam', type=str, required=True, help="coordinate sorted bam file(required)")
-    parser.add_argument('-o', type=str, default="output", help="output prefix(default=output)")
-    parser.add_argument('-z', type=int, default=500, help="use bins of specified size(default = 500bp) to measure the coverage of the entire bam file, set output to stdout to print to stdout")
-    parser.add_argument('-w', help="generate wig instead of bed", required=False, action="store_true")
-    parser.add_argument('-q', type=int, help="minimum mapping quality(default=20)", required=False, default=20)
-    parser.add_argument('--ref', type=str, help="reference fasta, used for reading cram")
-    args = parser.parse_args(argv)
-    if not os.path.isfile(args.bam):
-        print("error,  could not find the bam file")
-        return 1
-    from . import bamio, tiddit_coverage
+def coverage_from_bam(path, bin_size, min_q, threads=0, batch_reads=1 << 20):
+    """The reference's read loop (tiddit/__main__.py:225-242) on whole batches: libtdt_bam.so decodes the records into
+    columns, the (start, end) columns of the reads that count (mapped, not duplicate, mapq >= min_q) go to the coverage
+    kernel contig by contig.  -> ({contig: float64 bins}, header)"""
     import numpy as np
-    # the reference's loop (__main__.py:229-242) on whole batches: libtdt_bam.so decodes the records into columns,
-    # the (start, end) columns of the reads that count go to the coverage kernel contig by contig
-    with bamio.ColumnReader(args.bam) as reader:
+    from . import bamio, tiddit_coverage
+    with bamio.ColumnReader(path, threads=threads, batch_reads=batch_reads) as reader:
         bam_header = reader.header
-        cov = tiddit_coverage.DeviceCoverage(bam_header, args.z)
+        cov = tiddit_coverage.DeviceCoverage(bam_header, bin_size)
         for b in reader.batches():
-            keep = np.flatnonzero(((b.flag & (0x4 | 0x400)) == 0) & (b.mapq >= args.q))
+            keep = np.flatnonzero(((b.flag & (0x4 | 0x400)) == 0) & (b.mapq >= min_q))
             if not len(keep):
                 continue
             if np.any(b.ref_id[keep] < 0) or np.any(b.end[keep] < 0):
@@ -45,6 +34,24 @@ def run_cov(argv):
                 sel = keep[lo:hi]
                 cov.add_reads(reader.references[rid[lo]], b.pos[sel], b.end[sel])
     coverage_data, _ = cov.to_host()
+    return coverage_data, bam_header
+
+
+def run_cov(argv):
+    parser = argparse.ArgumentParser("""tiddit --cov --bam inputfile [-o prefix]""")
+    parser.add_argument('--cov', help="generate a coverage bed/wig file", required=False, action="store_true")
+    parser.add_argument('--bam', type=str, required=True, help="coordinate sorted bam file(required)")
+    parser.add_argument('-o', type=str, default="output", help="output prefix(default=output)")
+    parser.add_argument('-z', type=int, default=500, help="use bins of specified size(default = 500bp) to measure the coverage of the entire bam file, set output to stdout to print to stdout")
+    parser.add_argument('-w', help="generate wig instead of bed", required=False, action="store_true")
+    parser.add_argument('-q', type=int, help="minimum mapping quality(default=20)", required=False, default=20)
+    parser.add_argument('--ref', type=str, help="reference fasta, used for reading cram")
+    args = parser.parse_args(argv)
+    if not os.path.isfile(args.bam):
+        print("error,  could not find the bam file")
+        return 1
+    from . import tiddit_coverage
+    coverage_data, bam_header = coverage_from_bam(args.bam, args.z, args.q)
     if args.w:
         tiddit_coverage.print_coverage(coverage_data, bam_header, args.z, "wig", args.o + ".wig")
     else:

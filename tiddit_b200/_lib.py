@@ -9,7 +9,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libtdt_b200.so")
+# TDT_B200_LIB: another build of the same library (A/B of compile-time variants, tools/gpu_ab.sh)
+LIB_PATH = os.environ.get("TDT_B200_LIB") or os.path.join(_HERE, "libtdt_b200.so")
 
 TDT_OK, TDT_E_ARG, TDT_E_WORKSPACE, TDT_E_CUDA, TDT_E_RANGE = 0, -1, -2, -3, -4
 

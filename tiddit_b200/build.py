@@ -43,12 +43,13 @@ def build_bam(force=False):
     return BAM_LIB
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, out=None, build_dir=None):
+    """out / build_dir: build a variant (TDT_NVCC_DEFS) next to the default library without touching it."""
     build_bam(force)
-    if not force and not _stale():
+    if out is None and not force and not _stale():
         return LIB
     objs = []
-    build_dir = os.path.join(HERE, "_build")
+    build_dir = build_dir or os.path.join(HERE, "_build")
     os.makedirs(build_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -59,14 +60,15 @@ def build(force=False, verbose=False):
         objs.append(obj)
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write("== nvcc %s ==\n%s\n" % (src, out))
+            sys.stderr.write("== nvcc %s ==\n%s\n" % (src, log))
         failed = failed or p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([_nvcc(), "-shared", "-cudart", "static", "-o", LIB] + objs)
-    return LIB
+    subprocess.check_call([_nvcc(), "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+                           "-o", out or LIB] + objs)
+    return out or LIB
 
 
 if __name__ == "__main__":

@@ -51,6 +51,7 @@ struct WRParams {
     u32 *stw;             // out: run-start bits      (one word per 32 elements)
     u32 *cvw;             // out: "labelled" bits
     u32 *tile_pref;       // out: [tile][2] = run starts before the tile, second sum before the tile
+    int two_phase;        // 1: tile_pref receives the tile's OWN two sums; wr_tile_scan_kernel scans them in place
     u32 *totals;          // out: [0] = #runs, [1] = second sum (X: #labelled elements, Y: #segments)
     int32_t *gcnt_start;  // Y: [segment rank] = run starts before the segment; [#segments] = #runs
     int32_t *rank_of;     // Y, optional: rank_of[seg_value[j]] = segment rank, written at segment heads
@@ -308,12 +309,21 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_kernel(const WRParams 
 // labelled elements is a log-step shift/OR on the 64-bit (previous:current) word pair, and the prefix over
 // the 16 words is a warp shuffle scan.  Two block barriers in all (tile staged / carry known).
 // ----------------------------------------------------------------------------------------------
-template <int MODE>
+//
+// TWO_PHASE (the production form): the kernel stops after the bitmasks -- the warps add their two sums in
+// shared memory, the last one to arrive stores the tile's sums and everybody exits; wr_tile_scan_kernel turns
+// the sums into tile prefixes (in place) and wr_ranks_kernel (Y) writes the per-segment counts.  The chained form keeps a CTA resident until its look-back through the earlier tiles is
+// over (a third of all stall samples in the r01_v3 capture, 51 us for 4883 tiles); without the chain a CTA
+// lives for one TMA round trip plus 17 ballots.
+#ifndef TDT_WR_TWO_PHASE
+#define TDT_WR_TWO_PHASE 1
+#endif
+template <int MODE, bool TWO_PHASE>
 __global__ void __launch_bounds__(WR_THREADS) window_runs_small_kernel(const WRParams p) {
     constexpr int HL = 32, WPW = WR_WORDS / WR_WARPS;  // left halo, words per warp (16)
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ u32 s_wtot[WR_WARPS][2], s_wbase[WR_WARPS][2], s_pref[4];
+    __shared__ u32 s_wtot[WR_WARPS][2], s_wbase[WR_WARPS][2], s_pref[4], s_sum[3];
 
     const int m = p.m;
     const int HR = (m + 3) & ~3;
@@ -329,6 +339,7 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_small_kernel(const WRP
     const int64_t ext_base = tile_base - HL;
 
     if (threadIdx.x == 0) {
+        if (TWO_PHASE) s_sum[0] = s_sum[1] = s_sum[2] = 0u;
         mbar_init(&mbar, 1);
         fence_mbar_init();
         const int64_t n_pad = (n + 3) & ~(int64_t)3;
@@ -408,6 +419,19 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_small_kernel(const WRP
         p.stw[gw] = st;
         p.cvw[gw] = cv;
     }
+    if (TWO_PHASE) {
+        if (lane == WPW) {
+            atomicAdd(&s_sum[0], is);
+            atomicAdd(&s_sum[1], ic);
+            __threadfence_block();
+            if (atomicAdd(&s_sum[2], 1u) == WR_WARPS - 1) {  // every warp's sums are in
+                __threadfence_block();
+                *(uint2 *)(p.tile_pref + 2 * (int64_t)tile) =
+                    make_uint2(*(volatile u32 *)&s_sum[0], *(volatile u32 *)&s_sum[1]);
+            }
+        }
+        return;
+    }
     if (lane == WPW) {
         s_wtot[warp][0] = is;
         s_wtot[warp][1] = ic;
@@ -463,6 +487,119 @@ __global__ void __launch_bounds__(WR_THREADS) window_runs_small_kernel(const WRP
         p.totals[0] = totS;
         p.totals[1] = totC;
         if (MODE == MODE_Y) p.gcnt_start[totC] = (int32_t)totS;
+    }
+}
+
+// ----------------------------------------------------------------------------------------------
+// Second phase of the two-phase range query: tile prefixes from the per-warp sums (one CTA; the 30X set has
+// 4883 tiles, 64 bytes each), the totals, and -- y axis -- the per-segment run counts.
+// ----------------------------------------------------------------------------------------------
+constexpr int TS_THREADS = 1024, TS_PER = 8;   // one round for up to 8192 tiles (33.5 M elements)
+
+// in place: tile_pref[tile] = (the tile's own sums) -> (sums over the earlier tiles); totals = sums over all tiles
+__global__ void __launch_bounds__(TS_THREADS) wr_tile_scan_kernel(const Dims *dims, u32 *tile_pref, u32 *totals,
+                                                                  int32_t *gcnt_start) {
+    __shared__ u32 s_part[TS_THREADS / 32][2];
+    const int64_t n = dims->n;
+    const int n_tiles = (int)((n + WR_TILE - 1) / WR_TILE);
+    if (n_tiles == 0) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint2 *tp = (uint2 *)tile_pref;
+    u32 carryA = 0, carryB = 0;
+    for (int base = 0; base < n_tiles; base += TS_THREADS * TS_PER) {
+        const int t0 = base + threadIdx.x * TS_PER;
+        uint2 v[TS_PER];
+#pragma unroll
+        for (int k = 0; k < TS_PER; k++) v[k] = t0 + k < n_tiles ? tp[t0 + k] : make_uint2(0u, 0u);
+        u32 sumA = 0, sumB = 0;
+#pragma unroll
+        for (int k = 0; k < TS_PER; k++) {
+            sumA += v[k].x;
+            sumB += v[k].y;
+        }
+        u32 incA = sumA, incB = sumB;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const u32 a = __shfl_up_sync(0xffffffffu, incA, o);
+            const u32 b = __shfl_up_sync(0xffffffffu, incB, o);
+            if (lane >= o) {
+                incA += a;
+                incB += b;
+            }
+        }
+        if (lane == 31) {
+            s_part[warp][0] = incA;
+            s_part[warp][1] = incB;
+        }
+        __syncthreads();
+        u32 baseA = carryA + incA - sumA, baseB = carryB + incB - sumB;
+#pragma unroll 8
+        for (int w = 0; w < TS_THREADS / 32; w++) {
+            const u32 a = s_part[w][0], b = s_part[w][1];
+            if (w < warp) {
+                baseA += a;
+                baseB += b;
+            }
+            carryA += a;
+            carryB += b;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < TS_PER; k++) {
+            if (t0 + k < n_tiles) tp[t0 + k] = make_uint2(baseA, baseB);
+            baseA += v[k].x;
+            baseB += v[k].y;
+        }
+    }
+    if (threadIdx.x == 0) {
+        totals[0] = carryA;
+        totals[1] = carryB;
+        if (gcnt_start) gcnt_start[carryB] = (int32_t)carryA;
+    }
+}
+
+// y axis: every segment head records how many runs precede its segment (DBSCAN.py:88 restarts the count at 0)
+// and, optionally, the rank of its segment.  One CTA per tile: 128 threads, one word each.
+__global__ void __launch_bounds__(WR_WORDS) wr_ranks_kernel(const u32 *__restrict__ heads, const u32 *__restrict__ stw,
+                                                            const u32 *__restrict__ tile_pref, const Dims *dims,
+                                                            int32_t *__restrict__ gcnt_start, int32_t *rank_of,
+                                                            const int32_t *__restrict__ seg_value) {
+    __shared__ u32 s_part[WR_WORDS / 32][2];
+    const int64_t n = dims->n;
+    const int64_t gw = (int64_t)blockIdx.x * WR_WORDS + threadIdx.x;
+    if ((int64_t)blockIdx.x * WR_TILE >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const bool live = gw * 32 < n;
+    const u32 hword = live ? heads[gw] : 0u, st = live ? stw[gw] : 0u;
+    const u32 cs = __popc(st), cc = __popc(hword);
+    u32 is = cs, ic = cc;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 a = __shfl_up_sync(0xffffffffu, is, o);
+        const u32 b = __shfl_up_sync(0xffffffffu, ic, o);
+        if (lane >= o) {
+            is += a;
+            ic += b;
+        }
+    }
+    if (lane == 31) {
+        s_part[warp][0] = is;
+        s_part[warp][1] = ic;
+    }
+    __syncthreads();
+    u32 baseS = tile_pref[2 * (int64_t)blockIdx.x] + (is - cs), baseC = tile_pref[2 * (int64_t)blockIdx.x + 1] + (ic - cc);
+    for (int w = 0; w < warp; w++) {
+        baseS += s_part[w][0];
+        baseC += s_part[w][1];
+    }
+    u32 h = hword;
+    while (h) {
+        const int b = __ffs(h) - 1;
+        const u32 below = (1u << b) - 1u;
+        const u32 rank = baseC + __popc(hword & below);
+        gcnt_start[rank] = (int32_t)(baseS + __popc(st & below));
+        if (rank_of) rank_of[seg_value[gw * 32 + b]] = (int32_t)rank;
+        h &= h - 1;
     }
 }
 
@@ -937,12 +1074,32 @@ static int grid_for(int64_t n, int threads) {
     return (int)b;
 }
 
+// second phase (p.two_phase and TDT_WR_TWO_PHASE): tile prefixes, totals, y-axis segment counts
+template <int MODE>
+static int launch_window_runs_finish(const WRParams &p, int64_t n_max, cudaStream_t st) {
+#if TDT_WR_TWO_PHASE
+    if (!p.two_phase || p.m > 32) return TDT_OK;
+    TDT_LAUNCH(wr_tile_scan_kernel, 1, TS_THREADS, 0, st, p.dims, p.tile_pref, p.totals,
+               MODE == MODE_Y ? p.gcnt_start : nullptr);
+    if (MODE == MODE_Y)
+        TDT_LAUNCH(wr_ranks_kernel, (unsigned)wr_tiles(n_max), WR_WORDS, 0, st, p.heads, p.stw, p.tile_pref, p.dims,
+                   p.gcnt_start, p.rank_of, p.seg_value);
+#endif
+    return TDT_OK;
+}
+
 template <int MODE, bool GENERAL>
 static int launch_window_runs(const WRParams &p, int64_t n_max, cudaStream_t st) {
     if (!GENERAL && p.m <= 32) {
         const size_t HR = ((size_t)p.m + 3) & ~(size_t)3;
         const size_t smem = (32 + WR_TILE + HR) * 4 + ((32 + WR_TILE + HR) / 32 + 2) * 4;
-        TDT_LAUNCH((window_runs_small_kernel<MODE>), (unsigned)wr_tiles(n_max), WR_THREADS, smem, st, p);
+#if TDT_WR_TWO_PHASE
+        if (p.two_phase) {
+            TDT_LAUNCH((window_runs_small_kernel<MODE, true>), (unsigned)wr_tiles(n_max), WR_THREADS, smem, st, p);
+            return TDT_OK;
+        }
+#endif
+        TDT_LAUNCH((window_runs_small_kernel<MODE, false>), (unsigned)wr_tiles(n_max), WR_THREADS, smem, st, p);
         return TDT_OK;
     }
     const size_t smem = wr_smem_bytes(p.m);
@@ -1018,9 +1175,15 @@ static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, 
     p.gcnt_start = b.gcnt_start;
     p.rank_of = PLAIN ? rank_of : nullptr;
     p.seg_value = b.gx;
+    p.two_phase = 1;
     {
         ProfScope ps("window_runs_y", st);
         int rc = launch_window_runs<MODE_Y, false>(p, n, st);
+        if (rc) return rc;
+    }
+    {
+        ProfScope ps("tile_scan_y", st);
+        int rc = launch_window_runs_finish<MODE_Y>(p, n, st);
         if (rc) return rc;
         if (PLAIN) TDT_LAUNCH(set_nseg_from_totals_kernel, 1, 1, 0, st, &b.small->dims_y, b.small->totals_y);
     }
@@ -1093,10 +1256,16 @@ static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t 
     p.cvw = b.cvwX;
     p.tile_pref = b.tprefX;
     p.totals = b.small->totals_x;
+    p.two_phase = presorted_plain ? 0 : 1;
     {
         ProfScope ps("window_runs_x", st);
         int rc = presorted_plain ? launch_window_runs<MODE_X, true>(p, n, st)
                                  : launch_window_runs<MODE_X, false>(p, n, st);
+        if (rc) return rc;
+    }
+    {
+        ProfScope ps("tile_scan_x", st);
+        int rc = launch_window_runs_finish<MODE_X>(p, n, st);
         if (rc) return rc;
     }
     {

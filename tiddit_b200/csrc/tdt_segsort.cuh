@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256) segsort_tiny_kernel(SSArgs a) {
 // (mm: this warp's 256 words, all zero on entry and on exit)
 #ifndef TDT_SS_MATCH_BALLOT
 #define TDT_SS_MATCH_BALLOT 0   // measured on B200 (r01, posA sort of the 30X set): ballots 0.74 ms, atomicOr 0.65 ms
+                                // (later tree: atomicOr 0.60 ms, __match_any_sync / SASS MATCH.ANY 0.86 ms)
 #endif
 constexpr int SS_MM = TDT_SS_MATCH_BALLOT ? 0 : 1;  // per-warp match words only for the atomicOr variant
 __device__ __forceinline__ uint32_t ss_match(uint32_t *mm, uint32_t d, bool valid, int bits) {

@@ -1,13 +1,15 @@
 #!/bin/bash
-# A/B of compile-time variants on the GPU box: VARIANTS="name1:-DX=1 name2:-DX=0,-DY=2" bash tools/gpu_ab.sh
-# each variant: forced rebuild, the sort + cluster parity tests, a short device bench; stage times to gpurun_out/ab_<name>.json
+# A/B of compile-time variants on the GPU box.  Variants are pre-built by tools/build_variants.sh into
+# tiddit_b200/_variants/ (the box only runs them): VARIANTS="name1 name2" bash tools/gpu_ab.sh
+# each variant: the sort + cluster parity tests, a short device bench; stage times to gpurun_out/ab_<name>.json
 mkdir -p gpurun_out
-for v in ${VARIANTS:-base:}; do
-  name=${v%%:*}; defs=${v#*:}; defs=${defs//,/ }
-  echo "== variant $name  defs: $defs"
-  TDT_NVCC_DEFS="$defs" python -m tiddit_b200.build --force > gpurun_out/ab_build_$name.log 2>&1 || { echo build failed; tail -5 gpurun_out/ab_build_$name.log; continue; }
+for name in ${VARIANTS:-default}; do
+  lib=tiddit_b200/_variants/libtdt_b200_$name.so
+  [ "$name" = default ] && lib=tiddit_b200/libtdt_b200.so
+  echo "== variant $name ($lib)"
+  export TDT_B200_LIB=$PWD/$lib
   timeout 600 python -m pytest tests/test_gpu_segsort.py tests/test_gpu_cluster.py -m gpu -q -x --timeout 300 2>&1 | tail -2
-  timeout 600 python bench.py --steps ${STEPS:-10} --warmup 3 --no-cpu --no-coverage --no-extra ${BENCH_ARGS} > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
+  timeout 600 python bench.py --steps ${STEPS:-20} --warmup 3 --no-cpu --no-coverage --no-extra ${BENCH_ARGS} > gpurun_out/ab_$name.json 2> gpurun_out/ab_$name.err
   python - <<PY
 import json
 try:
@@ -17,5 +19,4 @@ except Exception as e:
     print("$name: no result", e)
 PY
 done
-# leave the default build in place
-python -m tiddit_b200.build --force > /dev/null 2>&1
+unset TDT_B200_LIB

@@ -7,12 +7,12 @@ R=${ROUND:-r01}
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_${R}.csv \
     python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1
 echo "launch list rc=$?"
-SKIP=58 COUNT=29 bash tools/gpu_launches.sh
+SKIP=64 COUNT=32 bash tools/gpu_launches.sh
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:'agg_|segsort' -s 119 -c 50 --csv --log-file gpurun_out/agg_launches.csv python tools/agg_target.py > gpurun_out/agg_launches.log 2>&1
 echo "agg step rc=$?"
 timeout 1200 ncu --set full --clock-control none \
-    -k regex:'window_runs_small|coverage_kernel|gc_small|segsort_pass|segsort_local|segsort_tiny|final_labels|pack_y|agg_|med_pass' \
-    -s 31 -c 60 -o /tmp/prof_${R} -f python tools/profile_target.py > gpurun_out/prof.log 2>&1
+    -k regex:'window_runs_small|wr_|coverage_kernel|gc_small|segsort_pass|segsort_local|segsort_tiny|final_labels|pack_y|agg_|med_pass' \
+    -s 36 -c 64 -o /tmp/prof_${R} -f python tools/profile_target.py > gpurun_out/prof.log 2>&1
 echo "full capture rc=$?"; tail -2 gpurun_out/prof.log
 ncu -i /tmp/prof_${R}.ncu-rep --page raw --csv > gpurun_out/prof_${R}_raw.csv 2> gpurun_out/prof_export.err
 echo "raw export rc=$? $(wc -c < gpurun_out/prof_${R}_raw.csv) bytes"
