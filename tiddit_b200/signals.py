@@ -84,6 +84,19 @@ class PackedSignals:
     def from_tab(cls, prefix, chromosomes, contig_length, samples, is_mp, min_contig, skip_assembly):
         """tiddit_cluster.pyx:47-137.  Quirks kept: positions are clamped to the contig length; for discordants
         the posB test is nested inside the posA test and overwrites posA (:67-70)."""
+        def lines(stem, sample):
+            with open("{}_tiddit/{}_{}.tab".format(prefix, stem, sample)) as handle:
+                yield from handle
+
+        sources = [(lines("discordants", sample), lines("splits", sample),
+                    None if skip_assembly else lines("contigs", sample)) for sample in samples]
+        return cls.from_lines(sources, chromosomes, contig_length, samples, is_mp, min_contig)
+
+    @classmethod
+    def from_lines(cls, sources, chromosomes, contig_length, samples, is_mp, min_contig):
+        """The same records from in-memory lines: sources[k] = (discordant lines, split lines, contig lines or None)
+        of samples[k], in the tab-file format -- e.g. tiddit_signal.discordant_lines / split_lines, so that the
+        text files between the signal and the cluster stage need not be read back."""
         chrA_l, chrB_l, posA_l, posB_l, span_l, name_l, flag_l, samp_l, oa_l, ob_l = ([] for _ in range(10))
         name_ids, ori_ids = {}, {}
 
@@ -105,33 +118,32 @@ class PackedSignals:
             oa_l.append(intern(ori_ids, oriA))
             ob_l.append(intern(ori_ids, oriB))
 
-        for k, sample in enumerate(samples):
-            with open("{}_tiddit/discordants_{}.tab".format(prefix, sample)) as handle:
+        for k, (disc, splits, contigs) in enumerate(sources):
+            for line in disc:
+                f = line.rstrip().split("\t")
+                chrA, chrB = f[1], f[2]
+                if contig_length[chrA] < min_contig or contig_length[chrB] < min_contig:
+                    continue
+                posA, posB = find_discordant_pos(f, is_mp)
+                if int(posA) > contig_length[chrA]:
+                    posA = contig_length[chrA]
+                    if int(posB) > contig_length[chrB]:
+                        posA = contig_length[chrB]
+                add(k, KIND_D, f[0], chrA, chrB, posA, f[5], posB, f[8], f[3], f[4], f[6], f[7])
+            for handle, kind in ((splits, KIND_S), (contigs, KIND_A)):
+                if handle is None:
+                    continue
                 for line in handle:
                     f = line.rstrip().split("\t")
                     chrA, chrB = f[1], f[2]
                     if contig_length[chrA] < min_contig or contig_length[chrB] < min_contig:
                         continue
-                    posA, posB = find_discordant_pos(f, is_mp)
+                    posA, posB = f[3], f[5]
                     if int(posA) > contig_length[chrA]:
                         posA = contig_length[chrA]
-                        if int(posB) > contig_length[chrB]:
-                            posA = contig_length[chrB]
-                    add(k, KIND_D, f[0], chrA, chrB, posA, f[5], posB, f[8], f[3], f[4], f[6], f[7])
-            sources = [("splits", KIND_S)] + ([] if skip_assembly else [("contigs", KIND_A)])
-            for stem, kind in sources:
-                with open("{}_tiddit/{}_{}.tab".format(prefix, stem, sample)) as handle:
-                    for line in handle:
-                        f = line.rstrip().split("\t")
-                        chrA, chrB = f[1], f[2]
-                        if contig_length[chrA] < min_contig or contig_length[chrB] < min_contig:
-                            continue
-                        posA, posB = f[3], f[5]
-                        if int(posA) > contig_length[chrA]:
-                            posA = contig_length[chrA]
-                        if int(posB) > contig_length[chrB]:
-                            posB = contig_length[chrB]
-                        add(k, kind, f[0], chrA, chrB, posA, f[4], posB, f[6], f[7], f[8], f[9], f[10])
+                    if int(posB) > contig_length[chrB]:
+                        posB = contig_length[chrB]
+                    add(k, kind, f[0], chrA, chrB, posA, f[4], posB, f[6], f[7], f[8], f[9], f[10])
 
         # group by pair in the reference's visiting order (:140-150); a pair whose chrA or chrB is not listed in
         # `chromosomes` is never visited

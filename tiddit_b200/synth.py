@@ -182,7 +182,7 @@ def signal_records(posA, posB, seg_off, seed=11, split_frac=0.18, contig_frac=0.
             "same_chrom": same, "n_names": n}
 
 
-def sv_bam_reads(contigs, n_fragments=4000, seed=13, read_len=100, max_ins=600):
+def sv_bam_reads(contigs, n_fragments=4000, seed=13, read_len=100, max_ins=600, n_events=12):
     """Reads for bamio.write_bam that exercise every branch of the signal worker (tiddit_signal.pyx:169-221):
     proper pairs, discordant pairs (far apart on one contig, across contigs, every orientation, mates that are
     unmapped / filtered / low quality), split reads with SA tags (one or several entries, either strand, soft and
@@ -283,6 +283,28 @@ def sv_bam_reads(contigs, n_fragments=4000, seed=13, read_len=100, max_ins=600):
             emit(ca, pa + ins, name, 0x1 | 0x2 | 0x80 | 0x10, mapq(), [(0, read_len)], (ca, pa), -ins)
             if rng.random() < 0.2:
                 emit(ca, place(ca, read_len), name, 0x100 | ra, mapq(), [(0, read_len)])
+    # planted structural variants: fragments that agree on a pair of breakpoints, so that the cluster stage has
+    # candidates to find (discordant pairs scattered around the breakpoints + split reads exactly on them)
+    for ev in range(n_events):
+        ca, cb = sorted(rng.integers(0, nc, 2).tolist()) if rng.random() < 0.4 else [int(rng.integers(0, nc))] * 2
+        bpa = place(ca, 4 * read_len + max_ins) + 2 * read_len
+        bpb = place(cb, 4 * read_len + max_ins) + 2 * read_len
+        if ca == cb and abs(bpb - bpa) < 3 * max_ins:
+            bpb = min(bpa + 5 * max_ins, contigs[cb][1] - 3 * read_len)
+        rev_b = rng.random() < 0.5
+        for k in range(int(rng.integers(4, 14))):
+            name = "sv%d_%d" % (ev, k)
+            q = int(rng.integers(25, 61))
+            if rng.random() < 0.65:
+                pa = max(0, bpa - read_len - int(rng.integers(0, 150)))
+                pb = min(bpb + int(rng.integers(0, 150)), contigs[cb][1] - read_len - 1)
+                tl = (pb + read_len - pa) if ca == cb else 0
+                emit(ca, pa, name, 0x1 | 0x40 | (0x20 if rev_b else 0), q, [(0, read_len)], (cb, pb), tl)
+                emit(cb, pb, name, 0x1 | 0x80 | (0x10 if rev_b else 0), q, [(0, read_len)], (ca, pa), -tl)
+            else:
+                keep = int(rng.integers(30, read_len - 30))
+                sa = "%s,%d,%s,%dS%dM,%d,0;" % (contigs[cb][0], bpb + 1, "-" if rev_b else "+", keep, read_len - keep, q)
+                emit(ca, bpa - keep, name, 0, q, [(0, keep), (4, read_len - keep)], tags={"SA": sa}, with_seq=True)
     reads = []
     for ci in range(nc):
         reads.extend(sorted(out[ci], key=lambda r: r["pos"]))   # stable: equal positions keep emission order

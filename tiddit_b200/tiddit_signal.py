@@ -20,7 +20,7 @@ import numpy as np
 
 from . import bamio, tiddit_coverage
 
-__all__ = ["main", "collect", "SA_analysis", "find_SA_query_range"]
+__all__ = ["main", "collect", "packed_signals", "discordant_lines", "split_lines", "SA_analysis", "find_SA_query_range"]
 
 _SA_OPS = {"M": 0, "S": 4, "H": 5, "D": 2, "I": 1}   # the operations the reference knows (tiddit_signal.pyx:24)
 
@@ -214,6 +214,17 @@ def split_lines(signals):
         for chrB, fragments in row.items():
             for name, fields in fragments.items():
                 yield "{}\t{}\t{}\t{}\n".format(name, chrA, chrB, "\t".join(map(str, fields)))
+
+
+def packed_signals(signals, sample_id, is_mp, min_contig, contig_lines=None):
+    """Signals -> signals.PackedSignals, the arrays tiddit_cluster.cluster_packed takes: the records
+    `main` writes to the tab files, handed over in memory.  contig_lines: the lines of contigs_<sample>.tab when the
+    assembly stage ran, None for --skip_assembly."""
+    from .signals import PackedSignals
+    contig_length = {sq["SN"]: sq["LN"] for sq in signals.header["SQ"]}
+    chromosomes = [sq["SN"] for sq in signals.header["SQ"]]     # tiddit/__main__.py:119-123: every @SQ, header order
+    return PackedSignals.from_lines([(discordant_lines(signals), split_lines(signals), contig_lines)], chromosomes,
+                                    contig_length, [sample_id], is_mp, min_contig)
 
 
 def main(bam_file_name, ref, prefix, min_q, max_ins, sample_id, threads, min_contig, skip_index, min_anchor_len,
