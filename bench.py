@@ -677,6 +677,29 @@ def main():
             "gpu_launches": int(launches) * args.steps, "gpu_launches_per_step": int(launches),
             "clocks": clocks, "roofline": roofline}
 
+    # N > 1, secondary figure: fixed work PER GPU (every rank clusters a whole 20M-signal set of its own -- N samples
+    # in flight, no collective), next to the headline strong-scaling number of BASELINE configs[3]
+    if world > 1:
+        a_full = torch.from_numpy(posA).cuda()
+        b_full = torch.from_numpy(posB).cuda()
+        off_full = torch.from_numpy(seg_off).cuda()
+        lab_full = torch.empty(n_total, dtype=torch.int32, device="cuda")
+        full_runner = None if args.no_graph else engine.GraphRunner(a_full, b_full, off_full, P_total, eps, m, L, lab_full)
+
+        def step_full():
+            if full_runner is not None:
+                full_runner.replay()
+            else:
+                device_ops.cluster_labels_device(a_full, b_full, off_full, P_total, eps, m, L, labels_out=lab_full)
+
+        ms_full = timed(step_full, args.steps, args.warmup)
+        if full_runner is not None:
+            full_runner.check()
+        line["weak_scaling"] = {"value": world * n_total / ms_full * 1e3, "unit": UNIT, "ms_per_step": ms_full,
+                                "work": "every rank clusters its own copy-sized set of %d signals (N sets in flight), "
+                                        "no collective; max over ranks" % n_total}
+        del a_full, b_full, off_full, lab_full, full_runner
+
     # result check of what the timed paths produced (the oracle as checker, bounded to the sample pairs' cost)
     torch.cuda.synchronize()
     if world > 1:

@@ -54,10 +54,17 @@ struct tdt_bam_reader {
     size_t map_len = 0;
     size_t cpos = 0;  // next compressed block
     int threads = 1;
-    std::vector<uint8_t> buf;  // inflated window
+    std::vector<uint8_t> buf;  // inflated window being parsed
     size_t bpos = 0, bend = 0;
-    size_t window_blocks = 1024;  // blocks inflated per refill (<= 64 MiB inflated)
+    size_t window_blocks = 1024;  // blocks inflated per window (<= 64 MiB inflated)
     bool eof = false;
+    // the NEXT window is inflated in the background while the caller works on the current one
+    std::vector<uint8_t> nbuf;    // next window, data at [kPad, kPad + nbytes)
+    std::thread bg;
+    bool bg_running = false;
+    int bg_rc = 0;                // 1 = bytes ready, 0 = end of file, < 0 error
+    size_t bg_bytes = 0;
+    char bg_err[512] = "";
     std::string text;
     std::vector<std::string> ref_names;
     std::vector<int32_t> ref_lens;
@@ -66,52 +73,54 @@ struct tdt_bam_reader {
 
 namespace {
 
-// Appends up to r->window_blocks inflated blocks after compacting the unread tail to the front.
-// Returns 1 if bytes were added, 0 at end of file, < 0 on error.
-int refill(tdt_bam_reader *r) {
-    if (r->bpos > 0) {
-        size_t left = r->bend - r->bpos;
-        if (left) memmove(r->buf.data(), r->buf.data() + r->bpos, left);
-        r->bpos = 0;
-        r->bend = left;
-    }
+constexpr size_t kPad = 1 << 20;  // headroom in front of a window for the unread tail of the previous one
+
+// Inflates the next up-to-window_blocks blocks (from r->cpos, which it advances) into dst at offset kPad.
+// Runs on the background thread: touches only cpos, dst and the bg_* fields.  Returns 1 / 0 (end of file) / < 0.
+int inflate_window(tdt_bam_reader *r, std::vector<uint8_t> &dst, size_t *nbytes, char *err, size_t err_len) {
     std::vector<Block> blocks;
-    size_t out = r->bend;
+    size_t out = kPad;
+    *nbytes = 0;
     while (blocks.size() < r->window_blocks && r->cpos < r->map_len) {
         const uint8_t *h = r->map + r->cpos;
         size_t left = r->map_len - r->cpos;
-        if (left < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4))
-            return fail(TDT_BAM_E_FORMAT, "%s: not a BGZF block at offset %zu", r->path.c_str(), r->cpos);
-        uint32_t xlen = le16(h + 10);
-        if (left < 12 + (size_t)xlen) return fail(TDT_BAM_E_FORMAT, "%s: truncated BGZF header", r->path.c_str());
-        int64_t bsize = -1;
-        for (uint32_t x = 0; x + 4 <= xlen;) {
-            const uint8_t *sf = h + 12 + x;
-            uint32_t slen = le16(sf + 2);
-            if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (int64_t)le16(sf + 4) + 1;
-            x += 4 + slen;
+        if (left < 18 || h[0] != 0x1f || h[1] != 0x8b || h[2] != 8 || !(h[3] & 4)) {
+            snprintf(err, err_len, "%s: not a BGZF block at offset %zu", r->path.c_str(), r->cpos);
+            return TDT_BAM_E_FORMAT;
         }
-        if (bsize < 0 || (size_t)bsize > left || (size_t)bsize < 12 + (size_t)xlen + 8)
-            return fail(TDT_BAM_E_FORMAT, "%s: bad BGZF block size at offset %zu", r->path.c_str(), r->cpos);
+        uint32_t xlen = le16(h + 10);
+        int64_t bsize = -1;
+        if (left >= 12 + (size_t)xlen) {
+            for (uint32_t x = 0; x + 4 <= xlen;) {
+                const uint8_t *sf = h + 12 + x;
+                uint32_t slen = le16(sf + 2);
+                if (sf[0] == 'B' && sf[1] == 'C' && slen == 2 && x + 6 <= xlen) bsize = (int64_t)le16(sf + 4) + 1;
+                x += 4 + slen;
+            }
+        }
+        if (bsize < 0 || (size_t)bsize > left || (size_t)bsize < 12 + (size_t)xlen + 8) {
+            snprintf(err, err_len, "%s: bad or truncated BGZF block at offset %zu", r->path.c_str(), r->cpos);
+            return TDT_BAM_E_FORMAT;
+        }
         Block b;
         b.payload = h + 12 + xlen;
         b.clen = (uint32_t)(bsize - 12 - xlen - 8);
         b.crc = le32(h + bsize - 8);
         b.isize = le32(h + bsize - 4);
-        if (b.isize > 65536) return fail(TDT_BAM_E_FORMAT, "%s: BGZF block inflates to %u bytes", r->path.c_str(), b.isize);
+        if (b.isize > 65536) {
+            snprintf(err, err_len, "%s: BGZF block inflates to %u bytes", r->path.c_str(), b.isize);
+            return TDT_BAM_E_FORMAT;
+        }
         b.dst = out;
         out += b.isize;
         r->cpos += (size_t)bsize;
         if (b.isize) blocks.push_back(b);  // the EOF marker and other empty blocks carry nothing
     }
-    if (blocks.empty()) {
-        r->eof = true;
-        return 0;
-    }
-    if (r->buf.size() < out) r->buf.resize(out + (out >> 2));
+    if (blocks.empty()) return 0;
+    if (dst.size() < out) dst.resize(out + (out >> 3));
     std::atomic<size_t> next(0);
     std::atomic<int> bad(0);
-    uint8_t *base = r->buf.data();
+    uint8_t *base = dst.data();
     auto work = [&]() {
         z_stream zs;
         memset(&zs, 0, sizeof zs);
@@ -141,12 +150,51 @@ int refill(tdt_bam_reader *r) {
         work();
         for (auto &t : pool) t.join();
     }
-    if (bad) return fail(TDT_BAM_E_FORMAT, "%s: a BGZF block failed to inflate (corrupt data or CRC mismatch)", r->path.c_str());
-    r->bend = out;
+    if (bad) {
+        snprintf(err, err_len, "%s: a BGZF block failed to inflate (corrupt data or CRC mismatch)", r->path.c_str());
+        return TDT_BAM_E_FORMAT;
+    }
+    *nbytes = out - kPad;
     return 1;
 }
 
-// at least n unread bytes in the window (used for the header only: it compacts the buffer)
+void start_prefetch(tdt_bam_reader *r) {
+    r->bg_running = true;
+    r->bg = std::thread([r]() { r->bg_rc = inflate_window(r, r->nbuf, &r->bg_bytes, r->bg_err, sizeof r->bg_err); });
+}
+
+// Makes the next window current, keeping the unread tail of the old one in front of it, and starts inflating the
+// window after it.  Returns 1 if bytes were added, 0 at end of file, < 0 on error.
+int refill(tdt_bam_reader *r) {
+    if (r->eof) return 0;
+    if (!r->bg_running) start_prefetch(r);
+    r->bg.join();
+    r->bg_running = false;
+    if (r->bg_rc < 0) return fail(r->bg_rc, "%s", r->bg_err);
+    if (r->bg_rc == 0) {
+        r->eof = true;
+        return 0;
+    }
+    const size_t left = r->bend - r->bpos;
+    if (left > kPad) {  // a record longer than the headroom: make room the slow way
+        std::vector<uint8_t> joined(left + r->bg_bytes + kPad);
+        memcpy(joined.data() + kPad, r->buf.data() + r->bpos, left);
+        memcpy(joined.data() + kPad + left, r->nbuf.data() + kPad, r->bg_bytes);
+        r->nbuf.swap(joined);
+        r->buf.swap(r->nbuf);
+        r->bpos = kPad;
+        r->bend = kPad + left + r->bg_bytes;
+    } else {
+        if (left) memcpy(r->nbuf.data() + kPad - left, r->buf.data() + r->bpos, left);
+        r->buf.swap(r->nbuf);
+        r->bpos = kPad - left;
+        r->bend = kPad + r->bg_bytes;
+    }
+    start_prefetch(r);  // into the window the caller has finished with
+    return 1;
+}
+
+// at least n unread bytes in the window (used for the header only)
 int ensure(tdt_bam_reader *r, size_t n) {
     while (r->bend - r->bpos < n) {
         int rc = refill(r);
@@ -250,6 +298,7 @@ int tdt_bam_open(const char *path, int threads, tdt_bam_reader **out) {
 
 void tdt_bam_close(tdt_bam_reader *r) {
     if (!r) return;
+    if (r->bg_running) r->bg.join();
     if (r->map) munmap(const_cast<uint8_t *>(r->map), r->map_len);
     if (r->fd >= 0) close(r->fd);
     delete r;

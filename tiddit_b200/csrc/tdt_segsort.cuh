@@ -230,11 +230,17 @@ __device__ __forceinline__ uint32_t ss_match(uint32_t *mm, uint32_t d, bool vali
 #endif
 }
 
-// info word per element: [7:0] digit, [12:8] rank among the chunk's lanes with the same digit,
-// [18:13] size of that group, [31] valid
-__device__ __forceinline__ uint32_t ss_info(uint32_t d, uint32_t peers) {
-    return d | ((uint32_t)__popc(peers & lanemask_lt()) << 8) | ((uint32_t)__popc(peers) << 13) | 0x80000000u;
-}
+// info word per element: the lanes of the warp's 32-element chunk that hold the same digit (0 = no element);
+// rank among them = popc(info & lanes below), group size = popc(info), group leader = lowest set lane.
+// TDT_SS_ATOMIC_RANK (default): the leader adds the group to the warp-private counter with ONE shared-memory
+// atomic in each phase and, when scattering, hands the old value to its group by shuffle -- instead of a read
+// by every lane plus a write by the leader (two bank-conflicted shared accesses per element and phase).
+// Measured on B200 (r01, posA sort of the 30X set): 0.601 ms with, 0.606 ms without -- within noise; the same for
+// the 64-bit (key, value) staging below (TDT_SS_KV64).  Fewer shared-memory wavefronts did not move the pass:
+// with 24 resident warps per SM it waits on latencies (scoreboard and barrier stalls), not on a saturated pipe.
+#ifndef TDT_SS_ATOMIC_RANK
+#define TDT_SS_ATOMIC_RANK 1
+#endif
 
 // count phase: warp-private digit histograms of the warp's own run of the tile; info[] keeps the match result
 template <int CHUNKS, typename DigitFn>
@@ -250,30 +256,45 @@ __device__ __forceinline__ void ss_count(int count, int epw, uint32_t *wh, uint3
             const uint32_t d = valid ? digit(e, c) : 0u;
             const uint32_t peers = ss_match(mm, d, valid, bits);
             if (valid) {
-                info[c] = ss_info(d, peers);
-                if ((peers & lanemask_lt()) == 0u) wh[d] += __popc(peers);
+                info[c] = peers;
+                if ((peers & lanemask_lt()) == 0u) {
+#if TDT_SS_ATOMIC_RANK
+                    atomicAdd(&wh[d], (uint32_t)__popc(peers));
+#else
+                    wh[d] += __popc(peers);
+#endif
+                }
             }
             __syncwarp();
         }
     }
 }
 
-// scatter phase: stable position of every element; wh[d] holds the running base of (this warp, digit)
-template <int CHUNKS, typename EmitFn>
-__device__ __forceinline__ void ss_scatter(int epw, uint32_t *wh, const uint32_t (&info)[CHUNKS], EmitFn emit) {
+// scatter phase: stable position of every element; wh[d] holds the running base of (this warp, digit).
+// digit(e, c) must return what it returned in the count phase.
+template <int CHUNKS, typename DigitFn, typename EmitFn>
+__device__ __forceinline__ void ss_scatter(int epw, uint32_t *wh, const uint32_t (&info)[CHUNKS], DigitFn digit,
+                                           EmitFn emit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < CHUNKS; c++) {
         if (c * 32 < epw) {
-            const uint32_t w = info[c];
-            const bool valid = w >> 31;
-            const uint32_t d = w & 255u, rank = (w >> 8) & 31u, group = (w >> 13) & 63u;
+            const uint32_t peers = info[c];
+            const bool valid = peers != 0u;
+            const int e = warp * epw + c * 32 + lane;
+            const uint32_t d = valid ? digit(e, c) : 0u;
+            const uint32_t rank = __popc(peers & lanemask_lt()), group = __popc(peers);
             uint32_t base = 0;
+#if TDT_SS_ATOMIC_RANK
+            if (valid && rank == 0u) base = atomicAdd(&wh[d], group);
+            base = __shfl_sync(0xffffffffu, base, valid ? (__ffs(peers) - 1) : lane);
+#else
             if (valid) base = wh[d];
             __syncwarp();
             if (valid && rank == 0u) wh[d] = base + group;
             __syncwarp();
-            if (valid) emit(warp * epw + c * 32 + lane, c, base + rank);
+#endif
+            if (valid) emit(e, c, base + rank);
         }
     }
 }
@@ -461,7 +482,10 @@ __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
                 uint32_t *Ka = K[cur ^ 1];
                 int32_t *Va = V[cur ^ 1];
                 uint16_t *La = Lid[cur ^ 1];
-                ss_scatter<SS_LCHUNKS>(epw, wh[warp], info, [&](int e, int, uint32_t pos) {
+                ss_scatter<SS_LCHUNKS>(epw, wh[warp], info, [&](int e, int) -> uint32_t {
+                    const unsigned long long comp = ((unsigned long long)Lc[e] << kb) | (unsigned long long)Kc[e];
+                    return (uint32_t)(comp >> sh) & 255u;
+                }, [&](int e, int, uint32_t pos) {
                     Ka[pos] = Kc[e];
                     Va[pos] = Vc[e];
                     La[pos] = Lc[e];
@@ -549,6 +573,9 @@ __device__ __forceinline__ void st_volatile_u32(uint32_t *p, uint32_t v) {
     asm volatile("st.volatile.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+#ifndef TDT_SS_KV64
+#define TDT_SS_KV64 1
+#endif
 constexpr size_t SS_PASS_SMEM = (size_t)SS_TILE * 4 * 2 + (size_t)SS_WARPS * 256 * 4 * (1 + SS_MM) + 256 * 4 + 256 * 8 + 64;
 
 // One pass over one tile.  Tiles are taken in blockIdx order (the chained scan waits only on tiles with a smaller
@@ -564,8 +591,12 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
                                                                   int32_t *dst_v) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     unsigned char *p = ss_smem;
+#if TDT_SS_KV64
+    uint2 *KV = (uint2 *)p; p += SS_TILE * 8;   // (key, value) staged as one 64-bit word: one scattered store, not two
+#else
     uint32_t *K2 = (uint32_t *)p; p += SS_TILE * 4;
     int32_t *V2 = (int32_t *)p; p += SS_TILE * 4;
+#endif
     uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
     uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_MM * SS_WARPS * 256 * 4;
     uint32_t *bin = (uint32_t *)p; p += 256 * 4;
@@ -622,10 +653,15 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
         gh = a.L.ghist[((size_t)seg * SS_MAX_PASSES + pass) * 256 + threadIdx.x];
     }
     __syncthreads();  // wh holds every warp's digit bases
-    ss_scatter<SS_CHUNKS>(epw, wh[warp], info, [&](int, int c, uint32_t pos) {
-        K2[pos] = key[c];
-        V2[pos] = val[c];
-    });
+    ss_scatter<SS_CHUNKS>(epw, wh[warp], info, [&](int, int c) -> uint32_t { return ss_digit(key[c], pass, bits); },
+                          [&](int, int c, uint32_t pos) {
+#if TDT_SS_KV64
+                              KV[pos] = make_uint2(key[c], (uint32_t)val[c]);
+#else
+                              K2[pos] = key[c];
+                              V2[pos] = val[c];
+#endif
+                          });
     {
         uint32_t before = 0;
         if (lt != 0 && live) {
@@ -655,10 +691,17 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
     }
     __syncthreads();
     for (int i = threadIdx.x; i < cnt; i += SS_THREADS) {
+#if TDT_SS_KV64
+        const uint2 kv = KV[i];
+        const uint32_t k = kv.x;
+        const int32_t v = (int32_t)kv.y;
+#else
         const uint32_t k = K2[i];
+        const int32_t v = V2[i];
+#endif
         const int64_t g = gbase[ss_digit(k, pass, bits)] + i;
         dst_k[g] = k;
-        dst_v[g] = V2[i];
+        dst_v[g] = v;
     }
     __syncthreads();   // K2 / V2 / gbase are rewritten by the next tile
     }
