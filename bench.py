@@ -469,7 +469,7 @@ def medians_leg(torch, args, hbm_peak, flush):
            "roofline": {"bound": "hbm", "achieved": 9.0 * n / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                         "frac": 9.0 * n / ms / 1e6 / hbm_peak,
                         "algorithmic_bytes": "9 B/bin (float64 coverage + int8 GC), read once; the radix select "
-                                             "streams them 9 times (8 digit passes + the upper-median pass)"}}
+                                             "streams them 6 times (digit passes of 11/11/11/11/11/9 bits; the upper median comes out of the last one)"}}
     if not args.no_cpu:
         R = _ref_modules()
         lo, hi = int(off[20]), int(off[22])                                  # chr21 + chr22: 1.95 M bins

@@ -21,7 +21,8 @@ def test_determine_ploidy_golden(tmp_path):
         assert open(prefix + ".ploidies.tab").read() == c["tab"]          # byte-identical
 
 
-@pytest.mark.parametrize("n_contigs,max_bins,seed", [(1, 1, 0), (3, 10, 1), (24, 300_000, 2), (2000, 3000, 3)])
+@pytest.mark.parametrize("n_contigs,max_bins,seed", [(1, 1, 0), (3, 10, 1), (24, 300_000, 2), (2000, 3000, 3),
+                                                      (500, 5000, 4), (40, 200_000, 7)])
 def test_medians_random_vs_oracle(n_contigs, max_bins, seed, oracle):
     from tiddit_b200 import device_ops
     rng = np.random.default_rng(seed)
@@ -42,6 +43,25 @@ def test_medians_random_vs_oracle(n_contigs, max_bins, seed, oracle):
     want_m, want_c = oracle.coverage_medians(cov, gc, off)
     assert np.array_equal(got_c, want_c)
     assert np.array_equal(got_m.view(np.uint64), want_m.view(np.uint64))   # bit-exact, nan included
+
+
+def test_medians_value_after_the_lower_median_known_answers(oracle):
+    """Even counts: the upper median may sit in the same last digit, in a later digit of the last histogram, or in a far
+    bucket (other exponent) -- the three places the kernels look for it -- and differs between a contig and the genome."""
+    from tiddit_b200 import device_ops
+    big, tiny = 1e300, 5e-324
+    contigs = [[1.0, 1.0, big, big], [1.0, np.nextafter(1.0, 2.0)], [2.0, 2.0, 2.0, 2.5], [tiny, 3.0], [7.0],
+               [0.0, 0.0], [4.0, 4.0 + 2.0 ** -44, 0.0, 9.0]]
+    cov = np.array([v for c in contigs for v in c])
+    off = np.concatenate([[0], np.cumsum([len(c) for c in contigs])]).astype(np.int64)
+    gc = np.full(len(cov), 40, dtype=np.int8)
+    got_m, got_c = device_ops.coverage_medians(cov, gc, off)
+    want = [np.median([v for v in c if v > 0]) if any(v > 0 for v in c) else np.nan for c in contigs]
+    want.append(np.median(cov[cov > 0]))
+    assert np.array_equal(got_m.view(np.uint64), np.array(want).view(np.uint64))
+    assert got_c.tolist() == [sum(v > 0 for v in c) for c in contigs] + [int((cov > 0).sum())]
+    want_m, _ = oracle.coverage_medians(cov, gc, off)
+    assert np.array_equal(got_m.view(np.uint64), want_m.view(np.uint64))
 
 
 def test_medians_genome_scale_property(oracle):
