@@ -21,8 +21,6 @@ timeout 600 ncu --set full --clock-control none --import-source on -k regex:'win
     -s 4 -c 1 -o gpurun_out/src_wr_${R} -f python tools/profile_target.py > gpurun_out/src_wr.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:'segsort_pass' \
     -s 17 -c 1 -o gpurun_out/src_pass_${R} -f python tools/profile_target.py > gpurun_out/src_pass.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:'coverage_kernel' \
-    -s 1 -c 1 -o gpurun_out/src_cov_${R} -f python tools/profile_target.py > gpurun_out/src_cov.log 2>&1
 echo "source captures done"; ls -la gpurun_out/*.ncu-rep
 timeout 300 python tools/kernel_times.py > gpurun_out/kernel_times_${R}.txt 2>&1
 echo "kernel times rc=$?"
