@@ -66,10 +66,11 @@ def run_sv(argv):
         print("tiddit_b200 replaces the clustering / coverage / GC stages only; --sv also needs the reference "
               "package (pysam, bwa) for signal extraction, assembly and variant calling: %s" % exc)
         return 2
-    from . import DBSCAN, tiddit_cluster, tiddit_coverage, tiddit_coverage_analysis, tiddit_gc
+    from . import DBSCAN, tiddit_cluster, tiddit_coverage, tiddit_coverage_analysis, tiddit_gc, tiddit_signal
     import tiddit
     for name, mod in (("DBSCAN", DBSCAN), ("tiddit_cluster", tiddit_cluster), ("tiddit_coverage", tiddit_coverage),
-                      ("tiddit_gc", tiddit_gc), ("tiddit_coverage_analysis", tiddit_coverage_analysis)):
+                      ("tiddit_gc", tiddit_gc), ("tiddit_coverage_analysis", tiddit_coverage_analysis),
+                      ("tiddit_signal", tiddit_signal)):
         sys.modules["tiddit." + name] = mod
         setattr(tiddit, name, mod)
         if hasattr(ref_main, name):
