@@ -753,14 +753,37 @@ int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *key
                                       (int)SS_PASS_SMEM));
         configured = true;
     }
+    // The tiny / small-segment kernels and the large-segment chain (hist, scan, passes) touch disjoint segments, and
+    // neither fills the machine on its own (both wait on latencies): they run as two branches -- a side stream forked
+    // here and joined after the last pass; inside a CUDA-graph capture the fork / join become parallel graph branches.
+#ifndef TDT_SS_FORK
+#define TDT_SS_FORK 1
+#endif
+    cudaStream_t side = st;
+#if TDT_SS_FORK
+    static thread_local cudaStream_t side_streams[16] = {};
+    static thread_local cudaEvent_t fork_ev[16] = {}, join_ev[16] = {};
+    int dev_id = 0;
+    TDT_CUDA(cudaGetDevice(&dev_id));
+    if (dev_id >= 0 && dev_id < 16) {
+        if (!side_streams[dev_id]) {
+            TDT_CUDA(cudaStreamCreateWithFlags(&side_streams[dev_id], cudaStreamNonBlocking));
+            TDT_CUDA(cudaEventCreateWithFlags(&fork_ev[dev_id], cudaEventDisableTiming));
+            TDT_CUDA(cudaEventCreateWithFlags(&join_ev[dev_id], cudaEventDisableTiming));
+        }
+        side = side_streams[dev_id];
+        TDT_CUDA(cudaEventRecord(fork_ev[dev_id], st));
+        TDT_CUDA(cudaStreamWaitEvent(side, fork_ev[dev_id], 0));
+    }
+#endif
     if (segid) {
         int64_t blocks = (n_max + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        TDT_LAUNCH(segsort_tiny_kernel, (unsigned)blocks, 256, 0, st, a);
+        TDT_LAUNCH(segsort_tiny_kernel, (unsigned)blocks, 256, 0, side, a);
     }
     int64_t nwin = (n_max + SS_WINDOW - 1) / SS_WINDOW;
     if (nwin > 148 * 4) nwin = 148 * 4;
-    TDT_LAUNCH(segsort_local_kernel, (unsigned)nwin, SS_LTHREADS, SS_LOCAL_SMEM, st, a);
+    TDT_LAUNCH(segsort_local_kernel, (unsigned)nwin, SS_LTHREADS, SS_LOCAL_SMEM, side, a);
     static thread_local int pass_cap = 0, hist_cap = 0;   // resident CTAs of the two tile kernels on this device
     if (!pass_cap) {
         int dev = 0, sms = 0, per_sm = 0;
@@ -785,6 +808,12 @@ int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *key
         int32_t *dv = to_out ? vals_out : vals_tmp;
         TDT_LAUNCH(segsort_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, st, a, pass, sk, sv, dk, dv);
     }
+#if TDT_SS_FORK
+    if (side != st) {
+        TDT_CUDA(cudaEventRecord(join_ev[dev_id], side));
+        TDT_CUDA(cudaStreamWaitEvent(st, join_ev[dev_id], 0));
+    }
+#endif
     return TDT_OK;
 }
 #endif  // TDT_SEGSORT_IMPL
