@@ -756,6 +756,7 @@ int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *key
     // The tiny / small-segment kernels and the large-segment chain (hist, scan, passes) touch disjoint segments, and
     // neither fills the machine on its own (both wait on latencies): they run as two branches -- a side stream forked
     // here and joined after the last pass; inside a CUDA-graph capture the fork / join become parallel graph branches.
+    // (A third branch for the tiny-segment kernel measured the same as two: 1.277 vs 1.268 ms for the 30X step.)
 #ifndef TDT_SS_FORK
 #define TDT_SS_FORK 1
 #endif
