@@ -16,6 +16,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
+#include <exception>
 #include <string>
 #include <thread>
 #include <vector>
@@ -160,7 +161,14 @@ int inflate_window(tdt_bam_reader *r, std::vector<uint8_t> &dst, size_t *nbytes,
 
 void start_prefetch(tdt_bam_reader *r) {
     r->bg_running = true;
-    r->bg = std::thread([r]() { r->bg_rc = inflate_window(r, r->nbuf, &r->bg_bytes, r->bg_err, sizeof r->bg_err); });
+    r->bg = std::thread([r]() {
+        try {
+            r->bg_rc = inflate_window(r, r->nbuf, &r->bg_bytes, r->bg_err, sizeof r->bg_err);
+        } catch (const std::exception &e) {   // bad_alloc, thread creation: no exception may leave the thread
+            snprintf(r->bg_err, sizeof r->bg_err, "%s: %s", r->path.c_str(), e.what());
+            r->bg_rc = TDT_BAM_E_IO;
+        }
+    });
 }
 
 // Makes the next window current, keeping the unread tail of the old one in front of it, and starts inflating the
@@ -264,9 +272,19 @@ extern "C" {
 
 const char *tdt_bam_last_error(void) { return g_err; }
 
+static int open_impl(const char *path, int threads, tdt_bam_reader **out);
+
 int tdt_bam_open(const char *path, int threads, tdt_bam_reader **out) {
     if (!path || !out) return fail(TDT_BAM_E_ARG, "tdt_bam_open: null argument");
     *out = nullptr;
+    try {   // no exception crosses the C boundary
+        return open_impl(path, threads, out);
+    } catch (const std::exception &e) {
+        return fail(TDT_BAM_E_IO, "%s: %s", path, e.what());
+    }
+}
+
+static int open_impl(const char *path, int threads, tdt_bam_reader **out) {
     int fd = open(path, O_RDONLY);
     if (fd < 0) return fail(TDT_BAM_E_IO, "cannot open %s", path);
     struct stat st;
@@ -316,10 +334,25 @@ int32_t tdt_bam_ref_len(const tdt_bam_reader *r, int32_t i) {
     return (i >= 0 && (size_t)i < r->ref_lens.size()) ? r->ref_lens[i] : -1;
 }
 
+static int64_t read_columns_impl(tdt_bam_reader *r, int64_t max_reads, int32_t *ref_id, int32_t *pos, int32_t *end,
+                                 int32_t *mate_ref, int32_t *mate_pos, int32_t *tlen, uint16_t *flag, uint8_t *mapq,
+                                 uint32_t *cig_first, uint32_t *cig_last, uint8_t *has_sa, int64_t *rec_off);
+
 int64_t tdt_bam_read_columns(tdt_bam_reader *r, int64_t max_reads, int32_t *ref_id, int32_t *pos, int32_t *end,
                              int32_t *mate_ref, int32_t *mate_pos, int32_t *tlen, uint16_t *flag, uint8_t *mapq,
                              uint32_t *cig_first, uint32_t *cig_last, uint8_t *has_sa, int64_t *rec_off) {
     if (!r || max_reads < 0) return fail(TDT_BAM_E_ARG, "tdt_bam_read_columns: bad argument");
+    try {
+        return read_columns_impl(r, max_reads, ref_id, pos, end, mate_ref, mate_pos, tlen, flag, mapq, cig_first, cig_last,
+                                 has_sa, rec_off);
+    } catch (const std::exception &e) {
+        return fail(TDT_BAM_E_IO, "%s: %s", r->path.c_str(), e.what());
+    }
+}
+
+static int64_t read_columns_impl(tdt_bam_reader *r, int64_t max_reads, int32_t *ref_id, int32_t *pos, int32_t *end,
+                                 int32_t *mate_ref, int32_t *mate_pos, int32_t *tlen, uint16_t *flag, uint8_t *mapq,
+                                 uint32_t *cig_first, uint32_t *cig_last, uint8_t *has_sa, int64_t *rec_off) {
     int64_t n = 0;
     while (n == 0 && max_reads > 0) {
         // a complete record at the read position?  otherwise bring in the next window (this is the only place
