@@ -308,6 +308,60 @@ def coverage_leg(torch, args, hbm_peak, flush):
     return out
 
 
+def gc_leg(torch, args, hbm_peak, flush):
+    """GC bins (tiddit_gc.pyx:6-33) of a chr1-sized contig resident in HBM, bin 50 like `--sv`: bases/s and bins/s."""
+    from tiddit_b200 import device_ops, synth
+    n_bases = args.gc_bases
+    seq_h = synth.fasta_sequence(n_bases)
+    seq, ln = device_ops.padded_sequence_device(seq_h)
+    z = 50
+    n_bins = (n_bases + z - 1) // z
+    out_bins = torch.zeros(n_bins, dtype=torch.int8, device="cuda")
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    times = []
+    for it in range(args.warmup + args.steps):
+        flush()
+        ev[0].record()
+        device_ops.gc_bins_device(seq, ln, z, 0.5, out=out_bins)
+        ev[1].record()
+        torch.cuda.synchronize()
+        if it >= args.warmup:
+            times.append(ev[0].elapsed_time(ev[1]))
+    ms = float(np.mean(times))
+    alg = float(n_bases + n_bins)
+    out = {"bases": n_bases, "bins": n_bins, "bin_size": z, "ms_per_step": ms, "bases_per_sec": n_bases / ms * 1e3,
+           "bins_per_sec": n_bins / ms * 1e3,
+           "roofline": {"bound": "hbm", "achieved": alg / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": alg / ms / 1e6 / hbm_peak, "kernel": "gc_small_kernel",
+                        "traffic_note": ncu_traffic("gc_small_kernel", note_only=True),
+                        "algorithmic_bytes": "1 B/base + 1 B/bin"}}
+    from oracle import oracle
+    k = min(n_bases, 5_000_000) // z * z
+    out["verified"] = bool(np.array_equal(out_bins[:k // z].cpu().numpy(), oracle.gc_bins(seq_h[:k], z, 0.5)))
+    if not args.no_cpu:
+        R = _ref_modules()
+        if R is not None and getattr(R, "tiddit_gc", None) is not None:
+            import tempfile
+            kk = min(k, 3_000_000)
+            tmp = tempfile.mkdtemp(prefix="tdt_bench_gc_")
+            fa = os.path.join(tmp, "ref.fa")
+            with open(fa, "w") as f:
+                f.write(">c\n")
+                text = bytes(seq_h[:kk]).decode("ascii")
+                f.write("\n".join(text[i:i + 60] for i in range(0, kk, 60)) + "\n")
+            R.tiddit_gc.binned_gc(fa, "c", z, 0.5)        # warms the stand-in FastaFile's cache: parsing is not timed
+            t0 = time.perf_counter()
+            R.tiddit_gc.binned_gc(fa, "c", z, 0.5)
+            dt = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": kk / dt, "unit": "bases/s", "cores": 1, "kind": "reference",
+                                   "sample": "binned_gc on the first %d bases (FASTA already in memory), %.1f s" % (kk, dt)}
+            import shutil
+            shutil.rmtree(tmp, ignore_errors=True)
+    del seq, out_bins
+    torch.cuda.empty_cache()
+    return out
+
+
 def bam_leg(torch, args):
     """`--cov` from a BAM FILE: libtdt_bam.so (BGZF inflated on the host cores, records as columns)
     + the coverage kernel batch by batch, host->device copies and the final device->host read of the bins included.
@@ -512,6 +566,7 @@ def main():
     ap.add_argument("--signals", type=int, default=0, help="override the workload's signal count")
     ap.add_argument("--cov-reads", type=int, default=617_653_966, help="reads for the coverage leg (30X = 617653966)")
     ap.add_argument("--no-coverage", action="store_true")
+    ap.add_argument("--gc-bases", type=int, default=248_956_422, help="bases of the GC leg (chr1 of GRCh38)")
     ap.add_argument("--bam-reads", type=int, default=2_000_000, help="reads of the synthetic BAM of the bam_coverage leg")
     ap.add_argument("--no-graph", action="store_true", help="issue the step's kernels eagerly instead of replaying a CUDA graph")
     ap.add_argument("--chunks", type=int, default=6, help="pair chunks of the pipelined host path (e2e, N=1)")
@@ -727,6 +782,7 @@ def main():
             _lib.release_workspaces()
             torch.cuda.empty_cache()
             line["ploidy_medians"] = medians_leg(torch, args, hbm_peak, flush)
+            line["gc"] = gc_leg(torch, args, hbm_peak, flush)
             line["bam_coverage"] = bam_leg(torch, args)
     if rank == 0:
         print(json.dumps(line))

@@ -106,3 +106,61 @@ def test_fasta_reader(tmp_path):
     fa = fasta.NumpyFasta(str(p))
     assert fa.references == ["c1", "c2"]
     assert fa.get_reference_length("c1") == 8 and fa.fetch("c1", 2, 6) == "GTNN" and fa.fetch("c2") == "TTA"
+
+
+def test_tab_column_reader_equals_line_reader(tmp_path):
+    """PackedSignals.from_tab: the pandas column reader and the line-by-line restatement of tiddit_cluster.pyx:47-137
+    give the same arrays and tables on the golden scenarios; irregular files (ragged split lines, blank-padded fields,
+    non-integer coordinates) are detected and read line by line."""
+    import shutil
+    from tiddit_b200 import signals
+    from tiddit_b200.signals import PackedSignals
+
+    def same(a, b):
+        assert a.pairs == b.pairs and a.chrA_present == b.chrA_present
+        assert (a.names, a.samples, a.ori_table) == (b.names, b.samples, b.ori_table)
+        for f in PackedSignals.FIELDS:
+            assert np.array_equal(getattr(a, f), getattr(b, f)), f
+
+    used = []
+    orig = signals._part_from_columns
+
+    def spy(path, *a, **k):
+        try:
+            part = orig(path, *a, **k)
+            used.append((os.path.basename(path), "columns"))
+            return part
+        except signals._IrregularTab:
+            used.append((os.path.basename(path), "lines"))
+            raise
+
+    signals._part_from_columns = spy
+    try:
+        for case in range(3):
+            exp = load_json("cluster_case%d_expected.json" % case)
+            a = exp["args"]
+            for is_mp in (False, True):
+                args = (os.path.join(GOLDEN, "cluster_case%d" % case), a["chromosomes"], a["contig_length"], a["samples"],
+                        is_mp, a["min_contig"], a["skip_assembly"])
+                same(PackedSignals.from_tab(*args, fast=True), PackedSignals.from_tab(*args, fast=False))
+        assert used and all(how == "columns" for _, how in used)
+        # irregular variants of case 0: each must fall back for that file only and still agree
+        exp = load_json("cluster_case0_expected.json")
+        a = exp["args"]
+        src = os.path.join(GOLDEN, "cluster_case0_tiddit")
+        sample = a["samples"][0]
+        edits = {"splits": lambda ls: ls[:3] + [ls[3].rstrip("\n") + "\t" + "\t".join(ls[1].rstrip("\n").split("\t")[3:]) + "\n"] + ls[4:],
+                 "discordants": lambda ls: [ls[0].rstrip("\n") + "  \n"] + ls[1:]}
+        for stem, edit in edits.items():
+            dst = str(tmp_path / ("irr_" + stem))
+            shutil.copytree(src, dst + "_tiddit")
+            path = os.path.join(dst + "_tiddit", "%s_%s.tab" % (stem, sample))
+            lines = open(path).readlines()
+            open(path, "w").writelines(edit(lines))
+            del used[:]
+            args = (dst, a["chromosomes"], a["contig_length"], a["samples"], a["is_mp"], a["min_contig"], a["skip_assembly"])
+            same(PackedSignals.from_tab(*args, fast=True), PackedSignals.from_tab(*args, fast=False))
+            if stem == "discordants":      # (the C parser takes longer split lines as they are: extra fields are unused)
+                assert ("%s_%s.tab" % (stem, sample), "lines") in used
+    finally:
+        signals._part_from_columns = orig
