@@ -225,7 +225,7 @@ def ncu_traffic(kernel, note_only=False):
     if rec is None:
         return None
     if note_only:
-        return "%s: %.1f MB per launch in the profiled (61.8M-read) shape" % (os.path.basename(files[-1]),
+        return "%s: %.1f MB per launch in the shape tools/profile_target.py runs" % (os.path.basename(files[-1]),
                                                                              rec["first_launch_bytes"] / 1e6)
     return rec["first_launch_bytes"]
 
