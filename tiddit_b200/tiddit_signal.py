@@ -216,15 +216,73 @@ def split_lines(signals):
                 yield "{}\t{}\t{}\t{}\n".format(name, chrA, chrB, "\t".join(map(str, fields)))
 
 
+def _record_parts(signals, sample_k, contig_length, is_mp, min_contig):
+    """The discordant and split records as the column sets PackedSignals assembles -- what reading the two tab files
+    back (tiddit_cluster.pyx:47-107) yields, without formatting and re-parsing the text."""
+    from .signals import KIND_D, KIND_S, find_discordant_pos
+
+    def new_part(kind):
+        return dict(kind=kind, sample=sample_k, name=[], chrA=[], chrB=[], posA=[], posB=[], oriA=[], oriB=[], span=[])
+
+    disc, split = new_part(KIND_D), new_part(KIND_S)
+    data = _merge(signals.chromosomes, signals.header, signals.data, extend=False)
+    for chrA, row in data.items():
+        for chrB, fragments in row.items():
+            if contig_length[chrA] < min_contig or contig_length[chrB] < min_contig:
+                continue
+            la, lb = contig_length[chrA], contig_length[chrB]
+            for name, recs in fragments.items():
+                if len(recs) < 2:
+                    continue
+                first, second = recs[0], recs[1]
+                if chrA != chrB and first[-1] != chrA:
+                    first, second = second, first
+                # the tab line's fields 3..8: startA, endA, reverseA, startB, endB, reverseB
+                f = [name, chrA, chrB, first[0], first[1], str(first[2]), second[0], second[1], str(second[2])]
+                posA, posB = find_discordant_pos(f, is_mp)
+                if posA > la:                      # tiddit_cluster.pyx:67-70, the nested test overwrites posA
+                    posA = la
+                    if posB > lb:
+                        posA = lb
+                disc["name"].append(name)
+                disc["chrA"].append(chrA)
+                disc["chrB"].append(chrB)
+                disc["posA"].append(posA)
+                disc["posB"].append(posB)
+                disc["oriA"].append(f[5])
+                disc["oriB"].append(f[8])
+                disc["span"].append((f[3], f[4], f[6], f[7]))
+    splits = _merge(signals.chromosomes, signals.header, signals.splits, extend=True)
+    for chrA, row in splits.items():
+        for chrB, fragments in row.items():
+            if contig_length[chrA] < min_contig or contig_length[chrB] < min_contig:
+                continue
+            la, lb = contig_length[chrA], contig_length[chrB]
+            for name, f in fragments.items():      # f: split_pos, reverse, SA_split_pos, SA reverse, startA, endA, startB, endB, ...
+                if None in f[:8]:
+                    raise ValueError("invalid literal for int() with base 10: 'None'")   # what reading the file back does
+                split["name"].append(name)
+                split["chrA"].append(chrA)
+                split["chrB"].append(chrB)
+                split["posA"].append(min(f[0], la))
+                split["posB"].append(min(f[2], lb))
+                split["oriA"].append(str(f[1]))
+                split["oriB"].append(str(f[3]))
+                split["span"].append((f[4], f[5], f[6], f[7]))
+    return disc, split
+
+
 def packed_signals(signals, sample_id, is_mp, min_contig, contig_lines=None):
     """Signals -> signals.PackedSignals, the arrays tiddit_cluster.cluster_packed takes: the records
-    `main` writes to the tab files, handed over in memory.  contig_lines: the lines of contigs_<sample>.tab when the
-    assembly stage ran, None for --skip_assembly."""
-    from .signals import PackedSignals
+    `main` writes to the tab files, handed over in memory without the text round trip.  contig_lines: the lines of
+    contigs_<sample>.tab when the assembly stage ran, None for --skip_assembly."""
+    from .signals import KIND_A, PackedSignals, _part_from_lines
     contig_length = {sq["SN"]: sq["LN"] for sq in signals.header["SQ"]}
     chromosomes = [sq["SN"] for sq in signals.header["SQ"]]     # tiddit/__main__.py:119-123: every @SQ, header order
-    return PackedSignals.from_lines([(discordant_lines(signals), split_lines(signals), contig_lines)], chromosomes,
-                                    contig_length, [sample_id], is_mp, min_contig)
+    parts = list(_record_parts(signals, 0, contig_length, is_mp, min_contig))
+    if contig_lines is not None:
+        parts.append(_part_from_lines(contig_lines, 0, KIND_A, contig_length, is_mp, min_contig))
+    return PackedSignals._assemble(parts, chromosomes, [sample_id])
 
 
 def main(bam_file_name, ref, prefix, min_q, max_ins, sample_id, threads, min_contig, skip_index, min_anchor_len,
