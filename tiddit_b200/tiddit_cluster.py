@@ -60,6 +60,19 @@ def candidates_from_table(packed, table):
         candidates.setdefault(a, {})[b] = {}
     if len(table) == 0:
         return candidates
+    # Millions of small containers are created below and none of them is garbage: with the cyclic collector on,
+    # its full passes over the growing heap took two thirds of the time (4.8 of 7.7 s for 61 k candidates).
+    import gc
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        return _fill_candidates(candidates, packed, table)
+    finally:
+        if was_enabled:
+            gc.enable()
+
+
+def _fill_candidates(candidates, packed, table):
     mem = table.member_idx
     # per-member columns as Python lists once; the loop below only slices them
     kind = (packed.flags[mem] & 3).tolist()
