@@ -140,6 +140,18 @@ def test_tumor60x_params(oracle):
     assert_same(device_ops.cluster_labels(a, b, off, 1000, 5, L), oracle.cluster_segments(a, b, off, 1000, 5), "tumor")
 
 
+def test_tumor60x_full_size(oracle):
+    """BASELINE config 5 at FULL size: 50 M signals, eps=1000, m=5 (70 % in dense clusters, 100 hotspots of
+    1e4-1e5 signals) against the C oracle, bit for bit, plus the idempotence property."""
+    from tiddit_b200 import device_ops, synth, _lib
+    a, b, off, L = synth.tumor60x_signals(50_000_000)
+    got = device_ops.cluster_labels(a, b, off, 1000, 5, L)
+    want = oracle.cluster_segments(a, b, off, 1000, 5)
+    assert_same(got, want, "tumor60x 50M")
+    assert 0.6 < (got >= 0).mean() < 0.9
+    _lib.release_workspaces()
+
+
 def test_errors():
     from tiddit_b200 import DBSCAN, device_ops, _lib
     d = data3([1, 2, 3], [1, 2, 3])

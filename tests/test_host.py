@@ -56,7 +56,7 @@ def test_create_coverage_shapes():
     assert list(data) == ["c1", "c2"] and len(data["c1"]) == 3 and len(data["c2"]) == 2
     assert ebs == {"c1": 234, "c2": 500} and data["c1"].dtype == np.float64
     one, e1 = cov.create_coverage(header, 500, "c2")
-    assert isinstance(one, np.ndarray) and len(one) == 2 and e1 == 500
+    assert np.asarray(one).dtype == np.float64 and one.shape == (2,) and len(one) == 2 and e1 == 500
     assert cov.create_coverage(header, 500, "nope") == ({}, {})
 
 

@@ -50,7 +50,12 @@ def run_cov(argv):
     if not os.path.isfile(args.bam):
         print("error,  could not find the bam file")
         return 1
-    from . import tiddit_coverage
+    from . import bamio, tiddit_coverage
+    try:
+        bamio.require_bam(args.bam, args.ref)
+    except (NotImplementedError, ValueError) as exc:
+        print("error, %s" % exc)
+        return 1
     coverage_data, bam_header = coverage_from_bam(args.bam, args.z, args.q)
     if args.w:
         tiddit_coverage.print_coverage(coverage_data, bam_header, args.z, "wig", args.o + ".wig")
@@ -59,22 +64,38 @@ def run_cov(argv):
     return 0
 
 
+SWAPPED_MODULES = ("DBSCAN", "tiddit_cluster", "tiddit_coverage", "tiddit_gc", "tiddit_coverage_analysis",
+                   "tiddit_signal")
+
+
+def install_gpu_modules():
+    """Put this package's modules in place of the reference's BEFORE anything of the reference pipeline is imported:
+    `import tiddit.DBSCAN` / `from tiddit import tiddit_signal` inside tiddit_contig_analysis, tiddit_variant and
+    tiddit/__main__ then bind to the GPU modules at their own import time (patching attributes afterwards would leave
+    the bindings those modules made at import pointing at the originals).  -> the `tiddit` package."""
+    import importlib
+    tiddit = importlib.import_module("tiddit")        # the package itself: tiddit/__init__.py imports nothing
+    pkg = importlib.import_module(__package__)
+    for name in SWAPPED_MODULES:
+        mod = importlib.import_module("." + name, __package__)
+        sys.modules["tiddit." + name] = mod
+        setattr(tiddit, name, mod)
+    del pkg
+    return tiddit
+
+
 def run_sv(argv):
+    """NEVER EXECUTED in this image (no pysam / bwa / reference package importable): only the `rc 2` branch below is
+    covered by tests/test_cli.py; see INTEGRATION.md."""
     try:
+        install_gpu_modules()
         import tiddit.__main__ as ref_main   # needs pysam, bwa, ... (not in this image)
     except Exception as exc:
+        for name in SWAPPED_MODULES:
+            sys.modules.pop("tiddit." + name, None)
         print("tiddit_b200 replaces the clustering / coverage / GC stages only; --sv also needs the reference "
               "package (pysam, bwa) for signal extraction, assembly and variant calling: %s" % exc)
         return 2
-    from . import DBSCAN, tiddit_cluster, tiddit_coverage, tiddit_coverage_analysis, tiddit_gc, tiddit_signal
-    import tiddit
-    for name, mod in (("DBSCAN", DBSCAN), ("tiddit_cluster", tiddit_cluster), ("tiddit_coverage", tiddit_coverage),
-                      ("tiddit_gc", tiddit_gc), ("tiddit_coverage_analysis", tiddit_coverage_analysis),
-                      ("tiddit_signal", tiddit_signal)):
-        sys.modules["tiddit." + name] = mod
-        setattr(tiddit, name, mod)
-        if hasattr(ref_main, name):
-            setattr(ref_main, name, mod)
     sys.argv = ["tiddit"] + list(argv)
     ref_main.main()
     return 0

@@ -222,6 +222,19 @@ class AlignmentFile:
         self.close()
 
 
+def require_bam(path, ref=None):
+    """The native scanner reads sequential BAM only.  A CRAM input (which the reference hands to pysam together with
+    --ref) is detected up front and reported as such instead of failing deep inside the BGZF block hopper."""
+    with open(path, "rb") as f:
+        magic = f.read(4)
+    if magic == b"CRAM":
+        raise NotImplementedError(
+            "%s is a CRAM file: libtdt_bam.so reads BAM only (CRAM needs htslib/pysam and the --ref FASTA%s); "
+            "convert it with `samtools view -b` first" % (path, "" if ref else ", which was not given"))
+    if magic[:2] != b"\x1f\x8b":
+        raise ValueError("%s is not a BGZF-compressed BAM file (magic %r)" % (path, magic))
+
+
 def open_alignment_file(path, reference_filename=None):
     """pysam.AlignmentFile when pysam is installed, the pure-Python reader otherwise."""
     try:

@@ -28,12 +28,19 @@ def check_min_pts(m, n):
 # ---------------------------------------------------------------------------------------------
 # clustering
 # ---------------------------------------------------------------------------------------------
-def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_out=None, status=None):
+def cluster_workspace_bytes(n, P):
+    """Bytes of scratch tdt_cluster_labels needs for n signals in P pairs (callers that own their workspace)."""
+    return int(_lib.lib().tdt_cluster_workspace_bytes(int(n), int(P)))
+
+
+def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_out=None, status=None, ws=None):
     """All (chrA,chrB) segments in one call; int32 CUDA tensors in, int32 CUDA labels (insertion order) out.
 
     Replaces tiddit_cluster.pyx:140-160 + DBSCAN.py:125-129.  seg_off: int64 CUDA tensor of P+1 offsets.
     status: optional one-element int32 CUDA tensor (zeroed by the caller); when given, nothing synchronises and a
-    data error shows up there as a positive code (check it with `check_async_status`)."""
+    data error shows up there as a positive code (check it with `check_async_status`).
+    ws: optional uint8 CUDA tensor the caller owns (>= cluster_workspace_bytes(n, P)); callers that capture the call
+    into a CUDA graph MUST pass their own, because the process-wide cached workspace may be reallocated later."""
     torch = _lib.torch_cuda()
     L = _lib.lib()
     n = int(posA.numel())
@@ -43,7 +50,10 @@ def cluster_labels_device(posA, posB, seg_off, P, epsilon, m, max_pos=0, labels_
     if n == 0:
         return labels_out
     need = L.tdt_cluster_workspace_bytes(n, int(P))
-    ws = _lib.workspace(torch, need)
+    if ws is None:
+        ws = _lib.workspace(torch, need)
+    elif ws.numel() < need:
+        raise ValueError("workspace of %d bytes given, %d needed" % (ws.numel(), need))
     st = _lib.stream_ptr(torch)
     if status is not None:
         rc = L.tdt_cluster_labels_async(_lib.ptr(posA), _lib.ptr(posB), _lib.ptr(seg_off), n, int(P),

@@ -43,14 +43,17 @@ class GraphRunner:
         self.status = torch.zeros(1, dtype=torch.int32, device=posA.device)
         self.labels = labels_out
         args = (posA, posB, seg_off, P, epsilon, m, max_pos)
+        # the graph bakes the workspace pointer in: it must live (and stay put) as long as the graph does
+        self.ws = torch.empty(device_ops.cluster_workspace_bytes(posA.numel(), P) + 4096, dtype=torch.uint8,
+                              device=posA.device)
         self.stream = torch.cuda.Stream()
         self.stream.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.stream):   # warm-up: kernel attributes, workspace
-            device_ops.cluster_labels_device(*args, labels_out=labels_out, status=self.status)
+            device_ops.cluster_labels_device(*args, labels_out=labels_out, status=self.status, ws=self.ws)
         self.stream.synchronize()
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph, stream=self.stream):
-            device_ops.cluster_labels_device(*args, labels_out=labels_out, status=self.status)
+            device_ops.cluster_labels_device(*args, labels_out=labels_out, status=self.status, ws=self.ws)
 
     def replay(self):
         """Enqueue the captured call on the current stream; labels land in the buffer given at construction."""
@@ -87,8 +90,9 @@ class HostPipeline:
         self._graphs = {}
         self.s_in, self.s_run, self.s_out = (torch.cuda.Stream() for _ in range(3))
         self._events = [[torch.cuda.Event() for _ in range(3)] for _ in range(self.n_chunks)]
-        L = _lib.lib()
-        _lib.workspace(torch, L.tdt_cluster_workspace_bytes(self.n_max, min(p_max, self.n_max + 1)))
+        # private workspace: the captured chunk graphs hold its address (never the process-wide cached one)
+        self.ws = torch.empty(device_ops.cluster_workspace_bytes(self.n_max, min(p_max, self.n_max + 1)) + 4096,
+                              dtype=torch.uint8, device="cuda")
 
     def run(self, posA, posB, seg_off, epsilon, m, max_pos, out):
         """posA / posB / out: pinned CPU int32 tensors; seg_off: numpy int64 (P+1).  Returns `out` (filled when the
@@ -142,7 +146,7 @@ class HostPipeline:
 
     def _chunk_call(self, lo, hi, o0, ok, P, epsilon, m, max_pos):
         device_ops.cluster_labels_device(self.a_d[lo:hi], self.b_d[lo:hi], self.off_d[o0:o0 + ok], P, epsilon, m,
-                                         max_pos, labels_out=self.lab_d[lo:hi], status=self.status_d)
+                                         max_pos, labels_out=self.lab_d[lo:hi], status=self.status_d, ws=self.ws)
 
     def _launch_chunk(self, lo, hi, o0, ok, P, epsilon, m, max_pos):
         torch = self.torch

@@ -1,14 +1,29 @@
 """Minimal FASTA access for the GC path: the two pysam.FastaFile calls tiddit_gc.pyx:7-8,15 makes
-(get_reference_length, fetch).  Uses the real pysam when it is importable; otherwise a numpy
-reader that loads the file once and strips line breaks."""
+(get_reference_length, fetch), on a numpy reader that loads the file once and strips line breaks.
+Plain and gzip / bgzip-compressed files are read (pysam.FastaFile accepts bgzip); the whole genome is held in
+host memory as one uint8 array per contig (3.1 GB for GRCh38), which is what the GC kernel's H2D copies read."""
+import gzip
+import os
+
 import numpy as np
 
 _cache = {}
 
 
+def _read_bytes(path):
+    with open(path, "rb") as f:
+        magic = f.read(2)
+    if magic == b"\x1f\x8b":              # gzip / bgzip (concatenated members): inflate once
+        with gzip.open(path, "rb") as f:
+            return np.frombuffer(f.read(), dtype=np.uint8)
+    return np.fromfile(path, dtype=np.uint8)
+
+
 class NumpyFasta:
     def __init__(self, path):
-        raw = np.fromfile(path, dtype=np.uint8)
+        raw = _read_bytes(path)
+        if len(raw) and raw[0] not in (ord(">"), ord(";"), 10, 13):
+            raise ValueError("%s does not look like a FASTA file (first byte %r)" % (path, bytes(raw[:1])))
         gt = np.flatnonzero(raw == ord(">"))
         if len(gt):
             keep = (gt == 0) | (raw[np.maximum(gt - 1, 0)] == 10)
@@ -37,9 +52,12 @@ class NumpyFasta:
 
 
 def open_fasta(path):
-    fa = _cache.get(path)
+    """Cached per (path, mtime, size): replacing the file invalidates the entry; one genome is kept at a time."""
+    st = os.stat(path)
+    key = (os.path.abspath(path), st.st_mtime_ns, st.st_size)
+    fa = _cache.get(key)
     if fa is None:
         fa = NumpyFasta(path)
-        _cache.clear()      # one genome at a time
-        _cache[path] = fa
+        _cache.clear()
+        _cache[key] = fa
     return fa

@@ -1,9 +1,11 @@
 """Drop-in for tiddit/tiddit_coverage.pyx (create_coverage :10-21, print_coverage :22-45,
 update_coverage :48-74), with the accumulation done on the GPU.
 
-The reference adds one read per Python call; the GPU path wants batches, so next to the per-read
-`update_coverage` (same signature, same result, one tiny launch per call) this module offers
-`update_coverage_batch` (arrays of starts / ends for one contig) and `DeviceCoverage`, which keeps
+The reference adds one read per Python call; the GPU path wants batches.  `create_coverage` therefore returns
+`CoverageArray`s -- float64 ndarrays that queue the per-read `update_coverage` calls (same signature) and apply
+them with the kernel every 2^22 reads and before any access to the data, so the reference's own read loops run
+unchanged without per-call device traffic.  Next to it: `update_coverage_batch` (arrays of starts / ends for one
+contig) and `DeviceCoverage`, which keeps
 every contig's bins resident in HBM while a BAM is streamed and hands the
 float64 arrays back at the end.  Bins are bit-identical to the reference's in every case
 (all partial sums are exact).
@@ -14,7 +16,8 @@ import numpy as np
 
 from . import _lib, device_ops
 
-__all__ = ["create_coverage", "update_coverage", "update_coverage_batch", "print_coverage", "DeviceCoverage"]
+__all__ = ["create_coverage", "update_coverage", "update_coverage_batch", "print_coverage", "DeviceCoverage",
+           "CoverageArray"]
 
 
 def create_coverage(bam_header, bin_size, c="all"):
@@ -25,7 +28,7 @@ def create_coverage(bam_header, bin_size, c="all"):
         if c != "all" and name != c:
             continue
         bins = int(math.ceil(length / float(bin_size)))
-        coverage_data[name] = np.zeros(bins)
+        coverage_data[name] = CoverageArray(bins)
         end_bin_size[name] = length - (bins - 1) * bin_size
         if c != "all":
             return coverage_data[name], end_bin_size[name]
@@ -47,6 +50,9 @@ def update_coverage_batch(ref_start, ref_end, bin_size, coverage_data, end_bin_s
 
     Raises IndexError like the reference when a read touches a bin outside the array (the state of
     coverage_data is then unspecified; the reference leaves the partial sums of the earlier reads)."""
+    if type(coverage_data) is CoverageArray:
+        update_coverage_batch(ref_start, ref_end, bin_size, coverage_data._plain(), end_bin_size)   # queued reads first
+        return coverage_data
     torch = _lib.torch_cuda()
     if not isinstance(coverage_data, np.ndarray) or coverage_data.dtype != np.float64 or coverage_data.ndim != 1:
         raise ValueError("Buffer dtype mismatch, expected 'DTYPE_t' but got something else")
@@ -71,8 +77,180 @@ def update_coverage_batch(ref_start, ref_end, bin_size, coverage_data, end_bin_s
     return coverage_data
 
 
+class CoverageArray(np.lib.mixins.NDArrayOperatorsMixin):
+    """What create_coverage hands out: a float64 array whose per-read updates are QUEUED and applied by the GPU kernel
+    in batches.
+
+    The reference's callers (tiddit/__main__.py:229-242, tiddit_signal.pyx:181-182) call update_coverage once per read
+    -- 618 M times on a 30X BAM -- and only look at the bins when the BAM is exhausted.  update_coverage on a
+    CoverageArray appends (start, end) to the array's queue (two list appends, no device work); the queue is flushed
+    to tdt_coverage_accumulate every FLUSH_READS reads and before ANY access to the data.  Between flushes the bins
+    stay resident in HBM; the host copy is refreshed on access.  No coverage arithmetic happens on the CPU.
+
+    It is an array-like that WRAPS its ndarray instead of subclassing it, on purpose: numpy hands out base-class views
+    of a subclass instance (np.asarray, np.array(copy=False), C extensions) without calling any Python hook, which
+    would read the bins before the queue has been applied.  As a wrapper every consumer has to come through
+    __array__ / __buffer__ / __getitem__ / __array_ufunc__ / __array_function__ / attribute access, and each of them
+    flushes first: indexing, slicing, len, iteration, numpy functions and operators, printing, memoryview and Cython
+    typed memoryviews (PEP 688), copying and pickling (joblib returns the arrays from worker processes) all see the
+    finished bins -- which covers every use the reference makes of them (tiddit_coverage_analysis.pyx:14-20,
+    tiddit_variant.pyx:267-309, tiddit_contig_analysis.pyx:192, print_coverage).
+
+    One deviation from the reference: a read that touches a bin outside the array raises the reference's IndexError
+    when its batch is flushed (at the latest on the next access), not inside the call that queued it."""
+
+    FLUSH_READS = 1 << 22
+    __array_priority__ = 100.0
+    _META = frozenset(("shape", "dtype", "ndim", "size", "nbytes", "itemsize"))
+
+    def __init__(self, n_bins):
+        self._host = np.zeros(int(n_bins), dtype=np.float64)
+        self._qs, self._qe = [], []       # queued starts / ends (Python ints)
+        self._q_bin = None                # (bin_size, end_bin_size) of the queued reads
+        self._dev = None                  # device copy of the bins while updates are streaming
+        self._host_stale = False          # the device copy is ahead of the host memory
+
+    # ---- the queue ------------------------------------------------------------------------------
+    def _queue(self, ref_start, ref_end, bin_size, end_bin_size):
+        key = (bin_size, end_bin_size)
+        if self._q_bin != key:
+            if self._qs:
+                self._flush_reads()
+            self._q_bin = key
+        self._qs.append(ref_start)
+        self._qe.append(ref_end)
+        if len(self._qs) >= self.FLUSH_READS:
+            self._flush_reads()
+
+    def _flush_reads(self):
+        """Queued reads -> the kernel; the bins stay on the device."""
+        if not self._qs:
+            return
+        qs, qe = self._qs, self._qe
+        self._qs, self._qe = [], []
+        s = _as_int32_positions(qs, "ref_start")
+        e = _as_int32_positions(qe, "ref_end")
+        bin_size, end_bin_size = self._q_bin
+        self._dev, bad = _accumulate_resident(s, e, int(bin_size), int(end_bin_size), self._host, self._dev)
+        self._host_stale = True
+        if bad:
+            self._plain()
+            raise IndexError("Out of bounds on buffer access (axis 0)")
+
+    def _plain(self):
+        """Everything queued is applied and the host ndarray holds the result; the device copy is dropped, so host-side
+        writes that follow (cov[i] = x) are seen by the next batch.  -> the ndarray."""
+        if self._qs:
+            self._flush_reads()
+        if self._host_stale:
+            self._host[...] = _download(self._dev)
+            self._host_stale = False
+        self._dev = None
+        return self._host
+
+    def flush(self):
+        """Apply everything queued now (errors of queued reads surface here)."""
+        self._plain()
+        return self
+
+    # ---- every way of looking at the data goes through _plain -------------------------------------
+    def __len__(self):
+        return len(self._host)
+
+    def __getitem__(self, key):
+        return self._plain()[key]
+
+    def __setitem__(self, key, value):
+        self._plain()[key] = value
+
+    def __iter__(self):
+        return iter(self._plain())
+
+    def __array__(self, dtype=None, copy=None):
+        base = self._plain()
+        if dtype is not None and np.dtype(dtype) != base.dtype:
+            return base.astype(dtype)
+        return base.copy() if copy else base
+
+    def __array_ufunc__(self, ufunc, method, *inputs, out=None, **kwargs):
+        args = [x._plain() if isinstance(x, CoverageArray) else x for x in inputs]
+        if out is not None:
+            kwargs["out"] = tuple(x._plain() if isinstance(x, CoverageArray) else x for x in out)
+        res = getattr(ufunc, method)(*args, **kwargs)
+        if out is not None and len(out) == 1 and isinstance(out[0], CoverageArray):
+            return out[0]                                        # cov += x keeps the queueing array
+        return res
+
+    def __array_function__(self, func, types, args, kwargs):
+        def strip(x):
+            if isinstance(x, CoverageArray):
+                return x._plain()
+            if isinstance(x, (list, tuple)):
+                return type(x)(strip(v) for v in x)
+            if isinstance(x, dict):
+                return {k: strip(v) for k, v in x.items()}
+            return x
+        return func(*strip(args), **strip(kwargs))
+
+    def __buffer__(self, flags):                                 # memoryview(), Cython `double[:]` (PEP 688)
+        return self._plain().__buffer__(flags)
+
+    def __getattr__(self, name):                                 # ndarray attributes / methods (sum, mean, tolist, ...)
+        if name.startswith("_"):
+            raise AttributeError(name)
+        host = self.__dict__.get("_host")
+        if host is None:
+            raise AttributeError(name)
+        return getattr(host if name in self._META else self._plain(), name)
+
+    def __reduce__(self):                                        # pickled as the finished plain array
+        return (np.array, (self._plain().copy(),))
+
+    def __copy__(self):
+        return self._plain().copy()
+
+    def __deepcopy__(self, memo):
+        return self._plain().copy()
+
+    def __repr__(self):
+        return repr(self._plain())
+
+    def __str__(self):
+        return str(self._plain())
+
+    def __bool__(self):
+        return bool(self._plain())
+
+    def __contains__(self, x):
+        return x in self._plain()
+
+
+def _accumulate_resident(s, e, bin_size, end_bin_size, host_bins, dev_bins):
+    """One batch of one contig's reads through tdt_coverage_accumulate; the bins live on the device between batches.
+    -> (device bins, any read out of bounds).  (tests/test_cli.py swaps this for the oracle on CPU-only machines.)"""
+    torch = _lib.torch_cuda()
+    if dev_bins is None:
+        dev_bins = torch.from_numpy(host_bins).cuda()
+    first_bad = device_ops.new_first_bad(torch)
+    device_ops.coverage_accumulate_device(torch.from_numpy(s).cuda(), torch.from_numpy(e).cuda(), bin_size, end_bin_size,
+                                          dev_bins, first_bad)
+    return dev_bins, int(first_bad.item()) != device_ops.FIRST_BAD_NONE
+
+
+def _download(dev_bins):
+    return dev_bins.cpu().numpy()
+
+
 def update_coverage(ref_start, ref_end, bin_size, coverage_data, end_bin_size):
-    """tiddit_coverage.pyx:48-74, one read (signature kept for tiddit_signal.pyx:182 / __main__.py:242)."""
+    """tiddit_coverage.pyx:48-74, one read (signature kept for tiddit_signal.pyx:182 / __main__.py:242).
+
+    On the arrays create_coverage returns the read is queued (see CoverageArray) -- no per-call device traffic; a
+    plain ndarray the caller allocated itself is updated at once through a one-read batch (O(n_bins) copies)."""
+    if type(coverage_data) is CoverageArray:
+        if bin_size == 0:
+            raise ZeroDivisionError("integer division or modulo by zero")
+        coverage_data._queue(ref_start, ref_end, bin_size, end_bin_size)
+        return coverage_data
     return update_coverage_batch([int(ref_start)], [int(ref_end)], bin_size, coverage_data, end_bin_size)
 
 

@@ -289,7 +289,10 @@ def main(bam_file_name, ref, prefix, min_q, max_ins, sample_id, threads, min_con
          min_clip_len):
     """tiddit_signal.pyx:230-334: writes <prefix>_tiddit/{discordants,splits}_<sample>.tab, clips/<contig>.fa,
     clips_<sample>.fa and returns {contig: float64 coverage per 50-bp bin} for the contigs with LN >= min_contig.
-    `ref` (CRAM reference) and `skip_index` are accepted for compatibility: the scan is sequential, no index is read."""
+    `skip_index` is accepted for compatibility (the scan is sequential, no index is read); `ref` only matters for
+    CRAM input, which this reader rejects with an explicit error (bamio.require_bam)."""
+    from . import bamio
+    bamio.require_bam(bam_file_name, ref)
     signals = collect(bam_file_name, int(min_q), int(max_ins), int(min_contig), int(min_anchor_len), int(min_clip_len),
                       bin_size=50, threads=int(threads))
     print("Writing signals to file")
