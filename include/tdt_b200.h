@@ -193,6 +193,29 @@ TDT_API int tdt_profile_end(char *out, size_t cap);
  * for bench.py's "gpu_launches" line. */
 TDT_API int64_t tdt_launch_count(void);
 
+/* --------------------------------------------------------------------------------------------
+ * Label exchange of the sharded clustering path over NVLink peer memory (csrc/tdt_peer.cu).
+ * The reference clusters the (chrA,chrB) pairs serially in one process (tiddit/tiddit_cluster.pyx:140-154); pairs
+ * are independent, so N ranks label disjoint pairs and exchange the finished labels once.  This is the
+ * collective half of the tdt_cluster_labels_sharded entry SURVEY.md section 8(b) proposes -- without a
+ * communicator: every rank owns one buffer [nranks * slot_elems int32 | flags | control] allocated with
+ * tdt_peer_alloc (cudaMalloc + cudaIpcGetMemHandle; the 64-byte handle travels to the other ranks by any host
+ * channel) and mapped by the others with tdt_peer_open.  The clustering call writes its labels into slot `rank`
+ * of the local buffer; tdt_peer_allgather enqueues ONE kernel that pushes that slot into every peer's buffer
+ * with 16-byte stores, publishes an epoch flag (release, system scope) and waits for every peer's flag
+ * (acquire).  No per-call arguments change, so the launch can be captured in a CUDA graph.  A peer that does
+ * not arrive within 5 s sets *status_accum to 77 instead of hanging the device.  Between two exchanges every
+ * rank must have consumed the previous result (any collective / barrier between steps).
+ * bufs_h: HOST array of nranks device pointers (the local mapping of every rank's buffer).
+ * ------------------------------------------------------------------------------------------ */
+TDT_API size_t tdt_peer_buffer_bytes(int64_t slot_elems, int32_t nranks);
+TDT_API int tdt_peer_alloc(size_t bytes, void **dev_ptr, unsigned char *handle64_h);
+TDT_API int tdt_peer_open(const unsigned char *handle64_h, void **dev_ptr);
+TDT_API int tdt_peer_close(void *dev_ptr);
+TDT_API int tdt_peer_free(void *dev_ptr);
+TDT_API int tdt_peer_allgather(void *const *bufs_h, int64_t slot_elems, int32_t rank, int32_t nranks,
+                               int32_t *status_accum, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,9 +25,13 @@ def test_cluster_main_fold_matches_reference(case, oracle, monkeypatch):
     from tiddit_b200 import tiddit_cluster, device_ops
     exp = load_json("cluster_case%d_expected.json" % case)
     a = exp["args"]
-    monkeypatch.setattr(device_ops, "cluster_labels",
-                        lambda posA, posB, seg_off, eps, m, max_pos=0: oracle.cluster_segments(posA, posB, seg_off, eps, m))
-    monkeypatch.setattr(device_ops, "cluster_aggregate", oracle.cluster_aggregate)
+    def cpu_cluster_and_aggregate(posA, posB, seg_off, span, name_id, flags, same_chrom, eps, m, max_ins_len, is_mp,
+                                  min_reads, max_pos=0, n_names=0):
+        labels = oracle.cluster_segments(posA, posB, seg_off, eps, m)
+        rows, mem = oracle.cluster_aggregate(labels, posA, posB, span, name_id, flags, seg_off, same_chrom, max_ins_len,
+                                             is_mp, min_reads)
+        return labels, rows, mem
+    monkeypatch.setattr(device_ops, "cluster_and_aggregate", cpu_cluster_and_aggregate)
     got = tiddit_cluster.main(os.path.join(GOLDEN, "cluster_case%d" % case), a["chromosomes"], a["contig_length"],
                               a["samples"], a["is_mp"], a["epsilon"], a["m"], a["max_ins_len"], a["min_contig"],
                               a["skip_assembly"], a["min_reads"])

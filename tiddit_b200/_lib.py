@@ -38,6 +38,12 @@ SIGNATURES = {
     "tdt_coverage_medians_workspace_bytes": (_sz, [_i32]),
     "tdt_coverage_medians": (ctypes.c_int, [_p, _p, _p, _i32, _i64, _p, _p, _p, _sz, _p]),
     "tdt_gc_bins": (ctypes.c_int, [_p, _i64, _i32, _dbl, _p, _p]),
+    "tdt_peer_buffer_bytes": (_sz, [_i64, _i32]),
+    "tdt_peer_alloc": (ctypes.c_int, [_sz, ctypes.POINTER(_p), ctypes.c_char_p]),
+    "tdt_peer_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_p)]),
+    "tdt_peer_close": (ctypes.c_int, [_p]),
+    "tdt_peer_free": (ctypes.c_int, [_p]),
+    "tdt_peer_allgather": (ctypes.c_int, [ctypes.POINTER(_p), _i64, _i32, _i32, _p, _p]),
     "tdt_debug_segsort": (ctypes.c_int, [_p, _p, _p, _p, _i64, _i64, _i32, _p, _p, _p, _sz, _p]),
 }
 

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtdt_b200.so")
 BAM_LIB = os.path.join(HERE, "libtdt_bam.so")
-SOURCES = ["tdt_api.cu", "tdt_cluster.cu", "tdt_aggregate.cu", "tdt_coverage.cu", "tdt_ploidy.cu", "tdt_gc.cu"]
+SOURCES = ["tdt_api.cu", "tdt_cluster.cu", "tdt_aggregate.cu", "tdt_coverage.cu", "tdt_ploidy.cu", "tdt_gc.cu", "tdt_peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "--expt-relaxed-constexpr"]
 

@@ -182,6 +182,25 @@ def cluster_aggregate(labels, posA, posB, span, name_id, flags, seg_off, same_ch
     return rows[:C].cpu().numpy(), mem[:M].cpu().numpy()
 
 
+def cluster_and_aggregate(posA, posB, seg_off, span, name_id, flags, same_chrom, epsilon, m, max_ins_len, is_mp, min_reads,
+                          max_pos=0, n_names=0):
+    """Host front end of tiddit_cluster.pyx:140-336 on packed arrays: ONE upload of every column, tdt_cluster_labels,
+    tdt_cluster_aggregate on the labels where they are (they never leave HBM between the two calls), then the labels,
+    the candidate rows and the member index come back once.  -> (labels int32 [n], rows int32 [C,16], member_idx int32 [M])."""
+    torch = _lib.torch_cuda()
+    seg_off = np.ascontiguousarray(seg_off, dtype=np.int64)
+    P = len(seg_off) - 1
+    d = lambda a, t: _lib.to_device(torch, a, t)
+    A, B, O = d(posA, np.int32), d(posB, np.int32), d(seg_off, np.int64)
+    span = np.ascontiguousarray(span, dtype=np.int32).reshape(-1, 4)
+    labels = cluster_labels_device(A, B, O, P, epsilon, m, max_pos)
+    rows, mem, counts = cluster_aggregate_device(labels, A, B, d(span, np.int32), d(name_id, np.int32), d(flags, np.uint8), O,
+                                                 d(same_chrom, np.uint8), P, max_ins_len, is_mp, min_reads, max_pos, n_names)
+    C, M, err, _ = (int(v) for v in counts.cpu().tolist())
+    check_aggregate_status(err)
+    return labels.cpu().numpy(), rows[:C].cpu().numpy(), mem[:M].cpu().numpy()
+
+
 def segsort_device(keys, vals, off, key_bits, segid=None):
     """Test hook: every segment [off[s], off[s+1]) of (keys uint32-as-int32, vals int32 or None) sorted by key,
     stable -> (keys_out, vals_out) CUDA tensors."""

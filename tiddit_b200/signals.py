@@ -153,7 +153,7 @@ class PackedSignals:
         self.sample_id = np.ascontiguousarray(sample_id, dtype=np.int32)
         self.oriA_id = np.ascontiguousarray(oriA_id, dtype=np.int32)  # index into ori_table (rec[4] verbatim)
         self.oriB_id = np.ascontiguousarray(oriB_id, dtype=np.int32)
-        self.names = list(names)
+        self.names = names if isinstance(names, _LazyNames) else list(names)
         self.samples = list(samples)
         self.ori_table = list(ori_table)
         self.same_chrom = np.array([a == b for a, b in self.pairs], dtype=np.uint8)
@@ -255,6 +255,22 @@ class PackedSignals:
                    [str(x) for x in names], samples, [str(x) for x in ori_table],
                    chrA_present=[a for a in dict.fromkeys(chromosomes) if a in chrA_all])
 
+    @classmethod
+    def from_arrays(cls, posA, posB, seg_off, rec, contigs, sample="S"):
+        """Packed arrays as a producer holds them (synth.signal_records layout: span, name_id, flags over the populated
+        (chrA,chrB) pairs of `contigs` in visiting order) -> PackedSignals, names interned lazily as "r<id>"."""
+        from .synth import populated_pairs
+        names_c = [c for c, _ in contigs]
+        pairs = [(names_c[ia], names_c[ib]) for ia, ib in populated_pairs(contigs)][:len(seg_off) - 1]
+        n = len(posA)
+        flags = np.asarray(rec["flags"], dtype=np.uint8)
+        ori_table = ["True", "False"]
+        oriA = np.where(flags & SIG_A_TRUE, 0, 1).astype(np.int32)
+        oriB = np.where(flags & SIG_B_TRUE, 0, 1).astype(np.int32)
+        n_names = int(rec.get("n_names", n))
+        return cls(pairs, seg_off, posA, posB, rec["span"], rec["name_id"], flags, np.zeros(n, dtype=np.int32), oriA, oriB,
+                   _LazyNames(n_names), [sample], ori_table)
+
     # ---- .npz round trip --------------------------------------------------------------------------------
     def save(self, path):
         np.savez(path, pairs=np.array(self.pairs, dtype=object).reshape(-1, 2).astype(str),
@@ -268,6 +284,22 @@ class PackedSignals:
         return cls([tuple(p) for p in z["pairs"].tolist()], z["seg_off"], z["posA"], z["posB"], z["span"], z["name_id"],
                    z["flags"], z["sample_id"], z["oriA_id"], z["oriB_id"], z["names"].tolist(), z["samples"].tolist(),
                    z["ori_table"].tolist(), z["chrA_present"].tolist())
+
+
+class _LazyNames:
+    """names[i] = "r<i>" without materialising millions of strings (PackedSignals.from_arrays)."""
+
+    def __init__(self, n):
+        self.n = int(n)
+
+    def __len__(self):
+        return self.n
+
+    def __getitem__(self, i):
+        return "r%d" % i
+
+    def __iter__(self):
+        return ("r%d" % i for i in range(self.n))
 
 
 class CandidateTable:

@@ -182,6 +182,40 @@ def signal_records(posA, posB, seg_off, seed=11, split_frac=0.18, contig_frac=0.
             "same_chrom": same, "n_names": n}
 
 
+def write_tab_files(prefix, sample, posA, posB, seg_off, rec, contigs=GRCH38):
+    """discordants_<sample>.tab / splits_<sample>.tab (writer tiddit_signal.pyx:298-326) for a synthetic
+    signal set, laid out so that the reference's reader (tiddit_cluster.pyx:47-137, paired-end library) parses back
+    exactly (posA, posB): discordant rows pick endA / startA and startB / endB by orientation (find_discordant_pos),
+    split rows carry the positions directly.  Assembly contigs (kind A) are written as splits.  -> number of lines."""
+    import os
+    import pandas as pd
+    os.makedirs(prefix + "_tiddit", exist_ok=True)
+    pairs = populated_pairs(contigs)
+    names = np.array([c for c, _ in contigs])
+    pid = np.repeat(np.arange(len(seg_off) - 1), np.diff(seg_off))
+    chrA = names[np.array([ia for ia, _ in pairs])[pid]]
+    chrB = names[np.array([ib for _, ib in pairs])[pid]]
+    flags = rec["flags"]
+    revA = np.where(flags & 0x04, "True", "False")
+    revB = np.where(flags & 0x10, "True", "False")
+    a, b = posA.astype(np.int64), posB.astype(np.int64)
+    read = np.char.add("r", rec["name_id"].astype(str))
+    disc = (flags & 3) == 0
+    startA = np.where(revA == "True", a, a - 100)
+    endA = np.where(revA == "True", a + 100, a)
+    startB = np.where(revB == "True", b, b - 100)
+    endB = np.where(revB == "True", b + 100, b)
+    d = pd.DataFrame({"n": read[disc], "ca": chrA[disc], "cb": chrB[disc], "sa": startA[disc], "ea": endA[disc],
+                      "ra": revA[disc], "sb": startB[disc], "eb": endB[disc], "rb": revB[disc]})
+    d.to_csv("%s_tiddit/discordants_%s.tab" % (prefix, sample), sep="\t", header=False, index=False)
+    sp = ~disc
+    span = rec["span"]
+    t = pd.DataFrame({"n": read[sp], "ca": chrA[sp], "cb": chrB[sp], "pa": a[sp], "ra": revA[sp], "pb": b[sp], "rb": revB[sp],
+                      "sa": span[sp, 0], "ea": span[sp, 1], "sb": span[sp, 2], "eb": span[sp, 3]})
+    t.to_csv("%s_tiddit/splits_%s.tab" % (prefix, sample), sep="\t", header=False, index=False)
+    return int(len(posA))
+
+
 def sv_bam_reads(contigs, n_fragments=4000, seed=13, read_len=100, max_ins=600, n_events=12):
     """Reads for bamio.write_bam that exercise every branch of the signal worker (tiddit_signal.pyx:169-221):
     proper pairs, discordant pairs (far apart on one contig, across contigs, every orientation, mates that are

@@ -34,10 +34,10 @@ def cluster_packed(packed, epsilon, m, max_ins_len, is_mp, min_reads):
     max_pos = packed.max_pos()
     if max_pos >= 2 ** 30:
         raise OverflowError("signal positions must lie in [0, 2^30)")
-    labels = device_ops.cluster_labels(packed.posA, packed.posB, packed.seg_off, epsilon, m, max_pos)
-    rows, members = device_ops.cluster_aggregate(labels, packed.posA, packed.posB, packed.span, packed.name_id,
-                                                 packed.flags, packed.seg_off, packed.same_chrom, max_ins_len, is_mp,
-                                                 min_reads, max_pos, max(len(packed.names), 1))
+    labels, rows, members = device_ops.cluster_and_aggregate(packed.posA, packed.posB, packed.seg_off, packed.span,
+                                                             packed.name_id, packed.flags, packed.same_chrom, epsilon, m,
+                                                             max_ins_len, is_mp, min_reads, max_pos,
+                                                             max(len(packed.names), 1))
     return labels, CandidateTable(rows, members)
 
 
