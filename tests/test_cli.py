@@ -127,9 +127,10 @@ def test_queued_update_coverage_host_logic_cpu(tmp_path, monkeypatch, oracle):
     cov[1] = 5.0                                            # host writes interleave with queued reads
     tc.update_coverage(400, 550, 500, cov, ebs)
     assert cov[1] == 5.0 + np.float64(np.float32(49) / np.float32(500))
-    tc.update_coverage(1200, 1600, 500, cov, ebs)           # beyond the contig: the reference's IndexError, at flush
-    with pytest.raises(IndexError):
-        cov.flush()
+    with pytest.raises(IndexError):                         # beyond the contig: the reference's IndexError, in the call
+        tc.update_coverage(1200, 1600, 500, cov, ebs)
+    tc.update_coverage(-100, -50, 500, cov, ebs)            # negative bins wrap around like the reference's indexing
+    assert cov[2] == np.float64(np.float32(50) / np.float32(500))
     with pytest.raises(ZeroDivisionError):
         tc.update_coverage(0, 10, 0, cov, ebs)
     out = str(tmp_path / "loop")

@@ -96,8 +96,9 @@ class CoverageArray(np.lib.mixins.NDArrayOperatorsMixin):
     finished bins -- which covers every use the reference makes of them (tiddit_coverage_analysis.pyx:14-20,
     tiddit_variant.pyx:267-309, tiddit_contig_analysis.pyx:192, print_coverage).
 
-    One deviation from the reference: a read that touches a bin outside the array raises the reference's IndexError
-    when its batch is flushed (at the latest on the next access), not inside the call that queued it."""
+    A read that touches a bin outside the array raises the reference's IndexError inside update_coverage, like the
+    reference (two integer comparisons on the fast path); the kernel's own bounds report is a second line of defence
+    at flush time."""
 
     FLUSH_READS = 1 << 22
     __array_priority__ = 100.0
@@ -107,6 +108,7 @@ class CoverageArray(np.lib.mixins.NDArrayOperatorsMixin):
         self._host = np.zeros(int(n_bins), dtype=np.float64)
         self._qs, self._qe = [], []       # queued starts / ends (Python ints)
         self._q_bin = None                # (bin_size, end_bin_size) of the queued reads
+        self._q_end = -1                  # n_bins * bin_size: reads inside [0, _q_end] cannot leave the array
         self._dev = None                  # device copy of the bins while updates are streaming
         self._host_stale = False          # the device copy is ahead of the host memory
 
@@ -117,6 +119,14 @@ class CoverageArray(np.lib.mixins.NDArrayOperatorsMixin):
             if self._qs:
                 self._flush_reads()
             self._q_bin = key
+            self._q_end = len(self._host) * bin_size if bin_size > 0 else -1
+        if not (0 <= ref_start and ref_end <= self._q_end):
+            # off the fast path: the reference's bounds check (tiddit_coverage.pyx:48-74 indexes with wrap-around,
+            # so bins -n_bins .. n_bins-1 are legal) -- raise where the reference raises, inside the call
+            nb = len(self._host)
+            fb, eb = ref_start // bin_size, (ref_end - 1) // bin_size
+            if not (-nb <= fb < nb) or (eb != fb and not (-nb <= eb < nb)):
+                raise IndexError("Out of bounds on buffer access (axis 0)")
         self._qs.append(ref_start)
         self._qe.append(ref_end)
         if len(self._qs) >= self.FLUSH_READS:
