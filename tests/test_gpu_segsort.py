@@ -5,6 +5,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["lsd", "samplesort"], autouse=True)
+def sort_generation(request, monkeypatch):
+    """Every test runs on the production LSD sort and on the sample-sort generation (tdt_segsort2.cuh, opt-in)."""
+    if request.param == "samplesort":
+        monkeypatch.setenv("TDT_SEGSORT_V2", "1")
+    else:
+        monkeypatch.delenv("TDT_SEGSORT_V2", raising=False)
+    return request.param
+
+
 def _expect(keys, vals, off):
     ko, vo = keys.copy(), vals.copy()
     for s in range(len(off) - 1):
@@ -67,6 +77,42 @@ def test_segsort_many_tiny_and_huge_mix():
     order = np.lexsort((vals, keys, seg))
     assert np.array_equal(got_k, keys[order])
     assert np.array_equal(got_v, vals[order])
+
+
+@pytest.mark.parametrize("kind", ["all_equal", "two_values", "pileup", "hotspot", "narrow", "boundaries", "sorted", "reversed"])
+def test_segsort_skewed_distributions(kind):
+    """What the sample-sort rounds and the interpolation finish must survive: heavy exact duplicates (the buckets cannot be
+    cut: LSD chain), pile-ups inside an otherwise uniform segment, a 2 kb hotspot, segment sizes around the local limit."""
+    rng = np.random.default_rng(sum(map(ord, kind)))
+    if kind == "boundaries":
+        sizes = [6143, 6144, 6145, 8191, 8192, 8193, 33, 32, 31, 1, 2, 12288, 12289, 0, 20000]
+    else:
+        sizes = [300_000, 5000, 40_000, 7, 6144]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(off[-1])
+    keys = rng.integers(0, 200_000_000, n, dtype=np.int64)
+    if kind == "all_equal":
+        keys[:] = 12345
+    elif kind == "two_values":
+        keys = np.where(rng.random(n) < 0.5, 77, 150_000_000)
+    elif kind == "pileup":
+        keys[rng.random(n) < 0.4] = 99_000_000          # 40 % of every segment at one position
+        keys[rng.random(n) < 0.1] = 5
+    elif kind == "hotspot":
+        hot = rng.random(n) < 0.6
+        keys[hot] = 50_000_000 + rng.integers(0, 2000, int(hot.sum()))
+    elif kind == "narrow":
+        keys = 1000 + rng.integers(0, 50, n)
+    elif kind == "sorted":
+        keys = np.sort(keys)
+    elif kind == "reversed":
+        keys = np.sort(keys)[::-1].copy()
+    keys = keys.astype(np.uint32)
+    vals = rng.permutation(n).astype(np.int32)
+    want_k, want_v = _expect(keys, vals, off)
+    got_k, got_v = _run(keys, vals, off, 28)
+    assert np.array_equal(got_k, want_k)
+    assert np.array_equal(got_v, want_v)
 
 
 def test_segsort_key_range_error():

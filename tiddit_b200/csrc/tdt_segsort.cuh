@@ -68,7 +68,7 @@ static inline int64_t ss_nlarge_max(int64_t n, int64_t nseg_max) {
     return a < nseg_max ? a : (nseg_max > 0 ? nseg_max : 1);
 }
 
-static inline size_t segsort_temp_bytes(int64_t n, int64_t nseg_max) {
+static inline size_t segsort1_temp_bytes(int64_t n, int64_t nseg_max) {
     const int64_t nl = ss_nlarge_max(n, nseg_max);
     const int64_t tiles = n / SS_TILE + nl + 1;
     const int64_t nwin = (n + SS_WINDOW - 1) / SS_WINDOW + 1;
@@ -714,14 +714,14 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
 // n_max / nseg_max: host-side upper bounds that size the grids; the actual n / nseg are read on the device
 // from dims[0] / dims[1].  keys_tmp / vals_tmp: scratch of n_max elements (only touched for large segments).
 // segid (optional): segment index of every element; enables the counting path for segments of <= 32 elements.
-int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *keys_out, int32_t *vals_out,
+int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *keys_out, int32_t *vals_out,
                          uint32_t *keys_tmp, int32_t *vals_tmp, const int64_t *off, const int64_t *dims,
                          const int32_t *segid, int64_t n_max, int64_t nseg_max, int key_bits, void *temp,
                          size_t temp_bytes, int *err, cudaStream_t st) {
     if (n_max <= 0 || nseg_max <= 0) return TDT_OK;
-    if (temp_bytes < segsort_temp_bytes(n_max, nseg_max))
+    if (temp_bytes < segsort1_temp_bytes(n_max, nseg_max))
         return fail(TDT_E_WORKSPACE, "segmented sort needs %zu bytes of temporary storage, %zu reserved",
-                    segsort_temp_bytes(n_max, nseg_max), temp_bytes);
+                    segsort1_temp_bytes(n_max, nseg_max), temp_bytes);
     if (key_bits < 1) key_bits = 1;
     if (key_bits > 32) key_bits = 32;
     SSArgs a;

@@ -1,19 +1,29 @@
 #!/bin/bash
-# multi-GPU session: NCCL sharding test + bench at N = 1 .. NGPU
+# multi-GPU session (gpurun --gpus N, NGPU=N): NCCL tests, then bench.py at N with the p2p and the NCCL label exchange
 mkdir -p gpurun_out
 NG=${NGPU:-2}
 nvidia-smi -L > gpurun_out/gpus.txt
-timeout 600 python -m pytest tests/test_gpu_engine.py -q --timeout 300 2>&1 | tail -3
-for n in 1 2 4 8; do
-  if [ $n -le $NG ]; then
-    if [ $n -eq 1 ]; then
-      timeout 600 python bench.py --gpus 1 --steps 10 --warmup 3 --no-coverage --no-cpu --no-extra > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
-    else
-      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 > gpurun_out/bench_n$n.json 2> gpurun_out/bench_n$n.err
-    fi
-    echo "N=$n rc=$?"; tail -2 gpurun_out/bench_n$n.err; python -c "
-import json,sys
-d=json.loads(open('gpurun_out/bench_n$n.json').read().strip().splitlines()[-1])
-print({k:d[k] for k in ['n_gpus','value','ms_per_step','verified']}, d['e2e']['ms_per_step'], d['roofline']['stages_ms'])"
-  fi
+nvidia-smi topo -m >> gpurun_out/gpus.txt 2>&1
+echo "== engine tests"; timeout 900 python -m pytest tests/test_gpu_engine.py -q --timeout 600 2>&1 | tail -8
+for n in ${NS:-$NG}; do
+  for ex in ${EXCH:-p2p nccl}; do
+    export TDT_LABEL_EXCHANGE=$ex
+    out=gpurun_out/bench_n${n}_$ex
+    timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $n --steps 10 --warmup 3 ${BENCH_ARGS} > $out.json 2> $out.err
+    echo "N=$n exchange=$ex rc=$?"; grep -v "^W\|^\*\*\*\|OMP_NUM" $out.err | tail -5
+    python - <<PY
+import json
+try:
+    d = json.loads(open("$out.json").read().strip().splitlines()[-1])
+    print({k: d[k] for k in ["n_gpus", "value", "ms_per_step", "verified"]}, "e2e_ms", d["e2e"]["ms_per_step"])
+    print("  exchange", d.get("exchange"))
+    print("  stages", d["roofline"]["stages_ms"])
+    t = d.get("tumor60x", {})
+    print("  tumor60x", {k: t.get(k) for k in ["value", "ms_per_step", "verified"]}, t.get("e2e", {}).get("ms_per_step"), t.get("exchange"))
+    print("  sharded", d.get("sharded"))
+except Exception as e:
+    print("no result:", e)
+PY
+  done
 done
+unset TDT_LABEL_EXCHANGE
