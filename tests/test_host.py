@@ -122,7 +122,7 @@ def test_tab_column_reader_equals_line_reader(tmp_path):
 
     def same(a, b):
         assert a.pairs == b.pairs and a.chrA_present == b.chrA_present
-        assert (a.names, a.samples, a.ori_table) == (b.names, b.samples, b.ori_table)
+        assert (list(a.names), a.samples, a.ori_table) == (list(b.names), b.samples, b.ori_table)
         for f in PackedSignals.FIELDS:
             assert np.array_equal(getattr(a, f), getattr(b, f)), f
 
@@ -146,7 +146,10 @@ def test_tab_column_reader_equals_line_reader(tmp_path):
             for is_mp in (False, True):
                 args = (os.path.join(GOLDEN, "cluster_case%d" % case), a["chromosomes"], a["contig_length"], a["samples"],
                         is_mp, a["min_contig"], a["skip_assembly"])
-                same(PackedSignals.from_tab(*args, fast=True), PackedSignals.from_tab(*args, fast=False))
+                same(PackedSignals.from_tab(*args, fast="columns"), PackedSignals.from_tab(*args, fast=False))
+                native = PackedSignals._from_tab_native(*args)         # libtdt_tab.so: same arrays, same tables
+                assert native is not None
+                same(native, PackedSignals.from_tab(*args, fast=False))
         assert used and all(how == "columns" for _, how in used)
         # irregular variants of case 0: each must fall back for that file only and still agree
         exp = load_json("cluster_case0_expected.json")
@@ -163,8 +166,68 @@ def test_tab_column_reader_equals_line_reader(tmp_path):
             open(path, "w").writelines(edit(lines))
             del used[:]
             args = (dst, a["chromosomes"], a["contig_length"], a["samples"], a["is_mp"], a["min_contig"], a["skip_assembly"])
+            same(PackedSignals.from_tab(*args, fast="columns"), PackedSignals.from_tab(*args, fast=False))
             same(PackedSignals.from_tab(*args, fast=True), PackedSignals.from_tab(*args, fast=False))
             if stem == "discordants":      # (the C parser takes longer split lines as they are: extra fields are unused)
                 assert ("%s_%s.tab" % (stem, sample), "lines") in used
+                assert PackedSignals._from_tab_native(*args) is None      # blank-padded field: not taken natively
+            else:
+                assert PackedSignals._from_tab_native(*args) is not None   # longer split lines are regular for the scanner
     finally:
         signals._part_from_columns = orig
+
+
+def test_tab_scanner_irregular_and_errors(tmp_path):
+    """libtdt_tab.so: what it must refuse (the line reader then decides) and what it must report like the reference."""
+    from tiddit_b200 import tabio
+    from tiddit_b200.signals import PackedSignals
+    good_d = "r1\tc1\tc2\t10\t110\tFalse\t500\t600\tTrue\n"
+    good_s = "r2\tc1\tc1\t40\tTrue\t90\tFalse\t1\t40\t90\t130\n"
+
+    def parse(text, kind):
+        path = str(tmp_path / "x.tab")
+        with open(path, "w", newline="") as f:
+            f.write(text)
+        ts = tabio.TabSet()
+        try:
+            lo, hi = ts.parse(path, kind)
+            return hi - lo, ts.col_i64(0).tolist(), ts.table(0), ts.table(1), ts.table(2)
+        finally:
+            ts.close()
+
+    assert parse(good_d * 3, "discordants") == (3, [10, 10, 10], ["r1"], ["c1", "c2"], ["False", "True"])
+    assert parse(good_d.rstrip("\n"), "discordants")[0] == 1                      # no newline at the end of the file
+    assert parse("", "discordants")[0] == 0
+    assert parse(good_s + good_s.rstrip("\n") + "\tx\ty\n", "splits")[0] == 2       # further fields are ignored
+    for bad in (good_d + "\n", good_d.replace("\n", "\r\n"), good_d.replace("10\t", "1e1\t", 1), good_d.replace("r1", " r1"),
+                good_d.replace("c2", ""), good_d.rstrip("\n") + "\textra\n", "\t".join(good_d.split("\t")[:8]) + "\n",
+                good_d.replace("110", "1_10"), good_d.replace("500", "99999999999999999999")):
+        with pytest.raises(tabio.IrregularTab):
+            parse(bad, "discordants")
+    with pytest.raises(tabio.IrregularTab):
+        parse("\t".join(good_s.split("\t")[:10]) + "\n", "splits")
+    with pytest.raises(OSError):
+        tabio.TabSet().parse(str(tmp_path / "missing.tab"), "splits")
+    # an unknown contig is the reference's KeyError (contig_length[chrA], tiddit_cluster.pyx:52)
+    os.makedirs(str(tmp_path / "k_tiddit"))
+    for stem, text in (("discordants", good_d), ("splits", good_s)):
+        with open(str(tmp_path / "k_tiddit" / ("%s_S.tab" % stem)), "w") as f:
+            f.write(text)
+    with pytest.raises(KeyError):
+        PackedSignals.from_tab(str(tmp_path / "k"), ["c1"], {"c1": 1000}, ["S"], False, 0, True)
+    pk = PackedSignals.from_tab(str(tmp_path / "k"), ["c1", "c2"], {"c1": 1000, "c2": 550}, ["S"], False, 0, True)
+    assert len(pk) == 2 and pk.pairs == [("c1", "c1"), ("c1", "c2")] and pk.posB.tolist() == [90, 500]
+    with pytest.raises(FileNotFoundError):
+        PackedSignals.from_tab(str(tmp_path / "nothing"), ["c1"], {"c1": 1000}, ["S"], False, 0, True)
+
+
+def test_tab_header_symbols_exported():
+    import re
+    from tiddit_b200 import build, tabio
+    build.build_tab()
+    text = open(os.path.join(os.path.dirname(GOLDEN), "..", "include", "tdt_tab.h")).read()
+    names = sorted(set(re.findall(r"TDT_TAB_API[^;(]*?\b(tdt_tab_[a-z0-9_]+)\s*\(", text)))
+    assert names == sorted(tabio.TAB_SIGNATURES)
+    L = tabio.tab_lib()
+    for n in names:
+        assert hasattr(L, n)

@@ -12,6 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libtdt_b200.so")
 BAM_LIB = os.path.join(HERE, "libtdt_bam.so")
+TAB_LIB = os.path.join(HERE, "libtdt_tab.so")
 SOURCES = ["tdt_api.cu", "tdt_cluster.cu", "tdt_aggregate.cu", "tdt_coverage.cu", "tdt_ploidy.cu", "tdt_gc.cu", "tdt_peer.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC,-O3,-fvisibility=hidden", "--expt-relaxed-constexpr"]
@@ -28,7 +29,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f != "tdt_bam.cpp"] + [os.path.join(HERE, "..", "include", "tdt_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f not in ("tdt_bam.cpp", "tdt_tab.cpp")] + [os.path.join(HERE, "..", "include", "tdt_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -43,9 +44,21 @@ def build_bam(force=False):
     return BAM_LIB
 
 
+def build_tab(force=False):
+    """g++ -O3 -shared: the signal tab-file scanner (host code only; include/tdt_tab.h)."""
+    src = os.path.join(CSRC, "tdt_tab.cpp")
+    hdr = os.path.join(HERE, "..", "include", "tdt_tab.h")
+    if not force and os.path.exists(TAB_LIB) and os.path.getmtime(TAB_LIB) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+        return TAB_LIB
+    subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
+                           "-Wall", "-o", TAB_LIB, src, "-lpthread"])
+    return TAB_LIB
+
+
 def build(force=False, verbose=False, out=None, build_dir=None):
     """out / build_dir: build a variant (TDT_NVCC_DEFS) next to the default library without touching it."""
     build_bam(force)
+    build_tab(force)
     if out is None and not force and not _stale():
         return LIB
     objs = []

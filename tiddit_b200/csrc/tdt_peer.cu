@@ -27,6 +27,10 @@
 namespace tdt {
 
 constexpr int PX_THREADS = 512;
+#ifndef TDT_PX_UNROLL
+#define TDT_PX_UNROLL 4
+#endif
+constexpr int PX_UNROLL = TDT_PX_UNROLL;
 constexpr int PX_MAX_RANKS = 16;
 constexpr int PX_FLAG_STRIDE = 32;   // u32 words (128 B) between two flags
 constexpr int PX_ERR_TIMEOUT = 77;
@@ -64,12 +68,24 @@ __global__ void __launch_bounds__(PX_THREADS) peer_allgather_kernel(const PeerAr
     const int64_t nvec = a.slot / 4;
     const uint4 *src = reinterpret_cast<const uint4 *>(mine + a.slot * a.rank);
     const int64_t stride = (int64_t)gridDim.x * PX_THREADS;
-    for (int64_t i = (int64_t)blockIdx.x * PX_THREADS + threadIdx.x; i < nvec; i += stride) {
-        const uint4 v = src[i];
+    // PX_UNROLL vectors per thread and round: all loads first, then the (nranks - 1) * PX_UNROLL remote stores -- posted
+    // writes, so the more of them are in flight per thread the closer the NVLink ports run to their rate
+    for (int64_t i0 = (int64_t)blockIdx.x * PX_THREADS + threadIdx.x; i0 < nvec; i0 += stride * PX_UNROLL) {
+        uint4 v[PX_UNROLL];
+#pragma unroll
+        for (int u = 0; u < PX_UNROLL; u++) {
+            const int64_t i = i0 + (int64_t)u * stride;
+            if (i < nvec) v[u] = src[i];
+        }
 #pragma unroll 1
         for (int d = 1; d < a.nranks; d++) {
             const int p = (a.rank + d) % a.nranks;
-            reinterpret_cast<uint4 *>(a.buf[p] + a.slot * a.rank)[i] = v;
+            uint4 *dst = reinterpret_cast<uint4 *>(a.buf[p] + a.slot * a.rank);
+#pragma unroll
+            for (int u = 0; u < PX_UNROLL; u++) {
+                const int64_t i = i0 + (int64_t)u * stride;
+                if (i < nvec) dst[i] = v[u];
+            }
         }
     }
     __threadfence_system();

@@ -89,16 +89,16 @@ static inline SSLayout ss_layout(void *temp, int64_t n, int64_t nseg_max) {
     p += ss_align((size_t)L.tiles_max * 256 * 4);
     L.win_cnt = (uint32_t *)p;
     p += ss_align((size_t)L.nwin * 4);
-    L.win_hi = (int32_t *)p;  // 0xff.. = -1 : "no small segment starts here"
+    L.win_hi = (int32_t *)p;  // (largest small segment that starts in the window) + 1; 0 = none
     p += ss_align((size_t)L.nwin * 4);
-    L.win_lo = (int32_t *)p;  // 0x7f.. : +inf
+    L.win_lo = (int32_t *)p;  // INT32_MAX - (smallest small segment that starts in the window); 0 = none
     p += ss_align((size_t)L.nwin * 4);
+    L.zero_bytes = (size_t)(p - (char *)temp);  // counters, status, the three window arrays: one memset
     L.large = (SSLarge *)p;
     p += ss_align((size_t)L.nlarge_max * sizeof(SSLarge));
     L.tile_seg = (int32_t *)p;
     p += ss_align((size_t)L.tiles_max * 4);
     L.ghist = (uint32_t *)p;
-    L.zero_bytes = (size_t)((char *)L.win_hi - (char *)temp);  // counters, status, win_cnt
     return L;
 }
 
@@ -148,15 +148,19 @@ __global__ void segsort_classify_kernel(SSArgs a) {
         const uint32_t peers = __match_any_sync(act, k);
         const uint32_t total = __reduce_add_sync(peers, (uint32_t)size);
         if ((peers & lanemask_lt()) == 0u) {
-            atomicMin(a.L.win_lo + k, (int32_t)s);
+            atomicMax(a.L.win_lo + k, 0x7fffffff - (int32_t)s);
             atomicAdd(a.L.win_cnt + k, total);
         }
-        if ((peers >> lane) == 1u) atomicMax(a.L.win_hi + k, (int32_t)s);
+        if ((peers >> lane) == 1u) atomicMax(a.L.win_hi + k, (int32_t)s + 1);
     }
-    if (size > SS_LOCAL_MAX) {
-        const int32_t idx = atomicAdd(&a.L.cnt->n_large, 1);
-        const int32_t nt = (int32_t)((size + SS_TILE - 1) / SS_TILE);
-        const int32_t tb = atomicAdd(&a.L.cnt->n_tiles, nt);
+    // large segments (rare): the whole warp writes the tile -> segment entries and zeroes the digit histograms of
+    // each one its lanes found (this was a kernel of its own, one more launch on the critical path of every sort)
+    const bool large = size > SS_LOCAL_MAX;
+    int32_t idx = 0, tb = 0, nt = 0;
+    if (large) {
+        idx = atomicAdd(&a.L.cnt->n_large, 1);
+        nt = (int32_t)((size + SS_TILE - 1) / SS_TILE);
+        tb = atomicAdd(&a.L.cnt->n_tiles, nt);
         SSLarge rec;
         rec.start = q;
         rec.size = size;
@@ -164,9 +168,20 @@ __global__ void segsort_classify_kernel(SSArgs a) {
         rec.pad = 0;
         a.L.large[idx] = rec;
     }
+    u32 todo = __ballot_sync(0xffffffffu, large);
+    while (todo) {
+        const int src = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int32_t i2 = __shfl_sync(0xffffffffu, idx, src), t2 = __shfl_sync(0xffffffffu, tb, src);
+        const int32_t n2 = __shfl_sync(0xffffffffu, nt, src);
+        for (int32_t t = lane; t < n2; t += 32) a.L.tile_seg[t2 + t] = i2;
+        uint32_t *h = a.L.ghist + (size_t)i2 * SS_MAX_PASSES * 256;
+        for (int i = lane; i < SS_MAX_PASSES * 256; i += 32) h[i] = 0u;
+    }
 }
 
-// one CTA per large segment: its tile -> segment entries and its zeroed digit histograms
+// one CTA per large segment: its tile -> segment entries and its zeroed digit histograms (callers that queue large
+// segments themselves -- the sample sort's leftovers -- still use it)
 __global__ void __launch_bounds__(256) segsort_fill_kernel(SSArgs a) {
     const int idx = blockIdx.x;
     if (idx >= a.L.cnt->n_large) return;
@@ -410,7 +425,7 @@ __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
             if (bw0 >= nround) break;
             next = bw1;
             const int64_t k0 = round + bw0, k1 = round + bw1;  // windows [k0, k1); both ends populated
-            const int32_t lo_s = a.L.win_lo[k0], hi_s = a.L.win_hi[k1 - 1];
+            const int32_t lo_s = 0x7fffffff - a.L.win_lo[k0], hi_s = a.L.win_hi[k1 - 1] - 1;
             const int64_t wbase = k0 * SS_WINDOW;
             // ---- A: the small segments of the batch, their compact layout (size sum << 16 | count) ----
             for (int64_t s0 = lo_s; s0 <= hi_s; s0 += SS_LTHREADS) {
@@ -741,10 +756,7 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     a.L = ss_layout(temp, n_max, nseg_max);
     a.err = err;
     TDT_CUDA(cudaMemsetAsync(temp, 0, a.L.zero_bytes, st));
-    TDT_CUDA(cudaMemsetAsync(a.L.win_hi, 0xff, (size_t)a.L.nwin * 4, st));
-    TDT_CUDA(cudaMemsetAsync(a.L.win_lo, 0x7f, (size_t)a.L.nwin * 4, st));
     TDT_LAUNCH(segsort_classify_kernel, (unsigned)((nseg_max + 255) / 256), 256, 0, st, a);
-    TDT_LAUNCH(segsort_fill_kernel, (unsigned)a.L.nlarge_max, 256, 0, st, a);
     static thread_local bool configured = false;
     if (!configured) {
         TDT_CUDA(cudaFuncSetAttribute(segsort_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
