@@ -1173,11 +1173,13 @@ static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, 
     const int64_t gmax = PLAIN ? (int64_t)plain_cluster_id + 1 : pl.gmax;
     {
         ProfScope ps("sort_y", st);
+        const bool fused_heads = segsort_want_heads(b.headsY);   // the sort's classify kernel walks the segments anyway
         int rc = segsort_pairs(b.ykey, b.yval, b.xs, b.xv, b.tmpK, b.tmpV, b.goff, (const int64_t *)&b.small->dims_y,
                                b.gx, n, gmax, key_bits, b.sort_temp, pl.sort, &b.small->err, st);
         if (rc) return rc;
-        TDT_LAUNCH(heads_from_offsets_kernel, (unsigned)((gmax + 255) / 256), 256, 0, st, b.goff, &b.small->dims_y,
-                   b.headsY);
+        if (!fused_heads)
+            TDT_LAUNCH(heads_from_offsets_kernel, (unsigned)((gmax + 255) / 256), 256, 0, st, b.goff, &b.small->dims_y,
+                       b.headsY);
     }
     WRParams p = {};
     p.keys = b.xs;
@@ -1248,12 +1250,14 @@ static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t 
     TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &b.small->dims_x, n, (int64_t)P, b.small->off2);
 
     const int32_t *xv = nullptr;
+    bool heads_done = false;
     if (presorted_plain) {
         // DBSCAN.main on the caller's order: no sort, identity permutation, one segment
         TDT_LAUNCH(pack_plain_kernel, grid_for(n, 256), 256, 0, st, posA, n, max_pos, b.xs, &b.small->err);
         seg_off = b.small->off2;
     } else {
         ProfScope ps("sort_x", st);
+        heads_done = segsort_want_heads(b.headsX);
         // posA as unsigned keys: a negative coordinate has bit 31 set and trips the key-range check
         int rc = segsort_pairs((const u32 *)posA, nullptr, b.xs, b.xv, b.tmpK, b.tmpV, seg_off,
                                (const int64_t *)&b.small->dims_x, nullptr, n, P, key_bits, b.sort_temp, pl.sort,
@@ -1261,7 +1265,8 @@ static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t 
         if (rc) return rc;
         xv = b.xv;
     }
-    TDT_LAUNCH(heads_from_offsets_kernel, (unsigned)((P + 255) / 256), 256, 0, st, seg_off, &b.small->dims_x, b.headsX);
+    if (!heads_done)
+        TDT_LAUNCH(heads_from_offsets_kernel, (unsigned)((P + 255) / 256), 256, 0, st, seg_off, &b.small->dims_x, b.headsX);
 
     WRParams p = {};
     p.keys = b.xs;

@@ -112,6 +112,7 @@ struct SSArgs {
     const int64_t *off;    // [nseg + 1], device
     const int64_t *dims;   // device: dims[0] = n, dims[1] = nseg (actual values; the grids use upper bounds)
     const int32_t *segid;  // optional: segment of every element (enables the tiny-segment path)
+    uint32_t *heads_out;   // optional: bit q set for the first element q of every non-empty segment (zeroed by the caller)
     int tiny_max;          // segments up to this size go through the tiny path (0 without segid)
     int key_bits, n_passes, bits_per_pass;
     SSLayout L;
@@ -129,7 +130,20 @@ int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *key
                   int64_t n_max, int64_t nseg_max, int key_bits, void *temp, size_t temp_bytes, int *err,
                   cudaStream_t st);
 
+// Callers that run several sorts concurrently (parallel branches of one call) give every branch its own forked side
+// stream: segsort_set_branch(b), b in [0, SS_BRANCHES), before each segsort_pairs (thread-local, default 0).
+constexpr int SS_BRANCHES = 4;
+void segsort_set_branch(int b);
+// The next segsort_pairs call of this thread also sets, in the zeroed bitmask `heads`, the bit of the first element of
+// every non-empty segment (what the range-query kernels read); returns false when the active sort generation cannot
+// (the caller then launches its own kernel).
+bool segsort_want_heads(uint32_t *heads);
+
 #ifdef TDT_SEGSORT_IMPL
+static thread_local int g_ss_branch = 0;
+static thread_local uint32_t *g_ss_heads_out = nullptr;   // set by segsort_want_heads for the NEXT segsort_pairs call
+void segsort_set_branch(int b) { g_ss_branch = b >= 0 && b < SS_BRANCHES ? b : 0; }
+
 // ---- classification: windows of the small segments, tile ranges of the large ones -----------------
 __global__ void segsort_classify_kernel(SSArgs a) {
     const int64_t nseg = a.dims[1];
@@ -139,6 +153,15 @@ __global__ void segsort_classify_kernel(SSArgs a) {
     if (s < nseg) {
         q = a.off[s];
         size = a.off[s + 1] - q;
+    }
+    {   // the caller's segment-head bitmask (a kernel of its own until r02): one atomic per group of lanes
+        const bool has = a.heads_out != nullptr && size > 0;
+        const uint32_t hact = __ballot_sync(0xffffffffu, has);
+        if (has) {
+            const uint32_t peers = __match_any_sync(hact, q >> 5);
+            const uint32_t bits = __reduce_or_sync(peers, 1u << (q & 31));
+            if ((peers & lanemask_lt()) == 0u) atomicOr(a.heads_out + (q >> 5), bits);
+        }
     }
     const bool small = size > a.tiny_max && size <= SS_LOCAL_MAX;
     // consecutive segments mostly start in the same window: one atomic pair per group of lanes
@@ -733,6 +756,8 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
                          uint32_t *keys_tmp, int32_t *vals_tmp, const int64_t *off, const int64_t *dims,
                          const int32_t *segid, int64_t n_max, int64_t nseg_max, int key_bits, void *temp,
                          size_t temp_bytes, int *err, cudaStream_t st) {
+    uint32_t *heads_out = g_ss_heads_out;
+    g_ss_heads_out = nullptr;
     if (n_max <= 0 || nseg_max <= 0) return TDT_OK;
     if (temp_bytes < segsort1_temp_bytes(n_max, nseg_max))
         return fail(TDT_E_WORKSPACE, "segmented sort needs %zu bytes of temporary storage, %zu reserved",
@@ -749,6 +774,7 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     a.off = off;
     a.dims = dims;
     a.segid = segid;
+    a.heads_out = heads_out;
     a.tiny_max = segid ? 32 : 0;
     a.key_bits = key_bits;
     a.n_passes = (key_bits + 7) / 8;
@@ -774,11 +800,12 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
 #endif
     cudaStream_t side = st;
 #if TDT_SS_FORK
-    static thread_local cudaStream_t side_streams[16] = {};
-    static thread_local cudaEvent_t fork_ev[16] = {}, join_ev[16] = {};
+    static thread_local cudaStream_t side_streams[16 * SS_BRANCHES] = {};
+    static thread_local cudaEvent_t fork_ev[16 * SS_BRANCHES] = {}, join_ev[16 * SS_BRANCHES] = {};
     int dev_id = 0;
     TDT_CUDA(cudaGetDevice(&dev_id));
     if (dev_id >= 0 && dev_id < 16) {
+        dev_id = dev_id * SS_BRANCHES + g_ss_branch;   // one side stream per (device, branch)
         if (!side_streams[dev_id]) {
             TDT_CUDA(cudaStreamCreateWithFlags(&side_streams[dev_id], cudaStreamNonBlocking));
             TDT_CUDA(cudaEventCreateWithFlags(&fork_ev[dev_id], cudaEventDisableTiming));

@@ -691,11 +691,12 @@ static int segsort2_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint3
     }
     // the LSD chain for whatever two rounds could not cut (a side branch: it touches other segments than the finish kernel)
     cudaStream_t side = st;
-    static thread_local cudaStream_t side_streams[16] = {};
-    static thread_local cudaEvent_t fork_ev[16] = {}, join_ev[16] = {};
+    static thread_local cudaStream_t side_streams[16 * SS_BRANCHES] = {};
+    static thread_local cudaEvent_t fork_ev[16 * SS_BRANCHES] = {}, join_ev[16 * SS_BRANCHES] = {};
     int dev_id = 0;
     TDT_CUDA(cudaGetDevice(&dev_id));
     if (rounds && dev_id >= 0 && dev_id < 16) {
+        dev_id = dev_id * SS_BRANCHES + g_ss_branch;
         if (!side_streams[dev_id]) {
             TDT_CUDA(cudaStreamCreateWithFlags(&side_streams[dev_id], cudaStreamNonBlocking));
             TDT_CUDA(cudaEventCreateWithFlags(&fork_ev[dev_id], cudaEventDisableTiming));
@@ -754,6 +755,13 @@ static int segsort2_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint3
         TDT_CUDA(cudaStreamWaitEvent(st, join_ev[dev_id], 0));
     }
     return TDT_OK;
+}
+
+bool segsort_want_heads(uint32_t *heads) {
+    const char *e = getenv("TDT_SEGSORT_V2");
+    if (e && e[0] == '1') return false;
+    g_ss_heads_out = heads;
+    return true;
 }
 
 // The entry every caller uses.  The LSD sort of tdt_segsort.cuh is the production path; TDT_SEGSORT_V2=1 in the
