@@ -123,9 +123,19 @@ __device__ __forceinline__ u32 lanemask_le() {
 // Single-pass chained scan ("decoupled look-back") over tiles, two 31-bit sums per tile.
 //   status[t] = flag(2 bits) | a(31) | b(31) in ONE 64-bit word, so a reader always sees a
 //   consistent (flag, a, b) without fences.  flag 0 = not yet published, 1 = tile aggregate,
-//   2 = inclusive prefix.  Tiles take their index from an atomic ticket (tdt::take_ticket), so
-//   every tile with a smaller index is already resident and publishes its aggregate before it
-//   waits on anybody: the look-back cannot deadlock whatever order the hardware starts CTAs in.
+//   2 = inclusive prefix.
+//   FORWARD PROGRESS.  A tile publishes its own aggregate BEFORE it waits on anybody and only ever waits on tiles
+//   with a SMALLER index.  Two ways of numbering tiles are in use:
+//     * an atomic ticket (group_extra_scan_kernel, the aggregation scans): every smaller index belongs to a CTA
+//       that is already running -- safe whatever order the hardware starts CTAs in;
+//     * blockIdx.x (window_runs_kernel / window_runs_small_kernel<., false>, segsort_pass_kernel, s2_pass_kernel):
+//       this ASSUMES the hardware starts the CTAs of a grid in blockIdx order (the assumption CUB's DeviceScan made
+//       for years): a waiting tile's predecessors then have a lower blockIdx and are resident or finished.  The
+//       persistent sort passes (grid capped at the resident-CTA count, CTA b takes tiles b, b + grid, ...) keep it:
+//       tile t waits on tiles < t, which belong to CTAs with a smaller blockIdx in the same or an earlier round.
+//       The cap is computed for the pass kernel alone; when the small-segment kernels of the same sort run on the
+//       forked side stream they may delay, never block, the start of higher-numbered CTAs -- those only wait on
+//       lower-numbered ones, which were scheduled first and drain without needing anybody.
 // ----------------------------------------------------------------------------------------------
 namespace tdt {
 

@@ -3,9 +3,9 @@
 # aggregation pass, (3) full-set metrics of our kernels exported as CSV on the box (the report itself would exceed the
 # 64 MiB gpurun_out/ limit), (4) a small --import-source capture of the top kernels, (5) in-stream per-kernel times.
 mkdir -p gpurun_out
-R=${ROUND:-r01}
+R=${ROUND:-r02_v2}
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches_${R}.csv \
-    python bench.py --steps 2 --warmup 3 --no-cpu --no-graph > gpurun_out/bench_under_ncu.log 2>&1
+    python bench.py --steps 2 --warmup 3 --no-cpu --no-graph --no-tumor --main-lines 100000 --cov-reads 61765396 --bam-reads 200000 > gpurun_out/bench_under_ncu.log 2>&1
 echo "launch list rc=$?"
 SKIP=64 COUNT=32 bash tools/gpu_launches.sh
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__throughput.avg.pct_of_peak_sustained_elapsed,gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed --clock-control none -k regex:'agg_|segsort' -s 119 -c 50 --csv --log-file gpurun_out/agg_launches.csv python tools/agg_target.py > gpurun_out/agg_launches.log 2>&1
