@@ -29,9 +29,47 @@ cv, ebs = tiddit_coverage.create_coverage(header, 500, "chr21")
 tiddit_coverage.update_coverage_batch(s[:roff[1]], e[:roff[1]], 500, cv, ebs)
 seq = synth.fasta_sequence(200_003)
 assert np.array_equal(tiddit_gc.gc_bins(seq, 50, 0.5), oracle.gc_bins(seq, 50, 0.5))
+assert np.array_equal(tiddit_gc.gc_bins(seq, 7, 0.5), oracle.gc_bins(seq, 7, 0.5))
+assert np.array_equal(tiddit_gc.gc_bins(seq, 500, 0.5), oracle.gc_bins(seq, 500, 0.5))
+# the queued per-read path
+cq, eq = tiddit_coverage.create_coverage(header, 500, "chr21")
+for x, y in zip(s[:2000].tolist(), e[:2000].tolist()):
+    cq = tiddit_coverage.update_coverage(x, y, 500, cq, eq)
+want = np.zeros(len(cq)); oracle.update_coverage_batch(s[:2000], e[:2000], 500, want, eq)
+assert np.array_equal(np.asarray(cq).view(np.uint64), want.view(np.uint64))
+# one large pair (large-segment chain of the LSD sort), then the same through the sample-sort generation
+a2, b2, off2, L2 = synth.config2_signals(40_000, n_clusters=800)
+want2 = oracle.cluster_segments(a2, b2, off2, 500, 3)
+assert np.array_equal(device_ops.cluster_labels(a2, b2, off2, 500, 3, L2), want2)
+os.environ["TDT_SEGSORT_V2"] = "1"
+assert np.array_equal(device_ops.cluster_labels(a2, b2, off2, 500, 3, L2), want2)
+assert np.array_equal(device_ops.cluster_labels(a, b, off, 500, 3, L), lab)
+del os.environ["TDT_SEGSORT_V2"]
 print("sanitizer target ok")
 PY
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 python /tmp/san_target.py > gpurun_out/sanitize_$tool.log 2>&1
   echo "$tool rc=$?"; grep -E "ERROR SUMMARY|RACECHECK SUMMARY|sanitizer target ok|hazard" gpurun_out/sanitize_$tool.log | tail -4
 done
+
+# the peer-memory label exchange (needs 2 GPUs): memcheck over both ranks
+if [ "$(nvidia-smi -L | wc -l)" -ge 2 ]; then
+cat > /tmp/san_peer.py <<'PY'
+import os, sys
+sys.path.insert(0, os.getcwd())
+import numpy as np, torch, torch.distributed as dist
+rank = int(os.environ["RANK"]); torch.cuda.set_device(rank)
+dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+from tiddit_b200 import engine, synth
+from oracle import oracle
+os.environ["TDT_LABEL_EXCHANGE"] = "p2p"
+a, b, off, L = synth.wgs30x_signals(80_000)
+for _ in range(3):
+    got = engine.sharded_labels(a, b, off, 500, 3, L)
+assert np.array_equal(got, oracle.cluster_segments(a, b, off, 500, 3))
+dist.barrier(); dist.destroy_process_group()
+print("peer target ok", rank)
+PY
+  timeout 900 compute-sanitizer --tool memcheck --target-processes all --error-exitcode 9 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29533 /tmp/san_peer.py > gpurun_out/sanitize_peer_memcheck.log 2>&1
+  echo "peer memcheck rc=$?"; grep -E "ERROR SUMMARY|peer target ok" gpurun_out/sanitize_peer_memcheck.log | tail -6
+fi
