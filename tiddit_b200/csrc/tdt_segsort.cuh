@@ -282,19 +282,39 @@ __device__ __forceinline__ uint32_t ss_match(uint32_t *mm, uint32_t d, bool vali
 #define TDT_SS_ATOMIC_RANK 1
 #endif
 
-// count phase: warp-private digit histograms of the warp's own run of the tile; info[] keeps the match result
+// TDT_SS_FUSED_RANK (default, r02): the count phase already yields every element's rank inside its warp -- the group
+// leader's atomicAdd on the warp-private counter RETURNS the number of equal digits the warp has seen before this chunk,
+// handed to the group by shuffle -- so the scatter phase is a plain shared-memory load of the (warp, digit) base instead
+// of a second round of leader atomics: two shared-memory atomics per element and pass (match + count) instead of three.
+// The passes do not speed up with more resident CTAs (r01: 3, 4 or 6 per SM give the same time), i.e. they are bound
+// by the shared-memory pipe these atomics go through.
+#ifndef TDT_SS_FUSED_RANK
+#define TDT_SS_FUSED_RANK 1
+#endif
+constexpr uint32_t SS_NO_ELEM = 0xffffffffu;
+
+// count phase: warp-private digit histograms of the warp's own run of the tile.
+// info[c]: FUSED_RANK: the element's rank among the warp's elements with the same digit (SS_NO_ELEM = no element);
+//          otherwise the match result (lanes of the chunk holding the same digit, 0 = no element).
 template <int CHUNKS, typename DigitFn>
 __device__ __forceinline__ void ss_count(int count, int epw, uint32_t *wh, uint32_t *mm, uint32_t (&info)[CHUNKS],
                                          int bits, DigitFn digit) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
     for (int c = 0; c < CHUNKS; c++) {
-        info[c] = 0u;
+        info[c] = TDT_SS_FUSED_RANK ? SS_NO_ELEM : 0u;
         if (c * 32 < epw) {
             const int e = warp * epw + c * 32 + lane;
             const bool valid = e < count;
             const uint32_t d = valid ? digit(e, c) : 0u;
             const uint32_t peers = ss_match(mm, d, valid, bits);
+#if TDT_SS_FUSED_RANK
+            const uint32_t rank = __popc(peers & lanemask_lt());
+            uint32_t before = 0;
+            if (valid && rank == 0u) before = atomicAdd(&wh[d], (uint32_t)__popc(peers));
+            before = __shfl_sync(0xffffffffu, before, valid ? (__ffs(peers) - 1) : lane);
+            if (valid) info[c] = before + rank;
+#else
             if (valid) {
                 info[c] = peers;
                 if ((peers & lanemask_lt()) == 0u) {
@@ -306,11 +326,12 @@ __device__ __forceinline__ void ss_count(int count, int epw, uint32_t *wh, uint3
                 }
             }
             __syncwarp();
+#endif
         }
     }
 }
 
-// scatter phase: stable position of every element; wh[d] holds the running base of (this warp, digit).
+// scatter phase: stable position of every element; wh[d] holds the base of (this warp, digit).
 // digit(e, c) must return what it returned in the count phase.
 template <int CHUNKS, typename DigitFn, typename EmitFn>
 __device__ __forceinline__ void ss_scatter(int epw, uint32_t *wh, const uint32_t (&info)[CHUNKS], DigitFn digit,
@@ -319,6 +340,10 @@ __device__ __forceinline__ void ss_scatter(int epw, uint32_t *wh, const uint32_t
 #pragma unroll
     for (int c = 0; c < CHUNKS; c++) {
         if (c * 32 < epw) {
+#if TDT_SS_FUSED_RANK
+            const int e = warp * epw + c * 32 + lane;
+            if (info[c] != SS_NO_ELEM) emit(e, c, wh[digit(e, c)] + info[c]);
+#else
             const uint32_t peers = info[c];
             const bool valid = peers != 0u;
             const int e = warp * epw + c * 32 + lane;
@@ -335,6 +360,7 @@ __device__ __forceinline__ void ss_scatter(int epw, uint32_t *wh, const uint32_t
             __syncwarp();
 #endif
             if (valid) emit(e, c, base + rank);
+#endif
         }
     }
 }
