@@ -593,7 +593,7 @@ def medians_leg(torch, args, hbm_peak, flush):
     out = {"bins": n, "contigs": len(nb), "ms_per_step": ms, "bins_per_sec": n / ms * 1e3,
            "roofline": {"bound": "hbm", "achieved": 9.0 * n / ms / 1e6, "peak": hbm_peak, "unit": "GB/s",
                         "frac": 9.0 * n / ms / 1e6 / hbm_peak,
-                        "algorithmic_bytes": "9 B/bin (float64 coverage + int8 GC), read once; the radix select streams them several times"}}
+                        "algorithmic_bytes": "9 B/bin (float64 coverage + int8 GC), read once; the radix select streams them 3 times (2 digit passes + 1 compaction of the prefix buckets)"}}
     # e2e: the arrays on the host (as tiddit_signal.main / tiddit_gc.main return them) -> medians on the host
     cov_h, gc_h = cov.cpu().numpy(), gc.cpu().numpy()
     ts = []

@@ -45,6 +45,32 @@ def test_medians_random_vs_oracle(n_contigs, max_bins, seed, oracle):
     assert np.array_equal(got_m.view(np.uint64), want_m.view(np.uint64))   # bit-exact, nan included
 
 
+@pytest.mark.parametrize("kind", ["all_equal_over_capacity", "ties_within_capacity", "two_values", "continuous"])
+def test_medians_compaction_and_fallback(kind, oracle):
+    """After two digit passes the prefix buckets are copied out and the remaining passes run on the copies; when the
+    buckets together exceed the reserved 4 M keys (nearly all bins equal) the streaming passes run instead -- both
+    ways must give numpy's median bit for bit, including the value after the lower median."""
+    from tiddit_b200 import device_ops
+    rng = np.random.default_rng(11)
+    sizes = [2_600_000, 1_400_001, 7, 0, 999_999]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(off[-1])
+    if kind == "all_equal_over_capacity":
+        cov = np.full(n, 29.875)                                           # every bin in one bucket: 2 x 5 M keys > 4 M
+    elif kind == "ties_within_capacity":
+        cov = rng.integers(1, 2000, n).astype(np.float64) / 64.0           # ~2000 distinct values, exact ties
+    elif kind == "two_values":
+        cov = np.where(rng.random(n) < 0.5, 30.0, np.nextafter(30.0, 31.0))   # the upper median differs in the last bit
+    else:
+        cov = rng.gamma(9.0, 3.3, n)
+    cov[rng.random(n) < 0.1] = 0.0
+    gc = rng.integers(-1, 60, n).astype(np.int8)
+    got_m, got_c = device_ops.coverage_medians(cov, gc, off)
+    want_m, want_c = oracle.coverage_medians(cov, gc, off)
+    assert np.array_equal(got_c, want_c)
+    assert np.array_equal(got_m.view(np.uint64), want_m.view(np.uint64))
+
+
 def test_medians_value_after_the_lower_median_known_answers(oracle):
     """Even counts: the upper median may sit in the same last digit, in a later digit of the last histogram, or in a far
     bucket (other exponent) -- the three places the kernels look for it -- and differs between a contig and the genome."""
