@@ -5,13 +5,16 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["lsd", "samplesort"], autouse=True)
+@pytest.fixture(params=["msd", "lsd", "samplesort"], autouse=True)
 def sort_generation(request, monkeypatch):
-    """Every test runs on the production LSD sort and on the sample-sort generation (tdt_segsort2.cuh, opt-in)."""
+    """Every test runs on the production sort (generation 3: MSD rounds + shared-memory finish, tdt_segsort3.cuh), on the
+    LSD chain it replaced (TDT_SEGSORT=lsd) and on the sample-sort generation (tdt_segsort2.cuh, TDT_SEGSORT_V2=1)."""
+    monkeypatch.delenv("TDT_SEGSORT_V2", raising=False)
+    monkeypatch.delenv("TDT_SEGSORT", raising=False)
     if request.param == "samplesort":
         monkeypatch.setenv("TDT_SEGSORT_V2", "1")
-    else:
-        monkeypatch.delenv("TDT_SEGSORT_V2", raising=False)
+    elif request.param == "lsd":
+        monkeypatch.setenv("TDT_SEGSORT", "lsd")
     return request.param
 
 
@@ -113,6 +116,42 @@ def test_segsort_skewed_distributions(kind):
     got_k, got_v = _run(keys, vals, off, 28)
     assert np.array_equal(got_k, want_k)
     assert np.array_equal(got_v, want_v)
+    # value = element index (the posA sort): the finish kernel breaks ties by value instead of by position
+    got_k2, got_v2 = _run(keys, None, off, 28)
+    want_k2, want_v2 = _expect(keys, np.arange(n, dtype=np.int32), off)
+    assert np.array_equal(got_k2, want_k2) and np.array_equal(got_v2, want_v2)
+
+
+@pytest.mark.parametrize("key_bits", [5, 12, 16, 20, 24, 28, 32])
+@pytest.mark.parametrize("kind", ["uniform", "narrow", "all_equal", "hot", "clustered"])
+def test_segsort_rounds_and_levels(kind, key_bits):
+    """Generation 3: every number of partition rounds (1-4), ranges that end in the scratch buffers (copy batches),
+    batches finished in place, crowded slots (bitonic path), sizes around the batch capacity."""
+    rng = np.random.default_rng(key_bits * 7 + len(kind))
+    sizes = [8191, 8192, 8193, 16384, 16385, 2049, 300_000, 0, 9000, 70_000, 1_300_000]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(off[-1])
+    hi = 1 << key_bits
+    keys = rng.integers(0, hi, n, dtype=np.int64)
+    if kind == "narrow":
+        keys = (hi // 3) + rng.integers(0, min(hi - hi // 3, 40), n)
+    elif kind == "all_equal":
+        keys[:] = hi - 1
+    elif kind == "hot":
+        hot = rng.random(n) < 0.7
+        keys[hot] = (hi // 2) + rng.integers(0, min(hi // 2, 3), int(hot.sum()))
+    elif kind == "clustered":
+        centres = rng.integers(0, hi, 2000, dtype=np.int64)
+        keys = np.clip(centres[rng.integers(0, 2000, n)] + rng.integers(-100, 100, n), 0, hi - 1)
+    keys = keys.astype(np.uint32)
+    vals = rng.permutation(n).astype(np.int32)
+    want_k, want_v = _expect(keys, vals, off)
+    got_k, got_v = _run(keys, vals, off, key_bits)
+    assert np.array_equal(got_k, want_k)
+    assert np.array_equal(got_v, want_v)
+    got_k2, got_v2 = _run(keys, None, off, key_bits)
+    want_k2, want_v2 = _expect(keys, np.arange(n, dtype=np.int32), off)
+    assert np.array_equal(got_k2, want_k2) and np.array_equal(got_v2, want_v2)
 
 
 def test_segsort_key_range_error():

@@ -1145,6 +1145,7 @@ static int err_to_code(int e) {
         case ERR_NONE: return TDT_OK;
         case ERR_RANGE_A: return fail(TDT_E_RANGE, "a posA / x coordinate is negative or above max_pos");
         case ERR_RANGE_B: return fail(TDT_E_RANGE, "a posB / y coordinate is negative or above max_pos");
+        case SS_ERR_INTERNAL: return fail(TDT_E_CUDA, "segmented sort: a work list overflowed (internal error)");
         default: return fail(TDT_E_RANGE, "a pair / cluster id is outside its range");
     }
 }
@@ -1474,6 +1475,7 @@ int tdt_debug_segsort(const uint32_t *keys, const int32_t *vals, const int64_t *
     Small h;
     TDT_CUDA(cudaMemcpyAsync(&h, small, sizeof(Small), cudaMemcpyDeviceToHost, st));
     TDT_CUDA(cudaStreamSynchronize(st));
+    if (h.err == SS_ERR_INTERNAL) return fail(TDT_E_CUDA, "segmented sort: a work list overflowed (internal error)");
     return h.err ? fail(TDT_E_RANGE, "a key has bits above key_bits") : TDT_OK;
 }
 

@@ -19,6 +19,8 @@
 // lanes with equal digits find each other through a shared-memory atomicOr of their lane bits, the lowest
 // lane of a group bumps the warp-private digit counter.
 #pragma once
+#include <stdlib.h>
+
 #include "tdt_common.cuh"
 
 namespace tdt {
@@ -38,6 +40,47 @@ constexpr int SS_LOCAL_CAP = 3072;         // >= SS_WINDOW - 1 + SS_LOCAL_MAX
 constexpr int SS_LCHUNKS = SS_LOCAL_CAP / SS_LTHREADS;
 constexpr int SS_MAX_PASSES = 4;
 constexpr int SS_ERR_KEY_RANGE = 1;
+constexpr int SS_ERR_INTERNAL = 64;  // a work list overflowed its (proven) bound; above every caller's own codes
+
+// third generation of the large-segment chain (tdt_segsort3.cuh): MSD partition rounds + shared-memory finish
+constexpr int M3_CAP = 8192;              // elements of a finish batch
+constexpr int M3_THREADS = 512;
+constexpr int M3_EPT = M3_CAP / M3_THREADS;
+constexpr int M3_SLOT_BITS = 13;
+constexpr int M3_NSLOT = 1 << M3_SLOT_BITS;
+constexpr int M3_ROUNDS = 4;              // 8-bit digits of a 32-bit key
+#ifndef TDT_M3_FIN_WAVES
+#define TDT_M3_FIN_WAVES 8                // finish grid = this many waves of 2 CTAs per SM (1 = persistent)
+#endif
+
+struct M3Range {   // a contiguous element range holding every element of key range [klo, klo + (256 << shift))
+    int64_t start;
+    int32_t size, tile_base;
+    uint32_t klo;
+    int32_t shift;
+    int32_t pad[2];
+};
+
+struct M3Batch {   // finish work item: `count` elements at `start`, keys in [klo, klo + (nslots << sh))
+    int64_t start;
+    int32_t count;
+    uint32_t klo;
+    int32_t sh, nslots, level, flags;
+};
+
+struct M3Counters {
+    int32_t n_rng[M3_ROUNDS], n_tiles[M3_ROUNDS], n_batches[2];
+    int32_t pad[6];
+};
+
+struct M3Layout {
+    M3Counters *cnt;
+    M3Range *rng[M3_ROUNDS];
+    int32_t *tile_rng[M3_ROUNDS];
+    uint32_t *hist[M3_ROUNDS];   // [range][256]
+    M3Batch *batch[2];           // list 0: whole segments + round-0 groups; list 1: the later rounds
+    int64_t rng_max, tiles_max, batch_max;
+};
 
 struct SSLarge {
     int64_t start, size;
@@ -68,19 +111,32 @@ static inline int64_t ss_nlarge_max(int64_t n, int64_t nseg_max) {
     return a < nseg_max ? a : (nseg_max > 0 ? nseg_max : 1);
 }
 
+static inline int64_t m3_rng_max(int64_t n) { return n / (M3_CAP + 1) + 1; }
+static inline int64_t m3_batch_max(int64_t n) { return n / SS_LOCAL_MAX + 40 * m3_rng_max(n) + 64; }
+static inline int64_t ss_tiles_max(int64_t n, int64_t nl) {
+    const int64_t r = m3_rng_max(n);
+    return n / SS_TILE + (nl > r ? nl : r) + 1;
+}
+static inline size_t m3_temp_bytes(int64_t n) {
+    const int64_t r = m3_rng_max(n), tiles = ss_tiles_max(n, 0);
+    return (size_t)M3_ROUNDS * (((size_t)r * sizeof(M3Range) + 255) / 256 * 256 + ((size_t)tiles * 4 + 255) / 256 * 256 +
+                                ((size_t)r * 256 * 4 + 255) / 256 * 256) +
+           2 * (((size_t)m3_batch_max(n) * sizeof(M3Batch) + 255) / 256 * 256) + 512;
+}
+
 static inline size_t segsort1_temp_bytes(int64_t n, int64_t nseg_max) {
     const int64_t nl = ss_nlarge_max(n, nseg_max);
-    const int64_t tiles = n / SS_TILE + nl + 1;
+    const int64_t tiles = ss_tiles_max(n, nl);
     const int64_t nwin = (n + SS_WINDOW - 1) / SS_WINDOW + 1;
     return ss_align(sizeof(SSCounters)) + ss_align((size_t)nl * sizeof(SSLarge)) + ss_align((size_t)tiles * 4) +
            3 * ss_align((size_t)nwin * 4) + ss_align((size_t)nl * SS_MAX_PASSES * 256 * 4) +
-           ss_align((size_t)tiles * 256 * 4) + 1024;
+           ss_align((size_t)tiles * 256 * 4) + m3_temp_bytes(n) + 1024;
 }
 
 static inline SSLayout ss_layout(void *temp, int64_t n, int64_t nseg_max) {
     SSLayout L;
     L.nlarge_max = ss_nlarge_max(n, nseg_max);
-    L.tiles_max = n / SS_TILE + L.nlarge_max + 1;
+    L.tiles_max = ss_tiles_max(n, L.nlarge_max);
     L.nwin = (n + SS_WINDOW - 1) / SS_WINDOW + 1;
     char *p = (char *)temp;
     L.cnt = (SSCounters *)p;
@@ -102,6 +158,26 @@ static inline SSLayout ss_layout(void *temp, int64_t n, int64_t nseg_max) {
     return L;
 }
 
+// the generation-3 arrays live behind generation 1's (the counters share the zeroed 256-byte head with SSCounters)
+static inline M3Layout m3_layout(void *temp, int64_t n, int64_t nseg_max) {
+    const SSLayout S = ss_layout(temp, n, nseg_max);
+    M3Layout M;
+    M.cnt = (M3Counters *)((char *)temp + 64);
+    M.rng_max = m3_rng_max(n);
+    M.tiles_max = ss_tiles_max(n, 0);
+    M.batch_max = m3_batch_max(n);
+    char *p = (char *)S.ghist + ss_align((size_t)S.nlarge_max * SS_MAX_PASSES * 256 * 4);
+    for (int r = 0; r < M3_ROUNDS; r++) {
+        M.rng[r] = (M3Range *)p; p += ss_align((size_t)M.rng_max * sizeof(M3Range));
+        M.tile_rng[r] = (int32_t *)p; p += ss_align((size_t)M.tiles_max * 4);
+        M.hist[r] = (uint32_t *)p; p += ss_align((size_t)M.rng_max * 256 * 4);
+    }
+    for (int l = 0; l < 2; l++) {
+        M.batch[l] = (M3Batch *)p; p += ss_align((size_t)M.batch_max * sizeof(M3Batch));
+    }
+    return M;
+}
+
 struct SSArgs {
     const uint32_t *keys_in;
     const int32_t *vals_in;  // nullptr: value = element index
@@ -116,6 +192,9 @@ struct SSArgs {
     int tiny_max;          // segments up to this size go through the tiny path (0 without segid)
     int key_bits, n_passes, bits_per_pass;
     SSLayout L;
+    int msd;               // 1: large segments go through the generation-3 chain (tdt_segsort3.cuh)
+    int m3_shift0;         // bit position of the round-0 digit
+    M3Layout m3;
     int *err;
 };
 
@@ -141,6 +220,8 @@ bool segsort_want_heads(uint32_t *heads);
 
 #ifdef TDT_SEGSORT_IMPL
 static thread_local int g_ss_branch = 0;
+static thread_local cudaEvent_t g_ss_join2_ev[16 * SS_BRANCHES] = {};   // join of the generation-3 side chain
+static thread_local int g_ss_join2_idx = 0;
 static thread_local uint32_t *g_ss_heads_out = nullptr;   // set by segsort_want_heads for the NEXT segsort_pairs call
 void segsort_set_branch(int b) { g_ss_branch = b >= 0 && b < SS_BRANCHES ? b : 0; }
 
@@ -178,6 +259,57 @@ __global__ void segsort_classify_kernel(SSArgs a) {
     }
     // large segments (rare): the whole warp writes the tile -> segment entries and zeroes the digit histograms of
     // each one its lanes found (this was a kernel of its own, one more launch on the critical path of every sort)
+    if (a.msd) {
+        // generation 3: a segment that fits one finish batch is queued as such (its keys span the whole key range);
+        // larger ones become round-0 ranges (tile -> range entries and zeroed digit counts written by the whole warp)
+        if (size > SS_LOCAL_MAX && size <= M3_CAP) {
+            const int32_t bi = atomicAdd(&a.m3.cnt->n_batches[0], 1);
+            if (bi < a.m3.batch_max) {
+                M3Batch B;
+                B.start = q;
+                B.count = (int32_t)size;
+                B.klo = 0u;
+                B.sh = a.key_bits > M3_SLOT_BITS ? a.key_bits - M3_SLOT_BITS : 0;
+                B.nslots = 1 << (a.key_bits > M3_SLOT_BITS ? M3_SLOT_BITS : a.key_bits);
+                B.level = 0;
+                B.flags = 0;
+                a.m3.batch[0][bi] = B;
+            } else {
+                atomicMax(a.err, SS_ERR_INTERNAL);
+            }
+        }
+        const bool ranged = size > M3_CAP;
+        int32_t ri = -1, rtb = 0, rnt = 0;
+        if (ranged) {
+            ri = atomicAdd(&a.m3.cnt->n_rng[0], 1);
+            rnt = (int32_t)((size + SS_TILE - 1) / SS_TILE);
+            rtb = atomicAdd(&a.m3.cnt->n_tiles[0], rnt);
+            if (ri < a.m3.rng_max && (int64_t)rtb + rnt <= a.m3.tiles_max) {
+                M3Range R;
+                R.start = q;
+                R.size = (int32_t)size;
+                R.tile_base = rtb;
+                R.klo = 0u;
+                R.shift = a.m3_shift0;
+                R.pad[0] = R.pad[1] = 0;
+                a.m3.rng[0][ri] = R;
+            } else {
+                atomicMax(a.err, SS_ERR_INTERNAL);
+                ri = -1;
+            }
+        }
+        u32 rtodo = __ballot_sync(0xffffffffu, ri >= 0);
+        while (rtodo) {
+            const int src = __ffs(rtodo) - 1;
+            rtodo &= rtodo - 1;
+            const int32_t i2 = __shfl_sync(0xffffffffu, ri, src), t2 = __shfl_sync(0xffffffffu, rtb, src);
+            const int32_t n2 = __shfl_sync(0xffffffffu, rnt, src);
+            for (int32_t t = lane; t < n2; t += 32) a.m3.tile_rng[0][t2 + t] = i2;
+            uint32_t *h = a.m3.hist[0] + (size_t)i2 * 256;
+            for (int i = lane; i < 256; i += 32) h[i] = 0u;
+        }
+        return;
+    }
     const bool large = size > SS_LOCAL_MAX;
     int32_t idx = 0, tb = 0, nt = 0;
     if (large) {
@@ -773,6 +905,22 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
     }
 }
 
+}  // namespace tdt
+#include "tdt_segsort3.cuh"
+namespace tdt {
+
+// which large-segment chain: TDT_SEGSORT=lsd selects the four stable LSD passes (generation 1), anything else the
+// MSD rounds + shared-memory finish of tdt_segsort3.cuh (generation 3, default); read at every call
+static inline bool ss_use_msd() {
+    const char *e = getenv("TDT_SEGSORT");
+    if (e && e[0] == 'l') return false;
+#ifdef TDT_SEGSORT_DEFAULT_LSD
+    return e && e[0] == 'm';
+#else
+    return true;
+#endif
+}
+
 // ---- host launcher ---------------------------------------------------------------------------------
 // Sorts every segment [off[s], off[s+1]) of keys_in/vals_in by key (stable) into keys_out/vals_out.
 // n_max / nseg_max: host-side upper bounds that size the grids; the actual n / nseg are read on the device
@@ -806,11 +954,19 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     a.n_passes = (key_bits + 7) / 8;
     a.bits_per_pass = (key_bits + a.n_passes - 1) / a.n_passes;
     a.L = ss_layout(temp, n_max, nseg_max);
+    a.msd = ss_use_msd() ? 1 : 0;
+    a.m3_shift0 = key_bits > 8 ? key_bits - 8 : 0;
+    a.m3 = m3_layout(temp, n_max, nseg_max);
     a.err = err;
     TDT_CUDA(cudaMemsetAsync(temp, 0, a.L.zero_bytes, st));
     TDT_LAUNCH(segsort_classify_kernel, (unsigned)((nseg_max + 255) / 256), 256, 0, st, a);
     static thread_local bool configured = false;
     if (!configured) {
+        TDT_CUDA(cudaFuncSetAttribute(m3_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_PASS_SMEM));
+        TDT_CUDA(cudaFuncSetAttribute(m3_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)M3_FIN_SMEM));
+        TDT_CUDA(cudaFuncSetAttribute(m3_finish_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)M3_FIN_SMEM));
         TDT_CUDA(cudaFuncSetAttribute(segsort_local_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)SS_LOCAL_SMEM));
         TDT_CUDA(cudaFuncSetAttribute(segsort_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -850,7 +1006,7 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     int64_t nwin = (n_max + SS_WINDOW - 1) / SS_WINDOW;
     if (nwin > 148 * 4) nwin = 148 * 4;
     TDT_LAUNCH(segsort_local_kernel, (unsigned)nwin, SS_LTHREADS, SS_LOCAL_SMEM, side, a);
-    static thread_local int pass_cap = 0, hist_cap = 0;   // resident CTAs of the two tile kernels on this device
+    static thread_local int pass_cap = 0, hist_cap = 0, sm_count = 0;   // resident CTAs of the two tile kernels on this device
     if (!pass_cap) {
         int dev = 0, sms = 0, per_sm = 0;
         TDT_CUDA(cudaGetDevice(&dev));
@@ -859,9 +1015,63 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         pass_cap = sms * (per_sm > 0 ? per_sm : 1);
         TDT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, segsort_hist_kernel, SS_THREADS, 0));
         hist_cap = sms * (per_sm > 0 ? per_sm : 1);
+        sm_count = sms;
     }
     const unsigned tiles = (unsigned)(a.L.tiles_max < pass_cap ? a.L.tiles_max : pass_cap);
     const unsigned htiles = (unsigned)(a.L.tiles_max < hist_cap ? a.L.tiles_max : hist_cap);
+    cudaStream_t side2 = st;   // generation 3: the later partition rounds and their finish
+    if (a.msd) {
+        // Generation 3 (tdt_segsort3.cuh).  Nothing is large when the whole input fits the small-segment kernel; no
+        // range can exist when it fits one finish batch.
+        const int n_rounds = n_max > M3_CAP ? (key_bits + 7) / 8 : 0;
+        const bool byval = vals_in == nullptr;   // value = element index: grows with the position
+        // The finish kernel's CTAs are short-lived (a few batches each) instead of one persistent wave: the later
+        // rounds run next to it on a HIGH-PRIORITY side stream and take the SM resources a retiring CTA frees.
+        const int64_t fin_want = a.m3.batch_max < (int64_t)TDT_M3_FIN_WAVES * 2 * sm_count ? a.m3.batch_max
+                                                                                           : (int64_t)TDT_M3_FIN_WAVES * 2 * sm_count;
+        const unsigned fin_grid = (unsigned)(fin_want > 0 ? fin_want : 1);
+        const char *ser = getenv("TDT_M3_SERIAL");   // measurement aid: everything on the caller's stream
+        const bool serial = ser && ser[0] == '1';
+        if (n_rounds > 0) {
+            const int dst0 = n_rounds == 1 ? 2 : 1;   // a single round leaves the data sorted: straight into out
+            TDT_LAUNCH(m3_hist_kernel, htiles, SS_THREADS, 0, st, a, 0);
+            TDT_LAUNCH(m3_plan_kernel, (unsigned)((a.m3.rng_max * 32 + 255) / 256), 256, 0, st, a, 0, dst0);
+            TDT_LAUNCH(m3_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, st, a, 0, dst0);
+        }
+        if (n_rounds > 1) {
+#if TDT_SS_FORK
+            static thread_local cudaStream_t side2_streams[16 * SS_BRANCHES] = {};
+            static thread_local cudaEvent_t fork2_ev[16 * SS_BRANCHES] = {};
+            int d2 = 0;
+            TDT_CUDA(cudaGetDevice(&d2));
+            if (!serial && d2 >= 0 && d2 < 16) {
+                d2 = d2 * SS_BRANCHES + g_ss_branch;
+                if (!side2_streams[d2]) {
+                    int pr_least = 0, pr_greatest = 0;
+                    TDT_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+                    TDT_CUDA(cudaStreamCreateWithPriority(&side2_streams[d2], cudaStreamNonBlocking, pr_greatest));
+                    TDT_CUDA(cudaEventCreateWithFlags(&fork2_ev[d2], cudaEventDisableTiming));
+                    TDT_CUDA(cudaEventCreateWithFlags(&g_ss_join2_ev[d2], cudaEventDisableTiming));
+                }
+                side2 = side2_streams[d2];
+                TDT_CUDA(cudaEventRecord(fork2_ev[d2], st));
+                TDT_CUDA(cudaStreamWaitEvent(side2, fork2_ev[d2], 0));
+                g_ss_join2_idx = d2;
+            }
+#endif
+            for (int round = 1; round < n_rounds; round++) {
+                TDT_LAUNCH(m3_hist_kernel, htiles, SS_THREADS, 0, side2, a, round);
+                TDT_LAUNCH(m3_plan_kernel, (unsigned)((a.m3.rng_max * 32 + 255) / 256), 256, 0, side2, a, round, round + 1);
+                TDT_LAUNCH(m3_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, side2, a, round, round + 1);
+            }
+            if (byval) TDT_LAUNCH(m3_finish_kernel<true>, fin_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
+            else TDT_LAUNCH(m3_finish_kernel<false>, fin_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
+        }
+        if (n_max > SS_LOCAL_MAX) {
+            if (byval) TDT_LAUNCH(m3_finish_kernel<true>, fin_grid, M3_THREADS, M3_FIN_SMEM, st, a, 0);
+            else TDT_LAUNCH(m3_finish_kernel<false>, fin_grid, M3_THREADS, M3_FIN_SMEM, st, a, 0);
+        }
+    } else {
     TDT_LAUNCH(segsort_hist_kernel, htiles, SS_THREADS, 0, st, a);
     const int64_t scan_warps = a.L.nlarge_max * SS_MAX_PASSES;
     TDT_LAUNCH(segsort_scan_hist_kernel, (unsigned)((scan_warps * 32 + 255) / 256), 256, 0, st, a);
@@ -873,6 +1083,11 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         uint32_t *dk = to_out ? keys_out : keys_tmp;
         int32_t *dv = to_out ? vals_out : vals_tmp;
         TDT_LAUNCH(segsort_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, st, a, pass, sk, sv, dk, dv);
+    }
+    }
+    if (side2 != st) {
+        TDT_CUDA(cudaEventRecord(g_ss_join2_ev[g_ss_join2_idx], side2));
+        TDT_CUDA(cudaStreamWaitEvent(st, g_ss_join2_ev[g_ss_join2_idx], 0));
     }
 #if TDT_SS_FORK
     if (side != st) {

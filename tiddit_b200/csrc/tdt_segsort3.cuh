@@ -1,0 +1,565 @@
+// tdt_segsort3.cuh -- third generation of the LARGE-segment chain of the segmented stable sort (sm_100a):
+// most-significant-digit partition rounds + ONE shared-memory finish per element, instead of a histogram read and
+// four stable LSD passes.  (Included by tdt_segsort.cuh inside TDT_SEGSORT_IMPL; the tiny / small-segment kernels of
+// tdt_segsort.cuh are unchanged.)
+//
+// Why: the LSD passes are bound by their ranking work (~111 thread-instructions per element and pass, DRAM at 26 % of
+// peak), so the way to go faster is fewer ranking rounds per element, not fewer bytes.
+//
+//   round r (r = 0..ceil(key_bits/8)-1)   the queued RANGES (round 0: segments of > M3_CAP elements; later: buckets of
+//       the previous round that are still > M3_CAP) are cut by the 8-bit digit at bit `shift` (round 0: the TOP eight
+//       bits of the key range): m3_hist_kernel (digit counts per range), m3_plan_kernel (exclusive scan; consecutive
+//       buckets are grouped greedily into BATCHES of <= M3_CAP elements for the finish kernel, larger buckets are queued
+//       for round r + 1), m3_pass_kernel (the stable onesweep pass of tdt_segsort.cuh with this digit).  A range whose
+//       digit was the lowest bits of the key is sorted by the pass alone (stable: equal keys keep their order).
+//   finish   m3_finish_kernel: a CTA (512 threads, 2 per SM) takes a batch -- a contiguous element range that holds
+//       every element of a contiguous KEY range [klo, klo + nslots << sh) -- and sorts it in shared memory with ONE
+//       ranking round whatever the key width: slot = (key - klo) >> sh (up to 8192 slots, about one element each for
+//       spread-out keys), a shared-memory atomic per element counts the slots, a block scan turns counts into slot
+//       starts, a second atomic places (key, tie-break) at an arbitrary position inside its slot, and the output loop
+//       ranks every element among the (mostly 1-3) members of its slot by direct 64-bit comparison.  The tie-break
+//       is the value when values grow with the position (vals_in == nullptr: the value IS the element index), else
+//       the position in the batch -- so the result is the STABLE order although the atomics are not ordered.
+//       A batch whose slots are crowded (sum of squared slot counts > 64 x elements: pile-ups, heavy duplicates) is
+//       sorted by a bitonic network on the same 64-bit words instead: bounded work for any input.
+//
+// Data moves in -> tmp (round 0) -> out (round 1) -> tmp -> out; a batch is read from wherever its range currently
+// lies ("level") and written to out -- in place when it already lies there (all loads of a batch precede its stores).
+// Rounds >= 1 (only pile-ups and pairs beyond 2 M signals need them) run on a forked side stream next to the finish
+// kernel of the round-0 batches; their own batches form a second list finished on that stream.
+#pragma once
+
+namespace tdt {
+
+constexpr int M3_FLAG_COPY = 1;
+constexpr size_t M3_FIN_SMEM = (size_t)M3_CAP * 8 + (size_t)M3_NSLOT * 4 + 64 * 4;
+
+__device__ __forceinline__ void m3_level_ptrs(const SSArgs &a, int level, const uint32_t *&k, const int32_t *&v) {
+    if (level == 0) {
+        k = a.keys_in;
+        v = a.vals_in;
+    } else if (level & 1) {
+        k = a.keys_tmp;
+        v = a.vals_tmp;
+    } else {
+        k = a.keys_out;
+        v = a.vals_out;
+    }
+}
+
+// ---- digit counts of every queued range ------------------------------------------------------------------------
+// A CTA owns a contiguous run of tiles and flushes its shared histogram only when the range changes.
+__global__ void __launch_bounds__(SS_THREADS) m3_hist_kernel(SSArgs a, int round) {
+    __shared__ uint32_t h[256];
+    const int n_tiles = a.m3.cnt->n_tiles[round];
+    if (n_tiles <= 0) return;
+    const int per = (n_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+    const int t_lo = (int)blockIdx.x * per;
+    const int t_hi = t_lo + per < n_tiles ? t_lo + per : n_tiles;
+    if (t_lo >= t_hi) return;
+    const uint32_t *src;
+    const int32_t *src_v;
+    m3_level_ptrs(a, round, src, src_v);
+    (void)src_v;
+    if (threadIdx.x < 256) h[threadIdx.x] = 0u;
+    __syncthreads();
+    int cur = a.m3.tile_rng[round][t_lo];
+    for (int tile = t_lo; tile < t_hi; tile++) {
+        const int r = a.m3.tile_rng[round][tile];
+        if (r != cur) {   // uniform over the CTA
+            __syncthreads();
+            if (threadIdx.x < 256) {
+                const uint32_t v = h[threadIdx.x];
+                if (v) atomicAdd(a.m3.hist[round] + (size_t)cur * 256 + threadIdx.x, v);
+                h[threadIdx.x] = 0u;
+            }
+            __syncthreads();
+            cur = r;
+        }
+        const M3Range R = a.m3.rng[round][r];
+        const int64_t t0 = R.start + (int64_t)(tile - R.tile_base) * SS_TILE;
+        const int64_t rem = R.start + R.size - t0;
+        const int cnt = rem < SS_TILE ? (int)rem : SS_TILE;
+        if (cnt == SS_TILE) {   // all loads of the tile in flight before the first atomic
+            uint32_t k[SS_CHUNKS];
+#pragma unroll
+            for (int c = 0; c < SS_CHUNKS; c++) k[c] = src[t0 + c * SS_THREADS + threadIdx.x];
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < SS_CHUNKS; c++) {
+                bad = bad || (a.key_bits < 32 && (k[c] >> a.key_bits));
+                uint32_t d = (k[c] - R.klo) >> R.shift;
+                d = d > 255u ? 255u : d;
+                atomicAdd(&h[d], 1u);
+            }
+            if (round == 0 && bad) atomicMax(a.err, SS_ERR_KEY_RANGE);
+        } else {
+            for (int e = threadIdx.x; e < cnt; e += SS_THREADS) {
+                const uint32_t key = src[t0 + e];
+                if (round == 0 && a.key_bits < 32 && (key >> a.key_bits)) atomicMax(a.err, SS_ERR_KEY_RANGE);
+                uint32_t d = (key - R.klo) >> R.shift;
+                d = d > 255u ? 255u : d;
+                atomicAdd(&h[d], 1u);
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 256) {
+        const uint32_t v = h[threadIdx.x];
+        if (v) atomicAdd(a.m3.hist[round] + (size_t)cur * 256 + threadIdx.x, v);
+    }
+}
+
+// ---- plan: bucket starts, finish batches, the next round's ranges -------------------------------------------------
+// writes batch `idx` of `list` (the caller reserved the index with one atomicAdd on n_batches for all of its batches:
+// an atomic per batch cost ~0.5 us each in the single lane that walks a range's buckets -- 140 us per round)
+__device__ __forceinline__ void m3_emit_batch(const SSArgs &a, int list, int32_t idx, int64_t start, int32_t count,
+                                              uint32_t klo, uint64_t span, int level, int flags) {
+    if (idx >= a.m3.batch_max) {
+        atomicMax(a.err, SS_ERR_INTERNAL);
+        return;
+    }
+    int bits = span > 1 ? 64 - __clzll((long long)(span - 1)) : 0;
+    M3Batch B;
+    B.start = start;
+    B.count = count;
+    B.klo = klo;
+    B.sh = bits > M3_SLOT_BITS ? bits - M3_SLOT_BITS : 0;
+    B.nslots = (int32_t)(((span ? span : 1) - 1) >> B.sh) + 1;
+    B.level = level;
+    B.flags = flags;
+    a.m3.batch[list][idx] = B;
+}
+
+// one warp per range
+__global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int dst_level) {
+    __shared__ uint32_t s_cnt[8][256], s_ex[8][256];
+    __shared__ uint8_t s_push[8][256], s_gf[8][256], s_gl[8][256];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int ri = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
+    if (ri >= a.m3.cnt->n_rng[round]) return;   // uniform over the warp
+    const M3Range R = a.m3.rng[round][ri];
+    uint32_t *H = a.m3.hist[round] + (size_t)ri * 256 + lane * 8;
+    uint32_t v[8], t = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        v[i] = H[i];
+        t += v[i];
+    }
+    uint32_t inc = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += u;
+    }
+    uint32_t ex = inc - t;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        H[i] = ex;   // the pass kernel reads exclusive bucket starts
+        s_cnt[w][lane * 8 + i] = v[i];
+        s_ex[w][lane * 8 + i] = ex;
+        ex += v[i];
+    }
+    __syncwarp();
+    const int list = round == 0 ? 0 : 1;
+    if (R.shift == 0) {
+        // the digit was the lowest bits of the key: the stable pass leaves the range sorted.  Where it leaves it in
+        // the scratch buffers, copy batches bring it home.
+        if (dst_level & 1) {
+            const int nch = (R.size + M3_CAP - 1) / M3_CAP;
+            int32_t base = 0;
+            if (lane == 0) base = atomicAdd(&a.m3.cnt->n_batches[list], nch);
+            base = __shfl_sync(0xffffffffu, base, 0);
+            for (int c = lane; c < nch; c += 32) {
+                const int32_t left = R.size - c * M3_CAP;
+                m3_emit_batch(a, list, base + c, R.start + (int64_t)c * M3_CAP, left < M3_CAP ? left : M3_CAP, 0u, 1,
+                              dst_level, M3_FLAG_COPY);
+            }
+        }
+        return;
+    }
+    // lane 0 walks the buckets (shared memory only): groups of consecutive buckets -> s_gf / s_gl (first, last bucket),
+    // buckets beyond a batch -> s_push
+    int npush = 0, ngroup = 0;
+    if (lane == 0) {
+        uint32_t acc = 0;
+        int first = 0, last = 0;
+        for (int b = 0; b < 256; b++) {
+            const uint32_t c = s_cnt[w][b];
+            if (c == 0u) continue;
+            const bool over = c > (uint32_t)M3_CAP;
+            if (acc && (over || acc + c > (uint32_t)M3_CAP)) {
+                s_gf[w][ngroup] = (uint8_t)first;
+                s_gl[w][ngroup++] = (uint8_t)last;
+                acc = 0;
+            }
+            if (over) {
+                s_push[w][npush++] = (uint8_t)b;
+                continue;
+            }
+            if (acc == 0u) first = b;
+            acc += c;
+            last = b;
+        }
+        if (acc) {
+            s_gf[w][ngroup] = (uint8_t)first;
+            s_gl[w][ngroup++] = (uint8_t)last;
+        }
+    }
+    ngroup = __shfl_sync(0xffffffffu, ngroup, 0);
+    __syncwarp();
+    {
+        int32_t base = 0;
+        if (lane == 0 && ngroup) base = atomicAdd(&a.m3.cnt->n_batches[list], ngroup);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int g = lane; g < ngroup; g += 32) {
+            const int first = s_gf[w][g], last = s_gl[w][g];
+            const uint32_t gstart = s_ex[w][first];
+            const uint32_t gend = s_ex[w][last] + s_cnt[w][last];
+            m3_emit_batch(a, list, base + g, R.start + gstart, (int32_t)(gend - gstart),
+                          R.klo + ((uint32_t)first << R.shift), (uint64_t)(last - first + 1) << R.shift, dst_level, 0);
+        }
+    }
+    npush = __shfl_sync(0xffffffffu, npush, 0);
+    __syncwarp();
+    for (int p = 0; p < npush; p++) {
+        const int b = s_push[w][p];
+        const uint32_t c = s_cnt[w][b];
+        const int32_t nt = (int32_t)((c + SS_TILE - 1) / SS_TILE);
+        int32_t idx = 0, tb = 0;
+        if (lane == 0) {
+            idx = atomicAdd(&a.m3.cnt->n_rng[round + 1], 1);
+            tb = atomicAdd(&a.m3.cnt->n_tiles[round + 1], nt);
+            if (idx < a.m3.rng_max && tb + nt <= a.m3.tiles_max) {
+                M3Range N;
+                N.start = R.start + s_ex[w][b];
+                N.size = (int32_t)c;
+                N.tile_base = tb;
+                N.klo = R.klo + ((uint32_t)b << R.shift);
+                N.shift = R.shift > 8 ? R.shift - 8 : 0;
+                N.pad[0] = N.pad[1] = 0;
+                a.m3.rng[round + 1][idx] = N;
+            } else {
+                atomicMax(a.err, SS_ERR_INTERNAL);
+                idx = -1;
+            }
+        }
+        idx = __shfl_sync(0xffffffffu, idx, 0);
+        tb = __shfl_sync(0xffffffffu, tb, 0);
+        if (idx < 0) continue;
+        for (int32_t i = lane; i < nt; i += 32) a.m3.tile_rng[round + 1][tb + i] = idx;
+        uint32_t *h2 = a.m3.hist[round + 1] + (size_t)idx * 256;
+        for (int i = lane; i < 256; i += 32) h2[i] = 0u;
+    }
+}
+
+// ---- partition pass: the onesweep pass of tdt_segsort.cuh, digit = ((key - klo) >> shift) of the tile's range -----
+__global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) m3_pass_kernel(SSArgs a, int round, int dst_level) {
+    extern __shared__ __align__(16) unsigned char ss_smem[];
+    unsigned char *p = ss_smem;
+    uint2 *KV = (uint2 *)p; p += SS_TILE * 8;
+    uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
+    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_MM * SS_WARPS * 256 * 4;
+    uint32_t *bin = (uint32_t *)p; p += 256 * 4;
+    int64_t *gbase = (int64_t *)p;
+
+    const int n_tiles = a.m3.cnt->n_tiles[round];
+    const uint32_t *src_k, *dk_c;
+    const int32_t *src_v, *dv_c;
+    m3_level_ptrs(a, round, src_k, src_v);
+    m3_level_ptrs(a, dst_level, dk_c, dv_c);
+    uint32_t *dst_k = (uint32_t *)dk_c;
+    int32_t *dst_v = (int32_t *)dv_c;
+    const uint32_t epoch = (uint32_t)round + 1u;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) {
+            (&wh[0][0])[i] = 0u;
+            if (SS_MM) (&mm[0][0])[i] = 0u;
+        }
+        const int r = a.m3.tile_rng[round][tile];
+        const M3Range R = a.m3.rng[round][r];
+        const int lt = tile - R.tile_base;
+        const int64_t t0 = R.start + (int64_t)lt * SS_TILE;
+        const int64_t rem = R.start + R.size - t0;
+        const int cnt = rem < SS_TILE ? (int)rem : SS_TILE;
+        const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        constexpr int epw = SS_TILE / SS_WARPS;
+        const uint32_t klo = R.klo;
+        const int shift = R.shift;
+        auto dig = [&](uint32_t key) -> uint32_t {
+            const uint32_t d = (key - klo) >> shift;
+            return d > 255u ? 255u : d;
+        };
+
+        uint32_t key[SS_CHUNKS];
+        int32_t val[SS_CHUNKS];
+#pragma unroll
+        for (int c = 0; c < SS_CHUNKS; c++) {
+            const int e = warp * epw + c * 32 + lane;
+            key[c] = 0u;
+            val[c] = 0;
+            if (e < cnt) {
+                key[c] = src_k[t0 + e];
+                val[c] = src_v ? src_v[t0 + e] : (int32_t)(t0 + e);
+            }
+        }
+        __syncthreads();
+        uint32_t info[SS_CHUNKS];
+        ss_count<SS_CHUNKS>(cnt, epw, wh[warp], mm[warp], info, 8, [&](int, int c) -> uint32_t { return dig(key[c]); });
+        __syncthreads();
+        uint32_t total, excl;
+        ss_digit_bases<SS_WARPS>(wh, bin, total, excl);
+        uint32_t *row = a.L.status + (size_t)tile * 256 + threadIdx.x;
+        const bool live = threadIdx.x < 256;
+        uint32_t gh = 0;
+        if (live) {
+            st_volatile_u32(row, ss_pack(lt == 0 ? 2u : 1u, epoch, total));
+            gh = a.m3.hist[round][(size_t)r * 256 + threadIdx.x];
+        }
+        __syncthreads();
+        ss_scatter<SS_CHUNKS>(epw, wh[warp], info, [&](int, int c) -> uint32_t { return dig(key[c]); },
+                              [&](int, int c, uint32_t pos) { KV[pos] = make_uint2(key[c], (uint32_t)val[c]); });
+        {
+            uint32_t before = 0;
+            if (lt != 0 && live) {
+                constexpr int LB = TDT_SS_LB;
+                const uint32_t *prow = row - 256;
+                int left = lt;
+                bool done = false;
+                while (!done) {
+                    uint32_t sv[LB];
+#pragma unroll
+                    for (int i = 0; i < LB; i++) sv[i] = i < left ? ld_volatile_u32(prow - (size_t)i * 256) : 0u;
+#pragma unroll
+                    for (int i = 0; i < LB; i++) {
+                        if (!done && i < left) {
+                            uint32_t s = sv[i];
+                            while ((s >> 30) == 0u || ((s >> 26) & 15u) != epoch) s = ld_volatile_u32(prow - (size_t)i * 256);
+                            before += s & 0x3ffffffu;
+                            done = (s >> 30) == 2u;
+                        }
+                    }
+                    prow -= (size_t)LB * 256;
+                    left -= LB;
+                }
+                st_volatile_u32(row, ss_pack(2u, epoch, before + total));
+            }
+            if (threadIdx.x < 256) gbase[threadIdx.x] = R.start + (int64_t)gh + (int64_t)before - (int64_t)excl;
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < cnt; i += SS_THREADS) {
+            const uint2 kv = KV[i];
+            const int64_t g = gbase[dig(kv.x)] + i;
+            dst_k[g] = kv.x;
+            dst_v[g] = (int32_t)kv.y;
+        }
+        __syncthreads();
+    }
+}
+
+// members of slot [lo, hi) that sort before `me` (four independent loads in flight)
+__device__ __forceinline__ uint32_t m3_rank_in_slot(const u64 *KV, uint32_t lo, uint32_t hi, u64 me) {
+    uint32_t rank = 0, j = lo;
+    for (; j + 4 <= hi; j += 4) {
+        const u64 x0 = KV[j], x1 = KV[j + 1], x2 = KV[j + 2], x3 = KV[j + 3];
+        rank += (x0 < me ? 1u : 0u) + (x1 < me ? 1u : 0u) + (x2 < me ? 1u : 0u) + (x3 < me ? 1u : 0u);
+    }
+    for (; j < hi; j++) rank += KV[j] < me ? 1u : 0u;
+    return rank;
+}
+
+#ifndef TDT_M3_HOT
+#define TDT_M3_HOT 32   // a batch goes through the bitonic network when sum(slot count ^ 2) > TDT_M3_HOT x elements
+#endif
+
+// ---- finish: one ranking round in shared memory ---------------------------------------------------------------
+// BYVAL: values grow with the position inside every segment (the value is the tie-break); otherwise the tie-break is
+// the position in the batch and every thread writes its own elements to their final places.
+template <bool BYVAL>
+__global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int list) {
+    extern __shared__ __align__(16) unsigned char ss_smem[];
+    u64 *KV = (u64 *)ss_smem;
+    uint32_t *cnt = (uint32_t *)(ss_smem + (size_t)M3_CAP * 8);
+    uint32_t *ws = cnt + M3_NSLOT;   // [0..15] warp sums, [32] sum of squared slot counts
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    int nb = a.m3.cnt->n_batches[list];
+    if ((int64_t)nb > a.m3.batch_max) nb = (int)a.m3.batch_max;
+    for (int b = blockIdx.x; b < nb; b += gridDim.x) {
+        const M3Batch B = a.m3.batch[list][b];
+        const uint32_t *sk;
+        const int32_t *sv;
+        m3_level_ptrs(a, B.level, sk, sv);
+        const int64_t g0 = B.start;
+        const int count = B.count;
+        if (B.flags & M3_FLAG_COPY) {   // uniform over the CTA; a copy never has src == dst (odd levels only)
+            for (int i = t; i < count; i += M3_THREADS) {
+                a.keys_out[g0 + i] = sk[g0 + i];
+                a.vals_out[g0 + i] = sv[g0 + i];
+            }
+            continue;
+        }
+        const int nslots = B.nslots, sh = B.sh;
+        const uint32_t klo = B.klo, smax = (uint32_t)nslots - 1u;
+        const int nz = (nslots + 15) & ~15;
+        for (int i = t * 4; i < nz; i += M3_THREADS * 4) *(uint4 *)(cnt + i) = make_uint4(0u, 0u, 0u, 0u);
+        if (t == 0) ws[32] = 0u;
+        uint32_t key[M3_EPT];
+        int32_t val[M3_EPT];
+#pragma unroll
+        for (int c = 0; c < M3_EPT; c++) {
+            const int e = c * M3_THREADS + t;
+            key[c] = 0u;
+            val[c] = 0;
+            if (e < count) {
+                key[c] = sk[g0 + e];
+                val[c] = sv ? sv[g0 + e] : (int32_t)(g0 + e);
+            }
+        }
+        if (B.level == 0 && a.key_bits < 32) {
+            bool bad = false;
+#pragma unroll
+            for (int c = 0; c < M3_EPT; c++) bad = bad || (key[c] >> a.key_bits);
+            if (bad) atomicMax(a.err, SS_ERR_KEY_RANGE);
+        }
+        __syncthreads();
+#pragma unroll
+        for (int c = 0; c < M3_EPT; c++) {
+            const int e = c * M3_THREADS + t;
+            if (e < count) {
+                uint32_t s = (key[c] - klo) >> sh;
+                s = s > smax ? smax : s;
+                atomicAdd(&cnt[s], 1u);
+            }
+        }
+        __syncthreads();
+        // block scan over the slot counts: thread t owns slots [16 t, 16 t + 16)
+        uint32_t sum = 0, sq = 0;
+        const bool own = t * 16 < nz;
+        if (own) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const uint4 x = *(const uint4 *)(cnt + t * 16 + q * 4);
+                sum += x.x + x.y + x.z + x.w;
+                sq += x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w;
+            }
+        }
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t u = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += u;
+        }
+        sq = warp_sum(sq);
+        if (lane == 31) ws[warp] = inc;
+        if (lane == 0 && sq) atomicAdd(&ws[32], sq);
+        __syncthreads();
+        uint32_t run = inc - sum;
+#pragma unroll
+        for (int w2 = 0; w2 < M3_THREADS / 32; w2++)
+            if (w2 < warp) run += ws[w2];
+        const bool hot = ws[32] > (uint32_t)TDT_M3_HOT * (uint32_t)count;
+        if (own) {
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+                uint4 x = *(const uint4 *)(cnt + t * 16 + q * 4);
+                uint4 y;
+                y.x = run; run += x.x;
+                y.y = run; run += x.y;
+                y.z = run; run += x.z;
+                y.w = run; run += x.w;
+                *(uint4 *)(cnt + t * 16 + q * 4) = y;
+            }
+        }
+        __syncthreads();
+        if (!hot) {
+            // place: after this loop cnt[s] is the END of slot s (= the start of slot s + 1)
+#pragma unroll
+            for (int c = 0; c < M3_EPT; c++) {
+                const int e = c * M3_THREADS + t;
+                if (e < count) {
+                    uint32_t s = (key[c] - klo) >> sh;
+                    s = s > smax ? smax : s;
+                    const uint32_t pos = atomicAdd(&cnt[s], 1u);
+                    KV[pos] = ((u64)key[c] << 32) | (u64)(uint32_t)(BYVAL ? val[c] : e);
+                }
+            }
+            __syncthreads();
+            if (BYVAL) {
+                for (int i = t; i < count; i += M3_THREADS) {
+                    const u64 me = KV[i];
+                    const uint32_t k = (uint32_t)(me >> 32);
+                    uint32_t s = (k - klo) >> sh;
+                    s = s > smax ? smax : s;
+                    const uint32_t hi = cnt[s], lo = s ? cnt[s - 1] : 0u;
+                    uint32_t rank = 0;
+                    if (hi - lo > 1u) rank = m3_rank_in_slot(KV, lo, hi, me);
+                    const int64_t g = g0 + lo + rank;
+                    a.keys_out[g] = k;
+                    a.vals_out[g] = (int32_t)(uint32_t)me;
+                }
+            } else {
+#pragma unroll
+                for (int c = 0; c < M3_EPT; c++) {
+                    const int e = c * M3_THREADS + t;
+                    if (e < count) {
+                        const u64 me = ((u64)key[c] << 32) | (u64)(uint32_t)e;
+                        uint32_t s = (key[c] - klo) >> sh;
+                        s = s > smax ? smax : s;
+                        const uint32_t hi = cnt[s], lo = s ? cnt[s - 1] : 0u;
+                        uint32_t rank = 0;
+                        if (hi - lo > 1u) rank = m3_rank_in_slot(KV, lo, hi, me);
+                        const int64_t g = g0 + lo + rank;
+                        a.keys_out[g] = key[c];
+                        a.vals_out[g] = val[c];
+                    }
+                }
+            }
+        } else {
+            // crowded slots: bitonic network over the padded batch, same 64-bit (key, tie-break) words
+            int P = 2;
+            while (P < count) P <<= 1;
+#pragma unroll
+            for (int c = 0; c < M3_EPT; c++) {
+                const int e = c * M3_THREADS + t;
+                if (e < P) KV[e] = e < count ? (((u64)key[c] << 32) | (u64)(uint32_t)(BYVAL ? val[c] : e)) : ~0ull;
+            }
+            __syncthreads();
+            for (int k = 2; k <= P; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    for (int i = t; i < (P >> 1); i += M3_THREADS) {
+                        const int lo = ((i & ~(j - 1)) << 1) | (i & (j - 1)), hi = lo | j;
+                        const u64 x = KV[lo], y = KV[hi];
+                        const bool asc = (lo & k) == 0;
+                        if ((x > y) == asc) {
+                            KV[lo] = y;
+                            KV[hi] = x;
+                        }
+                    }
+                    __syncthreads();
+                }
+            }
+            if (BYVAL) {
+                for (int i = t; i < count; i += M3_THREADS) {
+                    const u64 me = KV[i];
+                    a.keys_out[g0 + i] = (uint32_t)(me >> 32);
+                    a.vals_out[g0 + i] = (int32_t)(uint32_t)me;
+                }
+            } else {
+                for (int i = t; i < count; i += M3_THREADS) cnt[(uint32_t)KV[i]] = (uint32_t)i;   // final place of element e
+                __syncthreads();
+#pragma unroll
+                for (int c = 0; c < M3_EPT; c++) {
+                    const int e = c * M3_THREADS + t;
+                    if (e < count) {
+                        const int64_t g = g0 + cnt[e];
+                        a.keys_out[g] = key[c];
+                        a.vals_out[g] = val[c];
+                    }
+                }
+            }
+        }
+        __syncthreads();   // KV / cnt / ws are rewritten by the next batch
+    }
+}
+
+}  // namespace tdt
