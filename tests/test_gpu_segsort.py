@@ -5,16 +5,17 @@ import pytest
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["msd", "lsd", "samplesort"], autouse=True)
+@pytest.fixture(params=["auto", "msd", "lsd", "samplesort"], autouse=True)
 def sort_generation(request, monkeypatch):
-    """Every test runs on the production sort (generation 3: MSD rounds + shared-memory finish, tdt_segsort3.cuh), on the
-    LSD chain it replaced (TDT_SEGSORT=lsd) and on the sample-sort generation (tdt_segsort2.cuh, TDT_SEGSORT_V2=1)."""
+    """Every test runs on the production dispatch (generation 3 -- MSD rounds + shared-memory finish, tdt_segsort3.cuh --
+    for index-valued sorts, the LSD chain otherwise), on each chain forced for every sort (TDT_SEGSORT=msd / lsd) and on
+    the sample-sort generation (tdt_segsort2.cuh, TDT_SEGSORT_V2=1)."""
     monkeypatch.delenv("TDT_SEGSORT_V2", raising=False)
     monkeypatch.delenv("TDT_SEGSORT", raising=False)
     if request.param == "samplesort":
         monkeypatch.setenv("TDT_SEGSORT_V2", "1")
-    elif request.param == "lsd":
-        monkeypatch.setenv("TDT_SEGSORT", "lsd")
+    elif request.param in ("lsd", "msd"):
+        monkeypatch.setenv("TDT_SEGSORT", request.param)
     return request.param
 
 

@@ -20,6 +20,7 @@
 // lane of a group bumps the warp-private digit counter.
 #pragma once
 #include <stdlib.h>
+#include <string.h>
 
 #include "tdt_common.cuh"
 
@@ -58,7 +59,8 @@ struct M3Range {   // a contiguous element range holding every element of key ra
     int32_t size, tile_base;
     uint32_t klo;
     int32_t shift;
-    int32_t pad[2];
+    int32_t seg;       // the input segment the range belongs to
+    int32_t pad;
 };
 
 struct M3Batch {   // finish work item: `count` elements at `start`, keys in [klo, klo + (nslots << sh))
@@ -193,6 +195,7 @@ struct SSArgs {
     int key_bits, n_passes, bits_per_pass;
     SSLayout L;
     int msd;               // 1: large segments go through the generation-3 chain (tdt_segsort3.cuh)
+    int m3_byval;          // generation 3: the value is the element index (ties broken by value, unordered partition passes)
     int m3_shift0;         // bit position of the round-0 digit
     M3Layout m3;
     int *err;
@@ -291,7 +294,8 @@ __global__ void segsort_classify_kernel(SSArgs a) {
                 R.tile_base = rtb;
                 R.klo = 0u;
                 R.shift = a.m3_shift0;
-                R.pad[0] = R.pad[1] = 0;
+                R.seg = (int32_t)s;
+                R.pad = 0;
                 a.m3.rng[0][ri] = R;
             } else {
                 atomicMax(a.err, SS_ERR_INTERNAL);
@@ -347,6 +351,12 @@ __global__ void __launch_bounds__(256) segsort_fill_kernel(SSArgs a) {
     for (int i = threadIdx.x; i < SS_MAX_PASSES * 256; i += 256) h[i] = 0u;
 }
 
+#ifndef TDT_SS_TINY_SPLIT
+#define TDT_SS_TINY_SPLIT 0
+#endif
+#ifndef TDT_SS_TINY_MAX
+#define TDT_SS_TINY_MAX 32
+#endif
 // ---- tiny segments: rank by counting ------------------------------------------------------------------
 // (one element per thread and iteration: 2 / 4 consecutive elements per thread with 16-byte loads measured slower,
 //  sort_y 0.445 / 0.450 ms vs 0.432 ms -- fewer resident chains outweigh the batched prologue)
@@ -360,10 +370,29 @@ __global__ void __launch_bounds__(256) segsort_tiny_kernel(SSArgs a) {
         const uint32_t key = a.keys_in[j];
         if (a.key_bits < 32 && (key >> a.key_bits)) atomicMax(a.err, SS_ERR_KEY_RANGE);
         int rank = 0;
+#if TDT_SS_TINY_SPLIT
+        // members before j precede it on "<=", members after it on "<": one compare per member, four loads in flight
+        const uint32_t *kb = a.keys_in + s0;
+        const int nb = (int)(j - s0), na = (int)(s1 - j) - 1;
+        const uint32_t *ka = a.keys_in + j + 1;
+        int i = 0;
+        for (; i + 4 <= nb; i += 4) {
+            const uint32_t x0 = kb[i], x1 = kb[i + 1], x2 = kb[i + 2], x3 = kb[i + 3];
+            rank += (x0 <= key) + (x1 <= key) + (x2 <= key) + (x3 <= key);
+        }
+        for (; i < nb; i++) rank += kb[i] <= key;
+        i = 0;
+        for (; i + 4 <= na; i += 4) {
+            const uint32_t x0 = ka[i], x1 = ka[i + 1], x2 = ka[i + 2], x3 = ka[i + 3];
+            rank += (x0 < key) + (x1 < key) + (x2 < key) + (x3 < key);
+        }
+        for (; i < na; i++) rank += ka[i] < key;
+#else
         for (int64_t i = s0; i < s1; i++) {
             const uint32_t other = a.keys_in[i];
             rank += (other < key) || (other == key && i < j);
         }
+#endif
         a.keys_out[s0 + rank] = key;
         a.vals_out[s0 + rank] = a.vals_in ? a.vals_in[j] : (int32_t)j;
     }
@@ -909,17 +938,38 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) segsort_pas
 #include "tdt_segsort3.cuh"
 namespace tdt {
 
-// which large-segment chain: TDT_SEGSORT=lsd selects the four stable LSD passes (generation 1), anything else the
-// MSD rounds + shared-memory finish of tdt_segsort3.cuh (generation 3, default); read at every call
-static inline bool ss_use_msd() {
+// Which large-segment chain.  Default: generation 3 (MSD rounds + shared-memory finish, tdt_segsort3.cuh) for sorts
+// whose value is the element index (vals_in == nullptr: the posA sort of all pairs, the aggregation's sub-sorts) --
+// measured on B200 (30X set): 0.61 -> 0.xx ms for posA -- and the four stable LSD passes otherwise: the sorts with
+// explicit values (posB inside x-runs, grouping by candidate) have a few dozen large segments, all of them pile-ups
+// that need the later rounds, and the LSD chain is quicker there (0.335 vs 0.43 ms for posB).
+// TDT_SEGSORT=lsd / msd in the environment (read at every call) forces one chain for every sort (A/B runs, tests).
+static inline bool ss_use_msd(bool value_is_index) {
     const char *e = getenv("TDT_SEGSORT");
     if (e && e[0] == 'l') return false;
-#ifdef TDT_SEGSORT_DEFAULT_LSD
-    return e && e[0] == 'm';
-#else
-    return true;
-#endif
+    if (e && e[0] == 'm') return true;
+    return value_is_index;
 }
+
+#ifdef TDT_M3_DEBUG
+#define TDT_M3_DEBUG_DUMP(stream, what)                                                                                 \
+    do {                                                                                                                \
+        unsigned long long h[16];                                                                                       \
+        M3Counters hc;                                                                                                  \
+        cudaStreamSynchronize(stream);                                                                                  \
+        cudaMemcpyFromSymbol(h, g_m3_dbg, sizeof(h));                                                                   \
+        cudaMemcpy(&hc, a.m3.cnt, sizeof(hc), cudaMemcpyDeviceToHost);                                                  \
+        fprintf(stderr, "m3 %s byval=%d: ranges %d/%d/%d/%d tiles %d/%d/%d/%d batches %d/%d | finished %llu (hot %llu "  \
+                "normal %llu) cycles hot %llu normal %llu max %llu elements %llu sumsq %llu levels %llu/%llu/%llu/%llu/%llu\n", \
+                what, (int)byval, hc.n_rng[0], hc.n_rng[1], hc.n_rng[2], hc.n_rng[3], hc.n_tiles[0], hc.n_tiles[1],     \
+                hc.n_tiles[2], hc.n_tiles[3], hc.n_batches[0], hc.n_batches[1], h[0], h[1], h[2], h[3], h[4], h[5],      \
+                h[6], h[7], h[8], h[9], h[10], h[11], h[12]);                                                           \
+        memset(h, 0, sizeof(h));                                                                                        \
+        cudaMemcpyToSymbol(g_m3_dbg, h, sizeof(h));                                                                     \
+    } while (0)
+#else
+#define TDT_M3_DEBUG_DUMP(stream, what) do { } while (0)
+#endif
 
 // ---- host launcher ---------------------------------------------------------------------------------
 // Sorts every segment [off[s], off[s+1]) of keys_in/vals_in by key (stable) into keys_out/vals_out.
@@ -949,20 +999,22 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     a.dims = dims;
     a.segid = segid;
     a.heads_out = heads_out;
-    a.tiny_max = segid ? 32 : 0;
+    a.tiny_max = segid ? TDT_SS_TINY_MAX : 0;
     a.key_bits = key_bits;
     a.n_passes = (key_bits + 7) / 8;
     a.bits_per_pass = (key_bits + a.n_passes - 1) / a.n_passes;
     a.L = ss_layout(temp, n_max, nseg_max);
-    a.msd = ss_use_msd() ? 1 : 0;
+    a.msd = ss_use_msd(vals_in == nullptr) ? 1 : 0;
     a.m3_shift0 = key_bits > 8 ? key_bits - 8 : 0;
+    a.m3_byval = vals_in == nullptr ? 1 : 0;
     a.m3 = m3_layout(temp, n_max, nseg_max);
     a.err = err;
     TDT_CUDA(cudaMemsetAsync(temp, 0, a.L.zero_bytes, st));
     TDT_LAUNCH(segsort_classify_kernel, (unsigned)((nseg_max + 255) / 256), 256, 0, st, a);
     static thread_local bool configured = false;
     if (!configured) {
-        TDT_CUDA(cudaFuncSetAttribute(m3_pass_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_PASS_SMEM));
+        TDT_CUDA(cudaFuncSetAttribute(m3_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SS_PASS_SMEM));
+        TDT_CUDA(cudaFuncSetAttribute(m3_pass_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)M3_UPASS_SMEM));
         TDT_CUDA(cudaFuncSetAttribute(m3_finish_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)M3_FIN_SMEM));
         TDT_CUDA(cudaFuncSetAttribute(m3_finish_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1006,7 +1058,7 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     int64_t nwin = (n_max + SS_WINDOW - 1) / SS_WINDOW;
     if (nwin > 148 * 4) nwin = 148 * 4;
     TDT_LAUNCH(segsort_local_kernel, (unsigned)nwin, SS_LTHREADS, SS_LOCAL_SMEM, side, a);
-    static thread_local int pass_cap = 0, hist_cap = 0, sm_count = 0;   // resident CTAs of the two tile kernels on this device
+    static thread_local int pass_cap = 0, hist_cap = 0, upass_cap = 0, sm_count = 0;   // resident CTAs of the two tile kernels on this device
     if (!pass_cap) {
         int dev = 0, sms = 0, per_sm = 0;
         TDT_CUDA(cudaGetDevice(&dev));
@@ -1015,8 +1067,11 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         pass_cap = sms * (per_sm > 0 ? per_sm : 1);
         TDT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, segsort_hist_kernel, SS_THREADS, 0));
         hist_cap = sms * (per_sm > 0 ? per_sm : 1);
+        TDT_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, m3_pass_kernel<false>, SS_THREADS, M3_UPASS_SMEM));
+        upass_cap = sms * (per_sm > 0 ? per_sm : 1);
         sm_count = sms;
     }
+    const unsigned utiles = (unsigned)(a.L.tiles_max < upass_cap ? a.L.tiles_max : upass_cap);
     const unsigned tiles = (unsigned)(a.L.tiles_max < pass_cap ? a.L.tiles_max : pass_cap);
     const unsigned htiles = (unsigned)(a.L.tiles_max < hist_cap ? a.L.tiles_max : hist_cap);
     cudaStream_t side2 = st;   // generation 3: the later partition rounds and their finish
@@ -1033,10 +1088,13 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         const char *ser = getenv("TDT_M3_SERIAL");   // measurement aid: everything on the caller's stream
         const bool serial = ser && ser[0] == '1';
         if (n_rounds > 0) {
-            const int dst0 = n_rounds == 1 ? 2 : 1;   // a single round leaves the data sorted: straight into out
+            // a single STABLE round leaves the data sorted: straight into out (the unordered passes of the by-value
+            // mode are always followed by a finish batch)
+            const int dst0 = (n_rounds == 1 && !byval) ? 2 : 1;
             TDT_LAUNCH(m3_hist_kernel, htiles, SS_THREADS, 0, st, a, 0);
             TDT_LAUNCH(m3_plan_kernel, (unsigned)((a.m3.rng_max * 32 + 255) / 256), 256, 0, st, a, 0, dst0);
-            TDT_LAUNCH(m3_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, st, a, 0, dst0);
+            if (byval) TDT_LAUNCH(m3_pass_kernel<false>, utiles, SS_THREADS, M3_UPASS_SMEM, st, a, 0, dst0);
+            else TDT_LAUNCH(m3_pass_kernel<true>, tiles, SS_THREADS, SS_PASS_SMEM, st, a, 0, dst0);
         }
         if (n_rounds > 1) {
 #if TDT_SS_FORK
@@ -1062,14 +1120,17 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
             for (int round = 1; round < n_rounds; round++) {
                 TDT_LAUNCH(m3_hist_kernel, htiles, SS_THREADS, 0, side2, a, round);
                 TDT_LAUNCH(m3_plan_kernel, (unsigned)((a.m3.rng_max * 32 + 255) / 256), 256, 0, side2, a, round, round + 1);
-                TDT_LAUNCH(m3_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, side2, a, round, round + 1);
+                if (byval) TDT_LAUNCH(m3_pass_kernel<false>, utiles, SS_THREADS, M3_UPASS_SMEM, side2, a, round, round + 1);
+                else TDT_LAUNCH(m3_pass_kernel<true>, tiles, SS_THREADS, SS_PASS_SMEM, side2, a, round, round + 1);
             }
             if (byval) TDT_LAUNCH(m3_finish_kernel<true>, fin_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
             else TDT_LAUNCH(m3_finish_kernel<false>, fin_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
+            TDT_M3_DEBUG_DUMP(side2, "list 1");
         }
         if (n_max > SS_LOCAL_MAX) {
             if (byval) TDT_LAUNCH(m3_finish_kernel<true>, fin_grid, M3_THREADS, M3_FIN_SMEM, st, a, 0);
             else TDT_LAUNCH(m3_finish_kernel<false>, fin_grid, M3_THREADS, M3_FIN_SMEM, st, a, 0);
+            TDT_M3_DEBUG_DUMP(st, "list 0");
         }
     } else {
     TDT_LAUNCH(segsort_hist_kernel, htiles, SS_THREADS, 0, st, a);

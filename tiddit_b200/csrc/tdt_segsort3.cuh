@@ -32,7 +32,10 @@
 namespace tdt {
 
 constexpr int M3_FLAG_COPY = 1;
-constexpr size_t M3_FIN_SMEM = (size_t)M3_CAP * 8 + (size_t)M3_NSLOT * 4 + 64 * 4;
+constexpr int M3_FLAG_EQUAL = 2;   // every element of input segment `sh` whose key is `klo`, in input order
+constexpr size_t M3_UPASS_SMEM = (size_t)SS_TILE * 8 + 256 * 4 * 2 + 256 * 8 + 64;
+constexpr int M3_PAD = 64;   // all-ones words behind the staged elements (see m3_rank_in_slot)
+constexpr size_t M3_FIN_SMEM = (size_t)(M3_CAP + M3_PAD) * 8 + (size_t)M3_NSLOT * 4 + 64 * 4;
 
 __device__ __forceinline__ void m3_level_ptrs(const SSArgs &a, int level, const uint32_t *&k, const int32_t *&v) {
     if (level == 0) {
@@ -133,7 +136,7 @@ __device__ __forceinline__ void m3_emit_batch(const SSArgs &a, int list, int32_t
 
 // one warp per range
 __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int dst_level) {
-    __shared__ uint32_t s_cnt[8][256], s_ex[8][256];
+    __shared__ __align__(16) uint32_t s_cnt[8][256], s_ex[8][256];
     __shared__ uint8_t s_push[8][256], s_gf[8][256], s_gl[8][256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ri = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
@@ -162,7 +165,8 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
     }
     __syncwarp();
     const int list = round == 0 ? 0 : 1;
-    if (R.shift == 0) {
+    const bool byval = a.m3_byval != 0;
+    if (R.shift == 0 && !byval) {
         // the digit was the lowest bits of the key: the stable pass leaves the range sorted.  Where it leaves it in
         // the scratch buffers, copy batches bring it home.
         if (dst_level & 1) {
@@ -184,22 +188,28 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
     if (lane == 0) {
         uint32_t acc = 0;
         int first = 0, last = 0;
-        for (int b = 0; b < 256; b++) {
-            const uint32_t c = s_cnt[w][b];
-            if (c == 0u) continue;
-            const bool over = c > (uint32_t)M3_CAP;
-            if (acc && (over || acc + c > (uint32_t)M3_CAP)) {
-                s_gf[w][ngroup] = (uint8_t)first;
-                s_gl[w][ngroup++] = (uint8_t)last;
-                acc = 0;
+        for (int b0 = 0; b0 < 256; b0 += 8) {   // eight counts per round trip to shared memory
+            const uint4 x0 = *(const uint4 *)&s_cnt[w][b0], x1 = *(const uint4 *)&s_cnt[w][b0 + 4];
+            const uint32_t cs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint32_t c = cs[k];
+                const int b = b0 + k;
+                if (c == 0u) continue;
+                const bool over = c > (uint32_t)M3_CAP;
+                if (acc && (over || acc + c > (uint32_t)M3_CAP)) {
+                    s_gf[w][ngroup] = (uint8_t)first;
+                    s_gl[w][ngroup++] = (uint8_t)last;
+                    acc = 0;
+                }
+                if (over) {
+                    s_push[w][npush++] = (uint8_t)b;
+                    continue;
+                }
+                if (acc == 0u) first = b;
+                acc += c;
+                last = b;
             }
-            if (over) {
-                s_push[w][npush++] = (uint8_t)b;
-                continue;
-            }
-            if (acc == 0u) first = b;
-            acc += c;
-            last = b;
         }
         if (acc) {
             s_gf[w][ngroup] = (uint8_t)first;
@@ -222,6 +232,31 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
     }
     npush = __shfl_sync(0xffffffffu, npush, 0);
     __syncwarp();
+    if (R.shift == 0) {
+        // by-value mode, the digit was the lowest bits of the key: a bucket beyond a batch holds > M3_CAP EQUAL keys.
+        // Its values, sorted, are the positions of that key in the input segment, in input order: the finish kernel
+        // regenerates them by a stable compaction of the segment instead of sorting.
+        int32_t base = 0;
+        if (lane == 0 && npush) base = atomicAdd(&a.m3.cnt->n_batches[list], npush);
+        base = __shfl_sync(0xffffffffu, base, 0);
+        for (int p = lane; p < npush; p += 32) {
+            const int b = s_push[w][p];
+            if (base + p >= a.m3.batch_max) {
+                atomicMax(a.err, SS_ERR_INTERNAL);
+                continue;
+            }
+            M3Batch B;
+            B.start = R.start + s_ex[w][b];
+            B.count = (int32_t)s_cnt[w][b];
+            B.klo = R.klo + (uint32_t)b;
+            B.sh = R.seg;
+            B.nslots = 1;
+            B.level = dst_level;
+            B.flags = M3_FLAG_EQUAL;
+            a.m3.batch[list][base + p] = B;
+        }
+        return;
+    }
     for (int p = 0; p < npush; p++) {
         const int b = s_push[w][p];
         const uint32_t c = s_cnt[w][b];
@@ -237,7 +272,8 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
                 N.tile_base = tb;
                 N.klo = R.klo + ((uint32_t)b << R.shift);
                 N.shift = R.shift > 8 ? R.shift - 8 : 0;
-                N.pad[0] = N.pad[1] = 0;
+                N.seg = R.seg;
+                N.pad = 0;
                 a.m3.rng[round + 1][idx] = N;
             } else {
                 atomicMax(a.err, SS_ERR_INTERNAL);
@@ -254,12 +290,18 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
 }
 
 // ---- partition pass: the onesweep pass of tdt_segsort.cuh, digit = ((key - klo) >> shift) of the tile's range -----
-__global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) m3_pass_kernel(SSArgs a, int round, int dst_level) {
+// STABLE: the warp-private stable ranking of tdt_segsort.cuh (sorts with explicit values: equal keys must keep their
+// order).  !STABLE (by-value mode): the order inside a bucket is irrelevant -- the finish kernel orders ties by value --
+// so an element's place among the tile's equal digits is simply what ONE shared-memory atomicAdd on the digit's counter
+// returns: ~6 instead of ~33 instructions per element for the ranking, no per-warp counter arrays (16 KB less shared
+// memory per CTA).
+template <bool STABLE>
+__global__ void __launch_bounds__(SS_THREADS, STABLE ? TDT_SS_PASS_MINBLOCKS : 4) m3_pass_kernel(SSArgs a, int round, int dst_level) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     unsigned char *p = ss_smem;
     uint2 *KV = (uint2 *)p; p += SS_TILE * 8;
-    uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += SS_WARPS * 256 * 4;
-    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += SS_MM * SS_WARPS * 256 * 4;
+    uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += STABLE ? SS_WARPS * 256 * 4 : 256 * 4;   // !STABLE: one counter row
+    uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += STABLE ? SS_MM * SS_WARPS * 256 * 4 : 0;
     uint32_t *bin = (uint32_t *)p; p += 256 * 4;
     int64_t *gbase = (int64_t *)p;
 
@@ -272,9 +314,13 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) m3_pass_ker
     int32_t *dst_v = (int32_t *)dv_c;
     const uint32_t epoch = (uint32_t)round + 1u;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) {
-            (&wh[0][0])[i] = 0u;
-            if (SS_MM) (&mm[0][0])[i] = 0u;
+        if (STABLE) {
+            for (int i = threadIdx.x; i < SS_WARPS * 256; i += SS_THREADS) {
+                (&wh[0][0])[i] = 0u;
+                if (SS_MM) (&mm[0][0])[i] = 0u;
+            }
+        } else {
+            if (threadIdx.x < 256) wh[0][threadIdx.x] = 0u;
         }
         const int r = a.m3.tile_rng[round][tile];
         const M3Range R = a.m3.rng[round][r];
@@ -305,10 +351,26 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) m3_pass_ker
         }
         __syncthreads();
         uint32_t info[SS_CHUNKS];
-        ss_count<SS_CHUNKS>(cnt, epw, wh[warp], mm[warp], info, 8, [&](int, int c) -> uint32_t { return dig(key[c]); });
-        __syncthreads();
         uint32_t total, excl;
-        ss_digit_bases<SS_WARPS>(wh, bin, total, excl);
+        if (STABLE) {
+            ss_count<SS_CHUNKS>(cnt, epw, wh[warp], mm[warp], info, 8, [&](int, int c) -> uint32_t { return dig(key[c]); });
+            __syncthreads();
+            ss_digit_bases<SS_WARPS>(wh, bin, total, excl);
+        } else {
+#pragma unroll
+            for (int c = 0; c < SS_CHUNKS; c++) {
+                const int e = warp * epw + c * 32 + lane;
+                info[c] = 0u;
+                if (e < cnt) {
+                    const uint32_t d = dig(key[c]);
+                    info[c] = (d << 16) | atomicAdd(&wh[0][d], 1u);   // digit : place among the tile's equal digits
+                }
+            }
+            __syncthreads();
+            total = threadIdx.x < 256 ? wh[0][threadIdx.x] : 0u;
+            excl = ss_block_excl_scan_256<SS_WARPS>(total, bin);
+            if (threadIdx.x < 256) wh[0][threadIdx.x] = excl;
+        }
         uint32_t *row = a.L.status + (size_t)tile * 256 + threadIdx.x;
         const bool live = threadIdx.x < 256;
         uint32_t gh = 0;
@@ -317,8 +379,16 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) m3_pass_ker
             gh = a.m3.hist[round][(size_t)r * 256 + threadIdx.x];
         }
         __syncthreads();
-        ss_scatter<SS_CHUNKS>(epw, wh[warp], info, [&](int, int c) -> uint32_t { return dig(key[c]); },
-                              [&](int, int c, uint32_t pos) { KV[pos] = make_uint2(key[c], (uint32_t)val[c]); });
+        if (STABLE) {
+            ss_scatter<SS_CHUNKS>(epw, wh[warp], info, [&](int, int c) -> uint32_t { return dig(key[c]); },
+                                  [&](int, int c, uint32_t pos) { KV[pos] = make_uint2(key[c], (uint32_t)val[c]); });
+        } else {
+#pragma unroll
+            for (int c = 0; c < SS_CHUNKS; c++) {
+                const int e = warp * epw + c * 32 + lane;
+                if (e < cnt) KV[wh[0][info[c] >> 16] + (info[c] & 0xffffu)] = make_uint2(key[c], (uint32_t)val[c]);
+            }
+        }
         {
             uint32_t before = 0;
             if (lt != 0 && live) {
@@ -357,35 +427,54 @@ __global__ void __launch_bounds__(SS_THREADS, TDT_SS_PASS_MINBLOCKS) m3_pass_ker
     }
 }
 
-// members of slot [lo, hi) that sort before `me` (four independent loads in flight)
+// Members of slot [lo, hi) that sort before `me`; called by all 32 lanes (lanes without an element pass lo == hi == 0).
+// The staged words are in slot order, so whatever follows a slot is LARGER than its members, and the M3_PAD words behind
+// the last element are all-ones: the loop can run past hi without a bound check, to the largest slot among the warp's
+// lanes (one REDUX, no divergent exits) -- four instructions per step.  (The generic per-lane loop the compiler built for
+// `for j in [lo, hi)`, unrolled 16 / 8 / 4 / 2 / 1 with a reconvergence point each, was 68 % of the kernel's instructions.)
 __device__ __forceinline__ uint32_t m3_rank_in_slot(const u64 *KV, uint32_t lo, uint32_t hi, u64 me) {
-    uint32_t rank = 0, j = lo;
-    for (; j + 4 <= hi; j += 4) {
-        const u64 x0 = KV[j], x1 = KV[j + 1], x2 = KV[j + 2], x3 = KV[j + 3];
-        rank += (x0 < me ? 1u : 0u) + (x1 < me ? 1u : 0u) + (x2 < me ? 1u : 0u) + (x3 < me ? 1u : 0u);
+    uint32_t cmax = __reduce_max_sync(0xffffffffu, hi - lo);
+    uint32_t rank = 0;
+    if (cmax > 1u) {
+        if (cmax > (uint32_t)M3_PAD) {   // a crowded slot in a batch that is not crowded overall: bounded loop
+            for (uint32_t j = lo; j < hi; j++) rank += KV[j] < me ? 1u : 0u;
+        } else {
+            const u64 *p = KV + lo;
+#pragma unroll 4
+            for (uint32_t q = 0; q < cmax; q++) rank += p[q] < me ? 1u : 0u;
+        }
     }
-    for (; j < hi; j++) rank += KV[j] < me ? 1u : 0u;
     return rank;
 }
 
 #ifndef TDT_M3_HOT
-#define TDT_M3_HOT 32   // a batch goes through the bitonic network when sum(slot count ^ 2) > TDT_M3_HOT x elements
+#define TDT_M3_HOT 64   // a batch goes through the bitonic network when sum(slot count ^ 2) > TDT_M3_HOT x elements
 #endif
 
 // ---- finish: one ranking round in shared memory ---------------------------------------------------------------
 // BYVAL: values grow with the position inside every segment (the value is the tie-break); otherwise the tie-break is
 // the position in the batch and every thread writes its own elements to their final places.
+#ifdef TDT_M3_DEBUG
+__device__ unsigned long long g_m3_dbg[16];
+#define M3_DBG(stmt) do { if (threadIdx.x == 0) { stmt; } } while (0)
+#else
+#define M3_DBG(stmt) do { } while (0)
+#endif
+
 template <bool BYVAL>
 __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int list) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
     u64 *KV = (u64 *)ss_smem;
-    uint32_t *cnt = (uint32_t *)(ss_smem + (size_t)M3_CAP * 8);
+    uint32_t *cnt = (uint32_t *)(ss_smem + (size_t)(M3_CAP + M3_PAD) * 8);
     uint32_t *ws = cnt + M3_NSLOT;   // [0..15] warp sums, [32] sum of squared slot counts
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
     int nb = a.m3.cnt->n_batches[list];
     if ((int64_t)nb > a.m3.batch_max) nb = (int)a.m3.batch_max;
     for (int b = blockIdx.x; b < nb; b += gridDim.x) {
         const M3Batch B = a.m3.batch[list][b];
+#ifdef TDT_M3_DEBUG
+        const long long dbg_t0 = clock64();
+#endif
         const uint32_t *sk;
         const int32_t *sv;
         m3_level_ptrs(a, B.level, sk, sv);
@@ -398,6 +487,36 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
             }
             continue;
         }
+        if (B.flags & M3_FLAG_EQUAL) {
+            // > M3_CAP equal keys (by-value mode): their values in order are the positions of the key in the input
+            // segment, regenerated by a stable compaction of the segment (uniform over the CTA, rare)
+            const int64_t s0 = a.off[B.sh], s1 = a.off[B.sh + 1];
+            uint32_t run = 0;
+            for (int64_t base = s0; base < s1; base += M3_THREADS) {
+                const int64_t j = base + t;
+                const bool hit = j < s1 && a.keys_in[j] == B.klo;
+                const uint32_t bal = __ballot_sync(0xffffffffu, hit);
+                if (lane == 0) ws[warp] = __popc(bal);
+                __syncthreads();
+                uint32_t before = run, all = 0;
+#pragma unroll
+                for (int w2 = 0; w2 < M3_THREADS / 32; w2++) {
+                    const uint32_t x = ws[w2];
+                    if (w2 < warp) before += x;
+                    all += x;
+                }
+                if (hit) {
+                    const uint32_t pos = before + __popc(bal & lanemask_lt());
+                    if (pos < (uint32_t)count) {
+                        a.keys_out[g0 + pos] = B.klo;
+                        a.vals_out[g0 + pos] = (int32_t)j;
+                    }
+                }
+                run += all;
+                __syncthreads();
+            }
+            continue;
+        }
         const int nslots = B.nslots, sh = B.sh;
         const uint32_t klo = B.klo, smax = (uint32_t)nslots - 1u;
         const int nz = (nslots + 15) & ~15;
@@ -407,9 +526,13 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
         int32_t val[M3_EPT];
 #pragma unroll
         for (int c = 0; c < M3_EPT; c++) {
-            const int e = c * M3_THREADS + t;
             key[c] = 0u;
             val[c] = 0;
+        }
+#pragma unroll
+        for (int c = 0; c < M3_EPT; c++) {
+            if (c * M3_THREADS >= count) break;   // uniform: a batch rarely fills all sixteen chunks
+            const int e = c * M3_THREADS + t;
             if (e < count) {
                 key[c] = sk[g0 + e];
                 val[c] = sv ? sv[g0 + e] : (int32_t)(g0 + e);
@@ -424,6 +547,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
         __syncthreads();
 #pragma unroll
         for (int c = 0; c < M3_EPT; c++) {
+            if (c * M3_THREADS >= count) break;
             const int e = c * M3_THREADS + t;
             if (e < count) {
                 uint32_t s = (key[c] - klo) >> sh;
@@ -475,6 +599,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
             // place: after this loop cnt[s] is the END of slot s (= the start of slot s + 1)
 #pragma unroll
             for (int c = 0; c < M3_EPT; c++) {
+                if (c * M3_THREADS >= count) break;
                 const int e = c * M3_THREADS + t;
                 if (e < count) {
                     uint32_t s = (key[c] - klo) >> sh;
@@ -483,31 +608,44 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
                     KV[pos] = ((u64)key[c] << 32) | (u64)(uint32_t)(BYVAL ? val[c] : e);
                 }
             }
+            if (t < M3_PAD) KV[count + t] = ~0ull;
             __syncthreads();
             if (BYVAL) {
-                for (int i = t; i < count; i += M3_THREADS) {
-                    const u64 me = KV[i];
+                for (int base = 0; base < count; base += M3_THREADS) {   // uniform trip count: the ranking is warp-wide
+                    const int i = base + t;
+                    const bool live = i < count;
+                    const u64 me = live ? KV[i] : 0ull;
                     const uint32_t k = (uint32_t)(me >> 32);
                     uint32_t s = (k - klo) >> sh;
                     s = s > smax ? smax : s;
-                    const uint32_t hi = cnt[s], lo = s ? cnt[s - 1] : 0u;
-                    uint32_t rank = 0;
-                    if (hi - lo > 1u) rank = m3_rank_in_slot(KV, lo, hi, me);
-                    const int64_t g = g0 + lo + rank;
-                    a.keys_out[g] = k;
-                    a.vals_out[g] = (int32_t)(uint32_t)me;
+                    uint32_t hi = 0, lo = 0;
+                    if (live) {
+                        hi = cnt[s];
+                        lo = s ? cnt[s - 1] : 0u;
+                    }
+                    const uint32_t rank = m3_rank_in_slot(KV, lo, hi, me);
+                    if (live) {
+                        const int64_t g = g0 + lo + rank;
+                        a.keys_out[g] = k;
+                        a.vals_out[g] = (int32_t)(uint32_t)me;
+                    }
                 }
             } else {
 #pragma unroll
                 for (int c = 0; c < M3_EPT; c++) {
+                    if (c * M3_THREADS >= count) break;
                     const int e = c * M3_THREADS + t;
-                    if (e < count) {
-                        const u64 me = ((u64)key[c] << 32) | (u64)(uint32_t)e;
-                        uint32_t s = (key[c] - klo) >> sh;
-                        s = s > smax ? smax : s;
-                        const uint32_t hi = cnt[s], lo = s ? cnt[s - 1] : 0u;
-                        uint32_t rank = 0;
-                        if (hi - lo > 1u) rank = m3_rank_in_slot(KV, lo, hi, me);
+                    const bool live = e < count;
+                    const u64 me = ((u64)key[c] << 32) | (u64)(uint32_t)e;
+                    uint32_t s = (key[c] - klo) >> sh;
+                    s = s > smax ? smax : s;
+                    uint32_t hi = 0, lo = 0;
+                    if (live) {
+                        hi = cnt[s];
+                        lo = s ? cnt[s - 1] : 0u;
+                    }
+                    const uint32_t rank = m3_rank_in_slot(KV, lo, hi, me);
+                    if (live) {
                         const int64_t g = g0 + lo + rank;
                         a.keys_out[g] = key[c];
                         a.vals_out[g] = val[c];
@@ -549,6 +687,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
                 __syncthreads();
 #pragma unroll
                 for (int c = 0; c < M3_EPT; c++) {
+                    if (c * M3_THREADS >= count) break;
                     const int e = c * M3_THREADS + t;
                     if (e < count) {
                         const int64_t g = g0 + cnt[e];
@@ -559,6 +698,16 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
             }
         }
         __syncthreads();   // KV / cnt / ws are rewritten by the next batch
+        M3_DBG({
+            const unsigned long long dt = (unsigned long long)(clock64() - dbg_t0);
+            atomicAdd(&g_m3_dbg[0], 1ull);
+            atomicAdd(&g_m3_dbg[hot ? 1 : 2], 1ull);
+            atomicAdd(&g_m3_dbg[hot ? 3 : 4], dt);
+            atomicMax(&g_m3_dbg[5], dt);
+            atomicAdd(&g_m3_dbg[6], (unsigned long long)count);
+            atomicAdd(&g_m3_dbg[7], (unsigned long long)ws[32]);
+            atomicAdd(&g_m3_dbg[8 + (B.level < 5 ? B.level : 5)], 1ull);
+        });
     }
 }
 
