@@ -197,13 +197,22 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
                 const int b = b0 + k;
                 if (c == 0u) continue;
                 const bool over = c > (uint32_t)M3_CAP;
-                if (acc && (over || acc + c > (uint32_t)M3_CAP)) {
+                // a DENSE bucket becomes a batch of its own: grouped with sparse neighbours it would share their wide
+                // key span, i.e. coarse slots, and its elements would crowd a few of them (a 5 k-signal pile-up of 2 kb
+                // next to background: 300 elements per slot -> the bitonic path; alone: one slot per position)
+                const bool dense = c > (uint32_t)(M3_CAP / 4);
+                if (acc && (over || dense || acc + c > (uint32_t)M3_CAP)) {
                     s_gf[w][ngroup] = (uint8_t)first;
                     s_gl[w][ngroup++] = (uint8_t)last;
                     acc = 0;
                 }
                 if (over) {
                     s_push[w][npush++] = (uint8_t)b;
+                    continue;
+                }
+                if (dense) {
+                    s_gf[w][ngroup] = (uint8_t)b;
+                    s_gl[w][ngroup++] = (uint8_t)b;
                     continue;
                 }
                 if (acc == 0u) first = b;
