@@ -91,7 +91,8 @@ struct SSLarge {
 
 struct SSCounters {
     int32_t n_large, n_tiles;
-    int32_t pad[6];
+    int32_t n_small;   // segments of the small class (the small-segment kernel leaves at once when there are none)
+    int32_t pad[5];
 };
 
 struct SSLayout {  // carved out of the caller's temp storage
@@ -113,8 +114,12 @@ static inline int64_t ss_nlarge_max(int64_t n, int64_t nseg_max) {
     return a < nseg_max ? a : (nseg_max > 0 ? nseg_max : 1);
 }
 
-static inline int64_t m3_rng_max(int64_t n) { return n / (M3_CAP + 1) + 1; }
-static inline int64_t m3_batch_max(int64_t n) { return n / SS_LOCAL_MAX + 64 * m3_rng_max(n) + 64; }
+// Work-list bounds.  A queued range holds > M3_CAP / 4 elements (buckets beyond a batch, pile-up buckets), so a round
+// has at most n / (M3_CAP / 4) of them.  Batches: a whole segment (> SS_LOCAL_MAX elements) or a group of buckets; two
+// neighbouring groups of a run of ordinary buckets together exceed M3_CAP, and a run ends at a dense or queued bucket
+// (> M3_CAP / 4 elements) or at the end of its range: <= 6 n / M3_CAP + ranges + 1 groups per round, four rounds.
+static inline int64_t m3_rng_max(int64_t n) { return n / (M3_CAP / 4) + 1; }
+static inline int64_t m3_batch_max(int64_t n) { return 16 * m3_rng_max(n) + 64; }
 static inline int64_t ss_tiles_max(int64_t n, int64_t nl) {
     const int64_t r = m3_rng_max(n);
     return n / SS_TILE + (nl > r ? nl : r) + 1;
@@ -262,6 +267,7 @@ __global__ void segsort_classify_kernel(SSArgs a) {
             atomicMax(a.L.win_lo + k, 0x7fffffff - (int32_t)s);
             atomicAdd(a.L.win_cnt + k, total);
         }
+        if ((act & lanemask_lt()) == 0u) atomicAdd(&a.L.cnt->n_small, __popc(act));
         if ((peers >> lane) == 1u) atomicMax(a.L.win_hi + k, (int32_t)s + 1);
     }
     // large segments (rare): the whole warp writes the tile -> segment entries and zeroes the digit histograms of
@@ -603,6 +609,7 @@ __global__ void __launch_bounds__(SS_LTHREADS) segsort_local_kernel(SSArgs a) {
     __shared__ uint32_t s_carry;
     __shared__ int s_batch[2];  // next batch: [first window, one past the last window) relative to the round
 
+    if (a.L.cnt->n_small == 0) return;   // the posA sort of whole pairs: nothing here, leave the SMs to the large chain
     const int64_t n = a.dims[0];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (SS_MM)

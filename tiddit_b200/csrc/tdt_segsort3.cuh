@@ -137,7 +137,8 @@ __device__ __forceinline__ void m3_emit_batch(const SSArgs &a, int list, int32_t
 // one warp per range
 __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int dst_level) {
     __shared__ __align__(16) uint32_t s_cnt[8][256], s_ex[8][256];
-    __shared__ uint8_t s_push[8][256], s_gf[8][256], s_gl[8][256];
+    __shared__ uint8_t s_push[8][256];
+    __shared__ int32_t s_ptile[8][256];
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
     const int ri = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     if (ri >= a.m3.cnt->n_rng[round]) return;   // uniform over the warp
@@ -182,116 +183,245 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
         }
         return;
     }
-    // lane 0 walks the buckets (shared memory only): groups of consecutive buckets -> s_gf / s_gl (first, last bucket),
-    // buckets beyond a batch -> s_push
-    int npush = 0, ngroup = 0;
-    if (lane == 0) {
-        uint32_t acc = 0;
-        int first = 0, last = 0;
-        for (int b0 = 0; b0 < 256; b0 += 8) {   // eight counts per round trip to shared memory
-            const uint4 x0 = *(const uint4 *)&s_cnt[w][b0], x1 = *(const uint4 *)&s_cnt[w][b0 + 4];
-            const uint32_t cs[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+    // ---- grouping, all 32 lanes (a single lane walking the 256 buckets was a 12 us dependent chain per round) --------
+    // Buckets are ORDINARY (1 .. M3_CAP / 4 elements), DENSE (more, up to M3_CAP: a batch of their own -- grouped with
+    // sparse neighbours they would share a wide key span, i.e. coarse slots, and crowd a few of them) or QUEUED for the
+    // next round (beyond M3_CAP -- or a pile-up: dense AND > 8x the range's average bucket, a narrow hot region that one
+    // more cut turns into batches with a slot per position instead of a ~100 us bitonic batch).  Dense and queued
+    // buckets end a RUN of ordinary buckets; inside a run, bucket b joins group (Pi(b) - 1) / (3/4 M3_CAP), Pi = inclusive
+    // prefix of the run's counts: a group holds < 3/4 M3_CAP + M3_CAP / 4 elements and, except the last of a run, more
+    // than M3_CAP / 2.
+    constexpr uint32_t GRP = (uint32_t)(M3_CAP - M3_CAP / 4);
+    const uint32_t pile = (uint32_t)R.size / 32u;
+    uint32_t kind[8];   // 0 empty, 1 ordinary, 2 dense, 3 queued
+    uint32_t nord = 0, nbrk = 0;
 #pragma unroll
-            for (int k = 0; k < 8; k++) {
-                const uint32_t c = cs[k];
-                const int b = b0 + k;
-                if (c == 0u) continue;
-                const bool over = c > (uint32_t)M3_CAP;
-                // a DENSE bucket becomes a batch of its own: grouped with sparse neighbours it would share their wide
-                // key span, i.e. coarse slots, and its elements would crowd a few of them (a 5 k-signal pile-up of 2 kb
-                // next to background: 300 elements per slot -> the bitonic path; alone: one slot per position)
-                const bool dense = c > (uint32_t)(M3_CAP / 4);
-                if (acc && (over || dense || acc + c > (uint32_t)M3_CAP)) {
-                    s_gf[w][ngroup] = (uint8_t)first;
-                    s_gl[w][ngroup++] = (uint8_t)last;
-                    acc = 0;
-                }
-                if (over) {
-                    s_push[w][npush++] = (uint8_t)b;
-                    continue;
-                }
-                if (dense) {
-                    s_gf[w][ngroup] = (uint8_t)b;
-                    s_gl[w][ngroup++] = (uint8_t)b;
-                    continue;
-                }
-                if (acc == 0u) first = b;
-                acc += c;
-                last = b;
-            }
-        }
-        if (acc) {
-            s_gf[w][ngroup] = (uint8_t)first;
-            s_gl[w][ngroup++] = (uint8_t)last;
+    for (int i = 0; i < 8; i++) {
+        const uint32_t c = v[i];
+        const bool over = c > (uint32_t)M3_CAP || (R.shift > 0 && c > (uint32_t)(M3_CAP / 4) && c > pile);
+        kind[i] = c == 0u ? 0u : (over ? 3u : (c > (uint32_t)(M3_CAP / 4) ? 2u : 1u));
+        nord += kind[i] == 1u ? c : 0u;
+        nbrk += kind[i] >= 2u ? 1u : 0u;
+    }
+    // exclusive prefixes over the lanes: ordinary elements, breaks
+    uint32_t pord = nord, pbrk = nbrk;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, pord, o), y = __shfl_up_sync(0xffffffffu, pbrk, o);
+        if (lane >= o) {
+            pord += x;
+            pbrk += y;
         }
     }
-    ngroup = __shfl_sync(0xffffffffu, ngroup, 0);
-    __syncwarp();
+    pord -= nord;
+    pbrk -= nbrk;
+    // ordinary elements before the current run starts = the ordinary prefix at the latest break: per lane the value at
+    // its last break (if any), then a "latest defined" scan over the lanes
+    uint32_t run0_lane = 0xffffffffu;   // ordinary prefix at this lane's last break (none: all-ones)
     {
-        int32_t base = 0;
-        if (lane == 0 && ngroup) base = atomicAdd(&a.m3.cnt->n_batches[list], ngroup);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int g = lane; g < ngroup; g += 32) {
-            const int first = s_gf[w][g], last = s_gl[w][g];
-            const uint32_t gstart = s_ex[w][first];
-            const uint32_t gend = s_ex[w][last] + s_cnt[w][last];
-            m3_emit_batch(a, list, base + g, R.start + gstart, (int32_t)(gend - gstart),
-                          R.klo + ((uint32_t)first << R.shift), (uint64_t)(last - first + 1) << R.shift, dst_level, 0);
+        uint32_t po = pord;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (kind[i] == 1u) po += v[i];
+            if (kind[i] >= 2u) run0_lane = po;
         }
     }
-    npush = __shfl_sync(0xffffffffu, npush, 0);
-    __syncwarp();
-    if (R.shift == 0) {
-        // by-value mode, the digit was the lowest bits of the key: a bucket beyond a batch holds > M3_CAP EQUAL keys.
-        // Its values, sorted, are the positions of that key in the input segment, in input order: the finish kernel
-        // regenerates them by a stable compaction of the segment instead of sorting.
-        int32_t base = 0;
-        if (lane == 0 && npush) base = atomicAdd(&a.m3.cnt->n_batches[list], npush);
-        base = __shfl_sync(0xffffffffu, base, 0);
-        for (int p = lane; p < npush; p += 32) {
-            const int b = s_push[w][p];
-            if (base + p >= a.m3.batch_max) {
-                atomicMax(a.err, SS_ERR_INTERNAL);
-                continue;
+    uint32_t run0_in = run0_lane;   // inclusive "latest defined"
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, run0_in, o);
+        if (lane >= o && run0_in == 0xffffffffu) run0_in = x;
+    }
+    uint32_t run0 = __shfl_up_sync(0xffffffffu, run0_in, 1);   // value entering this lane
+    if (lane == 0 || run0 == 0xffffffffu) run0 = 0u;
+    // group key of every ordinary bucket: (breaks before it, (Pi - 1) / GRP)
+    uint32_t key[8];
+    uint32_t last_key = 0xffffffffu;   // key of this lane's last ordinary bucket
+    {
+        uint32_t po = pord, pb = pbrk, r0 = run0;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            key[i] = 0xffffffffu;
+            if (kind[i] == 1u) {
+                po += v[i];
+                key[i] = (pb << 20) | ((po - r0 - 1u) / GRP);   // <= 256 breaks, < 2^20 groups (n < 2^31)
+                last_key = key[i];
             }
-            M3Batch B;
-            B.start = R.start + s_ex[w][b];
-            B.count = (int32_t)s_cnt[w][b];
-            B.klo = R.klo + (uint32_t)b;
-            B.sh = R.seg;
-            B.nslots = 1;
-            B.level = dst_level;
-            B.flags = M3_FLAG_EQUAL;
-            a.m3.batch[list][base + p] = B;
+            if (kind[i] >= 2u) {
+                pb++;
+                r0 = po;
+            }
+        }
+    }
+    // key of the ordinary bucket before / after this lane's buckets
+    uint32_t prev_in = last_key;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, prev_in, o);
+        if (lane >= o && prev_in == 0xffffffffu) prev_in = x;
+    }
+    uint32_t prev_key = __shfl_up_sync(0xffffffffu, prev_in, 1);
+    if (lane == 0) prev_key = 0xffffffffu;
+    uint32_t first_key = 0xffffffffu;   // key of this lane's first ordinary bucket
+#pragma unroll
+    for (int i = 7; i >= 0; i--)
+        if (kind[i] == 1u) first_key = key[i];
+    uint32_t next_in = first_key;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_down_sync(0xffffffffu, next_in, o);
+        if (lane + o < 32 && next_in == 0xffffffffu) next_in = x;
+    }
+    uint32_t next_key = __shfl_down_sync(0xffffffffu, next_in, 1);
+    if (lane == 31) next_key = 0xffffffffu;
+    // heads (first bucket of a group) and tails (last bucket); a tail emits the batch, so it needs its group's head
+    uint32_t head_mask = 0, tail_mask = 0;
+    {
+        uint32_t pk = prev_key;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (kind[i] == 1u) {
+                if (key[i] != pk) head_mask |= 1u << i;
+                pk = key[i];
+            }
+        }
+        uint32_t nk = next_key;
+#pragma unroll
+        for (int i = 7; i >= 0; i--) {
+            if (kind[i] == 1u) {
+                if (key[i] != nk) tail_mask |= 1u << i;
+                nk = key[i];
+            }
+        }
+    }
+    // the head of the group that is open when this lane starts: bucket index of the latest head in the lanes before
+    uint32_t lane_head = 0xffffffffu;
+#pragma unroll
+    for (int i = 0; i < 8; i++)
+        if (head_mask & (1u << i)) lane_head = (uint32_t)(lane * 8 + i);
+    uint32_t head_in = lane_head;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, head_in, o);
+        if (lane >= o && head_in == 0xffffffffu) head_in = x;
+    }
+    uint32_t open_head = __shfl_up_sync(0xffffffffu, head_in, 1);
+    if (lane == 0) open_head = 0xffffffffu;
+    // batches this lane emits (tails + dense buckets), ranges it queues
+    uint32_t n_emit = 0, n_push = 0, nt_lane = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        n_emit += ((tail_mask >> i) & 1u) + (kind[i] == 2u ? 1u : 0u);
+        if (kind[i] == 3u) {
+            n_push++;
+            nt_lane += (v[i] + SS_TILE - 1) / SS_TILE;
+        }
+    }
+    uint32_t e_inc = n_emit, p_inc = n_push, t_inc = nt_lane;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t x = __shfl_up_sync(0xffffffffu, e_inc, o), y = __shfl_up_sync(0xffffffffu, p_inc, o);
+        const uint32_t z = __shfl_up_sync(0xffffffffu, t_inc, o);
+        if (lane >= o) {
+            e_inc += x;
+            p_inc += y;
+            t_inc += z;
+        }
+    }
+    const uint32_t e_tot = __shfl_sync(0xffffffffu, e_inc, 31), p_tot = __shfl_sync(0xffffffffu, p_inc, 31);
+    const uint32_t t_tot = __shfl_sync(0xffffffffu, t_inc, 31);
+    const bool final_digit = R.shift == 0;   // by-value mode only (the stable mode returned above)
+    int32_t e_base = 0, p_base = 0, t_base = 0;
+    if (lane == 0) {
+        // by-value mode, final digit: queued buckets are > M3_CAP EQUAL keys, regenerated by the finish kernel
+        const uint32_t nb = e_tot + (final_digit ? p_tot : 0u);
+        if (nb) e_base = atomicAdd(&a.m3.cnt->n_batches[list], (int32_t)nb);
+        if (p_tot && !final_digit) {
+            p_base = atomicAdd(&a.m3.cnt->n_rng[round + 1], (int32_t)p_tot);
+            t_base = atomicAdd(&a.m3.cnt->n_tiles[round + 1], (int32_t)t_tot);
+        }
+    }
+    e_base = __shfl_sync(0xffffffffu, e_base, 0);
+    p_base = __shfl_sync(0xffffffffu, p_base, 0);
+    t_base = __shfl_sync(0xffffffffu, t_base, 0);
+    {
+        int32_t ei = e_base + (int32_t)(e_inc - n_emit);
+        uint32_t cur_head = open_head;
+        uint32_t exi = ex - t;   // exclusive prefix of this lane's first bucket (ex was advanced past the lane above)
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            const uint32_t b = (uint32_t)(lane * 8 + i);
+            if (head_mask & (1u << i)) cur_head = b;
+            if (tail_mask & (1u << i)) {
+                const uint32_t gstart = s_ex[w][cur_head];
+                m3_emit_batch(a, list, ei++, R.start + gstart, (int32_t)(exi + v[i] - gstart),
+                              R.klo + (cur_head << R.shift), (uint64_t)(b - cur_head + 1u) << R.shift, dst_level, 0);
+            }
+            if (kind[i] == 2u)
+                m3_emit_batch(a, list, ei++, R.start + exi, (int32_t)v[i], R.klo + (b << R.shift), (uint64_t)1 << R.shift,
+                              dst_level, 0);
+            exi += v[i];
+        }
+    }
+    if (p_tot == 0u) return;
+    if (final_digit) {
+        int32_t bi = e_base + (int32_t)e_tot + (int32_t)(p_inc - n_push);
+        uint32_t exi = ex - t;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (kind[i] == 3u) {
+                if (bi >= a.m3.batch_max) {
+                    atomicMax(a.err, SS_ERR_INTERNAL);
+                } else {
+                    M3Batch B;
+                    B.start = R.start + exi;
+                    B.count = (int32_t)v[i];
+                    B.klo = R.klo + (uint32_t)(lane * 8 + i);
+                    B.sh = R.seg;
+                    B.nslots = 1;
+                    B.level = dst_level;
+                    B.flags = M3_FLAG_EQUAL;
+                    a.m3.batch[list][bi] = B;
+                }
+                bi++;
+            }
+            exi += v[i];
         }
         return;
     }
-    for (int p = 0; p < npush; p++) {
-        const int b = s_push[w][p];
-        const uint32_t c = s_cnt[w][b];
-        const int32_t nt = (int32_t)((c + SS_TILE - 1) / SS_TILE);
-        int32_t idx = 0, tb = 0;
-        if (lane == 0) {
-            idx = atomicAdd(&a.m3.cnt->n_rng[round + 1], 1);
-            tb = atomicAdd(&a.m3.cnt->n_tiles[round + 1], nt);
-            if (idx < a.m3.rng_max && tb + nt <= a.m3.tiles_max) {
+    if ((int64_t)p_base + p_tot > a.m3.rng_max || (int64_t)t_base + t_tot > a.m3.tiles_max) {
+        atomicMax(a.err, SS_ERR_INTERNAL);
+        return;
+    }
+    {
+        int32_t pi = p_base + (int32_t)(p_inc - n_push), ti = t_base + (int32_t)(t_inc - nt_lane);
+        uint32_t exi = ex - t;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+            if (kind[i] == 3u) {
                 M3Range N;
-                N.start = R.start + s_ex[w][b];
-                N.size = (int32_t)c;
-                N.tile_base = tb;
-                N.klo = R.klo + ((uint32_t)b << R.shift);
+                N.start = R.start + exi;
+                N.size = (int32_t)v[i];
+                N.tile_base = ti;
+                N.klo = R.klo + ((uint32_t)(lane * 8 + i) << R.shift);
                 N.shift = R.shift > 8 ? R.shift - 8 : 0;
                 N.seg = R.seg;
                 N.pad = 0;
-                a.m3.rng[round + 1][idx] = N;
-            } else {
-                atomicMax(a.err, SS_ERR_INTERNAL);
-                idx = -1;
+                a.m3.rng[round + 1][pi] = N;
+                s_push[w][pi - p_base] = (uint8_t)(lane * 8 + i);   // <= 256 queued buckets per range
+                s_ptile[w][pi - p_base] = ti;
+                pi++;
+                ti += (int32_t)((v[i] + SS_TILE - 1) / SS_TILE);
             }
+            exi += v[i];
         }
-        idx = __shfl_sync(0xffffffffu, idx, 0);
-        tb = __shfl_sync(0xffffffffu, tb, 0);
-        if (idx < 0) continue;
+    }
+    __syncwarp();
+    // tile -> range entries and zeroed digit counts of the queued ranges, by the whole warp
+    for (uint32_t p = 0; p < p_tot; p++) {
+        const int b = s_push[w][p];
+        const int32_t idx = p_base + (int32_t)p, tb = s_ptile[w][p];
+        const int32_t nt = (int32_t)((s_cnt[w][b] + SS_TILE - 1) / SS_TILE);
         for (int32_t i = lane; i < nt; i += 32) a.m3.tile_rng[round + 1][tb + i] = idx;
         uint32_t *h2 = a.m3.hist[round + 1] + (size_t)idx * 256;
         for (int i = lane; i < 256; i += 32) h2[i] = 0u;
@@ -457,7 +587,7 @@ __device__ __forceinline__ uint32_t m3_rank_in_slot(const u64 *KV, uint32_t lo, 
 }
 
 #ifndef TDT_M3_HOT
-#define TDT_M3_HOT 64   // a batch goes through the bitonic network when sum(slot count ^ 2) > TDT_M3_HOT x elements
+#define TDT_M3_HOT 32   // a batch goes through the bitonic network when sum(slot count ^ 2) > TDT_M3_HOT x elements
 #endif
 
 // ---- finish: one ranking round in shared memory ---------------------------------------------------------------
