@@ -63,6 +63,12 @@ struct M3Range {   // a contiguous element range holding every element of key ra
     int32_t pad;
 };
 
+struct M3Tile {    // a 4096-element tile of a queued range: everything the hist / pass kernels need to start loading
+    int64_t t0;    // first element
+    int32_t cnt;   // elements (the last tile of a range may be short)
+    int32_t rng;   // its range
+};
+
 struct M3Batch {   // finish work item: `count` elements at `start`, keys in [klo, klo + (nslots << sh))
     int64_t start;
     int32_t count;
@@ -78,7 +84,7 @@ struct M3Counters {
 struct M3Layout {
     M3Counters *cnt;
     M3Range *rng[M3_ROUNDS];
-    int32_t *tile_rng[M3_ROUNDS];
+    M3Tile *tile_rng[M3_ROUNDS];
     uint32_t *hist[M3_ROUNDS];   // [range][256]
     M3Batch *batch[2];           // list 0: whole segments + round-0 groups; list 1: the later rounds
     int64_t rng_max, tiles_max, batch_max;
@@ -126,7 +132,7 @@ static inline int64_t ss_tiles_max(int64_t n, int64_t nl) {
 }
 static inline size_t m3_temp_bytes(int64_t n) {
     const int64_t r = m3_rng_max(n), tiles = ss_tiles_max(n, 0);
-    return (size_t)M3_ROUNDS * (((size_t)r * sizeof(M3Range) + 255) / 256 * 256 + ((size_t)tiles * 4 + 255) / 256 * 256 +
+    return (size_t)M3_ROUNDS * (((size_t)r * sizeof(M3Range) + 255) / 256 * 256 + ((size_t)tiles * sizeof(M3Tile) + 255) / 256 * 256 +
                                 ((size_t)r * 256 * 4 + 255) / 256 * 256) +
            2 * (((size_t)m3_batch_max(n) * sizeof(M3Batch) + 255) / 256 * 256) + 512;
 }
@@ -176,7 +182,7 @@ static inline M3Layout m3_layout(void *temp, int64_t n, int64_t nseg_max) {
     char *p = (char *)S.ghist + ss_align((size_t)S.nlarge_max * SS_MAX_PASSES * 256 * 4);
     for (int r = 0; r < M3_ROUNDS; r++) {
         M.rng[r] = (M3Range *)p; p += ss_align((size_t)M.rng_max * sizeof(M3Range));
-        M.tile_rng[r] = (int32_t *)p; p += ss_align((size_t)M.tiles_max * 4);
+        M.tile_rng[r] = (M3Tile *)p; p += ss_align((size_t)M.tiles_max * sizeof(M3Tile));
         M.hist[r] = (uint32_t *)p; p += ss_align((size_t)M.rng_max * 256 * 4);
     }
     for (int l = 0; l < 2; l++) {
@@ -318,7 +324,14 @@ __global__ void segsort_classify_kernel(SSArgs a) {
             rtodo &= rtodo - 1;
             const int32_t i2 = __shfl_sync(0xffffffffu, ri, src), t2 = __shfl_sync(0xffffffffu, rtb, src);
             const int32_t n2 = __shfl_sync(0xffffffffu, rnt, src);
-            for (int32_t t = lane; t < n2; t += 32) a.m3.tile_rng[0][t2 + t] = i2;
+            const int64_t q2 = __shfl_sync(0xffffffffu, q, src), z2 = __shfl_sync(0xffffffffu, size, src);
+            for (int32_t t = lane; t < n2; t += 32) {
+                M3Tile T;
+                T.t0 = q2 + (int64_t)t * SS_TILE;
+                T.cnt = (int32_t)(z2 - (int64_t)t * SS_TILE < SS_TILE ? z2 - (int64_t)t * SS_TILE : SS_TILE);
+                T.rng = i2;
+                a.m3.tile_rng[0][t2 + t] = T;
+            }
             uint32_t *h = a.m3.hist[0] + (size_t)i2 * 256;
             for (int i = lane; i < 256; i += 32) h[i] = 0u;
         }

@@ -66,9 +66,10 @@ __global__ void __launch_bounds__(SS_THREADS) m3_hist_kernel(SSArgs a, int round
     (void)src_v;
     if (threadIdx.x < 256) h[threadIdx.x] = 0u;
     __syncthreads();
-    int cur = a.m3.tile_rng[round][t_lo];
+    int cur = a.m3.tile_rng[round][t_lo].rng;
     for (int tile = t_lo; tile < t_hi; tile++) {
-        const int r = a.m3.tile_rng[round][tile];
+        const M3Tile T = a.m3.tile_rng[round][tile];
+        const int r = T.rng;
         if (r != cur) {   // uniform over the CTA
             __syncthreads();
             if (threadIdx.x < 256) {
@@ -79,10 +80,9 @@ __global__ void __launch_bounds__(SS_THREADS) m3_hist_kernel(SSArgs a, int round
             __syncthreads();
             cur = r;
         }
-        const M3Range R = a.m3.rng[round][r];
-        const int64_t t0 = R.start + (int64_t)(tile - R.tile_base) * SS_TILE;
-        const int64_t rem = R.start + R.size - t0;
-        const int cnt = rem < SS_TILE ? (int)rem : SS_TILE;
+        const M3Range R = a.m3.rng[round][r];   // (klo, shift): needed after the keys are on their way
+        const int64_t t0 = T.t0;
+        const int cnt = T.cnt;
         if (cnt == SS_TILE) {   // all loads of the tile in flight before the first atomic
             uint32_t k[SS_CHUNKS];
 #pragma unroll
@@ -422,7 +422,15 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
         const int b = s_push[w][p];
         const int32_t idx = p_base + (int32_t)p, tb = s_ptile[w][p];
         const int32_t nt = (int32_t)((s_cnt[w][b] + SS_TILE - 1) / SS_TILE);
-        for (int32_t i = lane; i < nt; i += 32) a.m3.tile_rng[round + 1][tb + i] = idx;
+        const int64_t rs = R.start + s_ex[w][b];
+        const int32_t rz = (int32_t)s_cnt[w][b];
+        for (int32_t i = lane; i < nt; i += 32) {
+            M3Tile T;
+            T.t0 = rs + (int64_t)i * SS_TILE;
+            T.cnt = rz - i * SS_TILE < SS_TILE ? rz - i * SS_TILE : SS_TILE;
+            T.rng = idx;
+            a.m3.tile_rng[round + 1][tb + i] = T;
+        }
         uint32_t *h2 = a.m3.hist[round + 1] + (size_t)idx * 256;
         for (int i = lane; i < 256; i += 32) h2[i] = 0u;
     }
@@ -442,7 +450,8 @@ __global__ void __launch_bounds__(SS_THREADS, STABLE ? TDT_SS_PASS_MINBLOCKS : 4
     uint32_t(*wh)[256] = (uint32_t(*)[256])p; p += STABLE ? SS_WARPS * 256 * 4 : 256 * 4;   // !STABLE: one counter row
     uint32_t(*mm)[256] = (uint32_t(*)[256])p; p += STABLE ? SS_MM * SS_WARPS * 256 * 4 : 0;
     uint32_t *bin = (uint32_t *)p; p += 256 * 4;
-    int64_t *gbase = (int64_t *)p;
+    int32_t *gbase = (int32_t *)p;   // destination of a digit's first element, relative to the range (32-bit offsets:
+                                     // the 64-bit form cost 8 more instructions per element in the write loop)
 
     const int n_tiles = a.m3.cnt->n_tiles[round];
     const uint32_t *src_k, *dk_c;
@@ -461,12 +470,12 @@ __global__ void __launch_bounds__(SS_THREADS, STABLE ? TDT_SS_PASS_MINBLOCKS : 4
         } else {
             if (threadIdx.x < 256) wh[0][threadIdx.x] = 0u;
         }
-        const int r = a.m3.tile_rng[round][tile];
+        const M3Tile T = a.m3.tile_rng[round][tile];   // the key loads below depend on this record alone
+        const int r = T.rng;
+        const int64_t t0 = T.t0;
+        const int cnt = T.cnt;
         const M3Range R = a.m3.rng[round][r];
         const int lt = tile - R.tile_base;
-        const int64_t t0 = R.start + (int64_t)lt * SS_TILE;
-        const int64_t rem = R.start + R.size - t0;
-        const int cnt = rem < SS_TILE ? (int)rem : SS_TILE;
         const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
         constexpr int epw = SS_TILE / SS_WARPS;
         const uint32_t klo = R.klo;
@@ -553,14 +562,16 @@ __global__ void __launch_bounds__(SS_THREADS, STABLE ? TDT_SS_PASS_MINBLOCKS : 4
                 }
                 st_volatile_u32(row, ss_pack(2u, epoch, before + total));
             }
-            if (threadIdx.x < 256) gbase[threadIdx.x] = R.start + (int64_t)gh + (int64_t)before - (int64_t)excl;
+            if (threadIdx.x < 256) gbase[threadIdx.x] = (int32_t)(gh + before - excl);
         }
         __syncthreads();
+        uint32_t *dk = dst_k + R.start;
+        int32_t *dv = dst_v + R.start;
         for (int i = threadIdx.x; i < cnt; i += SS_THREADS) {
             const uint2 kv = KV[i];
-            const int64_t g = gbase[dig(kv.x)] + i;
-            dst_k[g] = kv.x;
-            dst_v[g] = (int32_t)kv.y;
+            const int32_t g = gbase[dig(kv.x)] + i;
+            dk[g] = kv.x;
+            dv[g] = (int32_t)kv.y;
         }
         __syncthreads();
     }
@@ -750,6 +761,8 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
             if (t < M3_PAD) KV[count + t] = ~0ull;
             __syncthreads();
             if (BYVAL) {
+                uint32_t *ok = a.keys_out + g0;
+                int32_t *ov = a.vals_out + g0;
                 for (int base = 0; base < count; base += M3_THREADS) {   // uniform trip count: the ranking is warp-wide
                     const int i = base + t;
                     const bool live = i < count;
@@ -764,9 +777,9 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
                     }
                     const uint32_t rank = m3_rank_in_slot(KV, lo, hi, me);
                     if (live) {
-                        const int64_t g = g0 + lo + rank;
-                        a.keys_out[g] = k;
-                        a.vals_out[g] = (int32_t)(uint32_t)me;
+                        const uint32_t g = lo + rank;
+                        ok[g] = k;
+                        ov[g] = (int32_t)(uint32_t)me;
                     }
                 }
             } else {
@@ -792,7 +805,131 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
                 }
             }
         } else {
-            // crowded slots: bitonic network over the padded batch, same 64-bit (key, tie-break) words
+            // Crowded slots: equal-width slots do not fit this batch (clusters of a sparse pair: the batch spans
+            // megabases, a slot kilobases, and every cluster sits in one slot).  EQUI-DEPTH slots do: every 8th element
+            // (in source order) is a sample, the sorted samples are the splitters, an element's slot is the number of
+            // splitters <= its (key, tie-break) word -- about eight elements per slot whatever the distribution -- and
+            // the rest is the same count / scan / place / rank-in-slot sequence.  Shared memory: the 32 KB of the slot
+            // counters hold [0, 4 KB) the 1024 new counters, [8, 16 KB) the splitters, [16, 32 KB) the slot of every
+            // placed element (16 bits each).  Only heavy exact duplicates crowd equi-depth slots; they go to the
+            // bitonic network below.
+            u64 *SP = (u64 *)(cnt + 2048);
+            uint16_t *SL = (uint16_t *)(cnt + 4096);
+            auto word = [&](int c, int e) -> u64 { return ((u64)key[c] << 32) | (u64)(uint32_t)(BYVAL ? val[c] : e); };
+            auto slot_of = [&](u64 x) -> uint32_t {   // number of splitters <= x, capped at 1023
+                uint32_t pos = 0;
+#pragma unroll
+                for (uint32_t step = 512; step > 0; step >>= 1)
+                    if (SP[pos + step - 1] <= x) pos += step;
+                return pos;
+            };
+            for (int i = t; i < 1024; i += M3_THREADS) cnt[i] = 0u;
+            if ((t & 7) == 3) {   // e = c * 512 + t: e mod 8 == 3 for every c
+#pragma unroll
+                for (int c = 0; c < M3_EPT; c++) {
+                    const int e = c * M3_THREADS + t;
+                    SP[c * (M3_THREADS / 8) + (t >> 3)] = e < count ? word(c, e) : ~0ull;
+                }
+            }
+            if (t == 0) ws[33] = 0u;
+            __syncthreads();
+            for (int k = 2; k <= 1024; k <<= 1) {
+                for (int j = k >> 1; j > 0; j >>= 1) {
+                    const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1)), hi = lo | j;   // 512 threads, 512 pairs
+                    const u64 x = SP[lo], y = SP[hi];
+                    if ((x > y) == ((lo & k) == 0)) {
+                        SP[lo] = y;
+                        SP[hi] = x;
+                    }
+                    __syncthreads();
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < M3_EPT; c++) {
+                if (c * M3_THREADS >= count) break;
+                const int e = c * M3_THREADS + t;
+                if (e < count) atomicAdd(&cnt[slot_of(word(c, e))], 1u);
+            }
+            __syncthreads();
+            {   // scan of the 1024 counters: two per thread
+                const uint32_t c0 = cnt[2 * t], c1 = cnt[2 * t + 1];
+                uint32_t inc2 = c0 + c1;
+                const uint32_t mine = inc2;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t u = __shfl_up_sync(0xffffffffu, inc2, o);
+                    if (lane >= o) inc2 += u;
+                }
+                if (lane == 31) ws[warp] = inc2;
+                const uint32_t big = __reduce_max_sync(0xffffffffu, c0 > c1 ? c0 : c1);
+                if (lane == 0 && big > (uint32_t)M3_PAD) atomicMax(&ws[33], big);
+                __syncthreads();
+                uint32_t run2 = inc2 - mine;
+#pragma unroll
+                for (int w2 = 0; w2 < M3_THREADS / 32; w2++)
+                    if (w2 < warp) run2 += ws[w2];
+                cnt[2 * t] = run2;
+                cnt[2 * t + 1] = run2 + c0;
+            }
+            __syncthreads();
+            const bool dup = ws[33] != 0u;   // a slot beyond the padded reach of the ranking loop: heavy duplicates
+            if (!dup) {
+#pragma unroll
+                for (int c = 0; c < M3_EPT; c++) {
+                    if (c * M3_THREADS >= count) break;
+                    const int e = c * M3_THREADS + t;
+                    if (e < count) {
+                        const u64 x = word(c, e);
+                        const uint32_t sl = slot_of(x);
+                        const uint32_t pos = atomicAdd(&cnt[sl], 1u);   // afterwards cnt[sl] = END of slot sl
+                        KV[pos] = x;
+                        SL[pos] = (uint16_t)sl;
+                    }
+                }
+                if (t < M3_PAD) KV[count + t] = ~0ull;
+                __syncthreads();
+                if (BYVAL) {
+                    uint32_t *ok = a.keys_out + g0;
+                    int32_t *ov = a.vals_out + g0;
+                    for (int base = 0; base < count; base += M3_THREADS) {
+                        const int i = base + t;
+                        const bool live = i < count;
+                        const u64 me = live ? KV[i] : 0ull;
+                        uint32_t hi = 0, lo = 0;
+                        if (live) {
+                            const uint32_t sl = SL[i];
+                            hi = cnt[sl];
+                            lo = sl ? cnt[sl - 1] : 0u;
+                        }
+                        const uint32_t rank = m3_rank_in_slot(KV, lo, hi, me);
+                        if (live) {
+                            ok[lo + rank] = (uint32_t)(me >> 32);
+                            ov[lo + rank] = (int32_t)(uint32_t)me;
+                        }
+                    }
+                } else {
+#pragma unroll
+                    for (int c = 0; c < M3_EPT; c++) {
+                        if (c * M3_THREADS >= count) break;
+                        const int e = c * M3_THREADS + t;
+                        const bool live = e < count;
+                        const u64 me = word(c, e);
+                        uint32_t hi = 0, lo = 0;
+                        if (live) {
+                            const uint32_t sl = slot_of(me);
+                            hi = cnt[sl];
+                            lo = sl ? cnt[sl - 1] : 0u;
+                        }
+                        const uint32_t rank = m3_rank_in_slot(KV, lo, hi, me);
+                        if (live) {
+                            const int64_t g = g0 + lo + rank;
+                            a.keys_out[g] = key[c];
+                            a.vals_out[g] = val[c];
+                        }
+                    }
+                }
+            } else {
+            // heavy duplicates: bitonic network over the padded batch, same 64-bit (key, tie-break) words
             int P = 2;
             while (P < count) P <<= 1;
 #pragma unroll
@@ -834,6 +971,7 @@ __global__ void __launch_bounds__(M3_THREADS, 2) m3_finish_kernel(SSArgs a, int 
                         a.vals_out[g] = val[c];
                     }
                 }
+            }
             }
         }
         __syncthreads();   // KV / cnt / ws are rewritten by the next batch

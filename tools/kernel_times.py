@@ -9,19 +9,21 @@ import torch
 from tiddit_b200 import device_ops, synth, _lib
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
-a, b, off, L = synth.wgs30x_signals(n)
+tumor = os.environ.get("TDT_KT_WORKLOAD") == "tumor"   # BASELINE configs[4]: eps 1000, m 5
+EPS, M = (1000, 5) if tumor else (500, 3)
+a, b, off, L = (synth.tumor60x_signals if tumor else synth.wgs30x_signals)(n)
 rec = synth.signal_records(a, b, off)
 d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
 A, B, O = d(a), d(b), d(off)
 span, name, flags, same = d(rec["span"]), d(rec["name_id"]), d(rec["flags"]), d(rec["same_chrom"])
 P = len(off) - 1
-labels = device_ops.cluster_labels_device(A, B, O, P, 500, 3, L)
+labels = device_ops.cluster_labels_device(A, B, O, P, EPS, M, L)
 rows = torch.empty((n, 16), dtype=torch.int32, device="cuda")
 mem = torch.empty(n, dtype=torch.int32, device="cuda")
 counts = torch.zeros(4, dtype=torch.int64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
-calls = {"cluster": lambda: device_ops.cluster_labels_device(A, B, O, P, 500, 3, L, labels_out=labels),
-         "aggregate": lambda: device_ops.cluster_aggregate_device(labels, A, B, span, name, flags, O, same, P, 5000, False, 3, L, n, rows, mem, counts)}
+calls = {"cluster": lambda: device_ops.cluster_labels_device(A, B, O, P, EPS, M, L, labels_out=labels),
+         "aggregate": lambda: device_ops.cluster_aggregate_device(labels, A, B, span, name, flags, O, same, P, 5000, False, M, L, n, rows, mem, counts)}
 for what, fn in calls.items():
     fn(); fn()
     acc, reps = None, 5
