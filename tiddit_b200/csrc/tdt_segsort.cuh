@@ -236,6 +236,8 @@ bool segsort_want_heads(uint32_t *heads);
 static thread_local int g_ss_branch = 0;
 static thread_local cudaEvent_t g_ss_join2_ev[16 * SS_BRANCHES] = {};   // join of the generation-3 side chain
 static thread_local int g_ss_join2_idx = 0;
+static thread_local cudaEvent_t g_ss_join3_ev[16 * SS_BRANCHES] = {};
+static thread_local int g_ss_join3_idx = 0;
 static thread_local uint32_t *g_ss_heads_out = nullptr;   // set by segsort_want_heads for the NEXT segsort_pairs call
 void segsort_set_branch(int b) { g_ss_branch = b >= 0 && b < SS_BRANCHES ? b : 0; }
 
@@ -1075,10 +1077,29 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         TDT_CUDA(cudaStreamWaitEvent(side, fork_ev[dev_id], 0));
     }
 #endif
+    cudaStream_t side3 = st;   // the tiny-segment kernel's own branch (TDT_SS_TINY_BRANCH=1)
     if (segid) {
         int64_t blocks = (n_max + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        TDT_LAUNCH(segsort_tiny_kernel, (unsigned)blocks, 256, 0, side, a);
+        cudaStream_t ts = side;
+#if TDT_SS_FORK
+        const char *tb = getenv("TDT_SS_TINY_BRANCH");
+        if (tb && tb[0] == '1' && side != st) {
+            static thread_local cudaStream_t side3_streams[16 * SS_BRANCHES] = {};
+            static thread_local cudaEvent_t fork3_ev[16 * SS_BRANCHES] = {};
+            if (!side3_streams[dev_id]) {
+                TDT_CUDA(cudaStreamCreateWithFlags(&side3_streams[dev_id], cudaStreamNonBlocking));
+                TDT_CUDA(cudaEventCreateWithFlags(&fork3_ev[dev_id], cudaEventDisableTiming));
+                TDT_CUDA(cudaEventCreateWithFlags(&g_ss_join3_ev[dev_id], cudaEventDisableTiming));
+            }
+            side3 = side3_streams[dev_id];
+            TDT_CUDA(cudaEventRecord(fork3_ev[dev_id], st));
+            TDT_CUDA(cudaStreamWaitEvent(side3, fork3_ev[dev_id], 0));
+            g_ss_join3_idx = dev_id;
+            ts = side3;
+        }
+#endif
+        TDT_LAUNCH(segsort_tiny_kernel, (unsigned)blocks, 256, 0, ts, a);
     }
     int64_t nwin = (n_max + SS_WINDOW - 1) / SS_WINDOW;
     if (nwin > 148 * 4) nwin = 148 * 4;
@@ -1106,10 +1127,17 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         const int n_rounds = n_max > M3_CAP ? (key_bits + 7) / 8 : 0;
         const bool byval = vals_in == nullptr;   // value = element index: grows with the position
         // The finish kernel's CTAs are short-lived (a few batches each) instead of one persistent wave: the later
-        // rounds run next to it on a HIGH-PRIORITY side stream and take the SM resources a retiring CTA frees.
-        const int64_t fin_want = a.m3.batch_max < (int64_t)TDT_M3_FIN_WAVES * 2 * sm_count ? a.m3.batch_max
-                                                                                           : (int64_t)TDT_M3_FIN_WAVES * 2 * sm_count;
+        // rounds run next to it on a HIGH-PRIORITY side stream and take the SM resources a retiring CTA frees.  The
+        // grids follow the input size -- a CTA that finds no batch still costs its 96 KB shared-memory carve-out, and
+        // 2000 of them were 12 us of a 2.5 M-signal shard's sort.
+        const int64_t wave = 2 * (int64_t)sm_count;
+        int64_t fin_want = n_max / (M3_CAP / 2) + 64;   // about one CTA per expected batch
+        if (fin_want > (int64_t)TDT_M3_FIN_WAVES * wave) fin_want = (int64_t)TDT_M3_FIN_WAVES * wave;
+        if (fin_want > a.m3.batch_max) fin_want = a.m3.batch_max;
         const unsigned fin_grid = (unsigned)(fin_want > 0 ? fin_want : 1);
+        int64_t fin1_want = n_max / (4 * M3_CAP) + 64;   // the later rounds' list: usually a few pile-ups
+        if (fin1_want > 4 * wave) fin1_want = 4 * wave;
+        const unsigned fin1_grid = (unsigned)fin1_want;
         const char *ser = getenv("TDT_M3_SERIAL");   // measurement aid: everything on the caller's stream
         const bool serial = ser && ser[0] == '1';
         if (n_rounds > 0) {
@@ -1148,8 +1176,8 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
                 if (byval) TDT_LAUNCH(m3_pass_kernel<false>, utiles, SS_THREADS, M3_UPASS_SMEM, side2, a, round, round + 1);
                 else TDT_LAUNCH(m3_pass_kernel<true>, tiles, SS_THREADS, SS_PASS_SMEM, side2, a, round, round + 1);
             }
-            if (byval) TDT_LAUNCH(m3_finish_kernel<true>, fin_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
-            else TDT_LAUNCH(m3_finish_kernel<false>, fin_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
+            if (byval) TDT_LAUNCH(m3_finish_kernel<true>, fin1_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
+            else TDT_LAUNCH(m3_finish_kernel<false>, fin1_grid, M3_THREADS, M3_FIN_SMEM, side2, a, 1);
             TDT_M3_DEBUG_DUMP(side2, "list 1");
         }
         if (n_max > SS_LOCAL_MAX) {
@@ -1170,6 +1198,10 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         int32_t *dv = to_out ? vals_out : vals_tmp;
         TDT_LAUNCH(segsort_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, st, a, pass, sk, sv, dk, dv);
     }
+    }
+    if (side3 != st) {
+        TDT_CUDA(cudaEventRecord(g_ss_join3_ev[g_ss_join3_idx], side3));
+        TDT_CUDA(cudaStreamWaitEvent(st, g_ss_join3_ev[g_ss_join3_idx], 0));
     }
     if (side2 != st) {
         TDT_CUDA(cudaEventRecord(g_ss_join2_ev[g_ss_join2_idx], side2));

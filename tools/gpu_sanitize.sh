@@ -45,6 +45,37 @@ os.environ["TDT_SEGSORT_V2"] = "1"
 assert np.array_equal(device_ops.cluster_labels(a2, b2, off2, 500, 3, L2), want2)
 assert np.array_equal(device_ops.cluster_labels(a, b, off, 500, 3, L), lab)
 del os.environ["TDT_SEGSORT_V2"]
+# generation 3 of the segmented sort (tdt_segsort3.cuh): by-value mode (value = element index) and, forced, the stable mode;
+# clustered keys (equi-depth path), pile-ups (later rounds), > 8192 equal keys (compaction path / copy batches), narrow keys
+import torch
+def sort_case(keys, sizes, key_bits, with_vals):
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    n = int(off[-1])
+    vals = np.random.default_rng(3).permutation(n).astype(np.int32) if with_vals else np.arange(n, dtype=np.int32)
+    k = torch.from_numpy(keys.astype(np.int64).astype(np.uint32).view(np.int32)).cuda()
+    v = torch.from_numpy(vals).cuda() if with_vals else None
+    ko, vo = device_ops.segsort_device(k, v, torch.from_numpy(off).cuda(), key_bits, None)
+    ko, vo = ko.cpu().numpy().view(np.uint32), vo.cpu().numpy()
+    for s in range(len(sizes)):
+        lo, hi = off[s], off[s + 1]
+        order = np.argsort(keys[lo:hi], kind="stable")
+        assert np.array_equal(ko[lo:hi], keys[lo:hi][order].astype(np.uint32)) and np.array_equal(vo[lo:hi], vals[lo:hi][order])
+r3 = np.random.default_rng(11)
+sizes3 = [90_000, 9000, 30_000, 8193, 5000]
+n3 = sum(sizes3)
+for key_bits in (28, 20):
+    hi = 1 << key_bits
+    centres = r3.integers(0, hi, 300)
+    clustered = np.clip(centres[r3.integers(0, 300, n3)] + r3.integers(-100, 100, n3), 0, hi - 1)
+    hot = r3.integers(0, hi, n3); m = r3.random(n3) < 0.7; hot[m] = hi // 2 + r3.integers(0, 3, int(m.sum()))
+    equal = np.full(n3, hi - 5)
+    narrow = hi // 3 + r3.integers(0, 40, n3)
+    for keys in (clustered, hot, equal, narrow):
+        for mode, with_vals in (("", False), ("msd", True), ("", True)):
+            if mode:
+                os.environ["TDT_SEGSORT"] = mode
+            sort_case(keys, sizes3, key_bits, with_vals)
+            os.environ.pop("TDT_SEGSORT", None)
 print("sanitizer target ok")
 PY
 for tool in memcheck racecheck synccheck; do
