@@ -236,8 +236,6 @@ bool segsort_want_heads(uint32_t *heads);
 static thread_local int g_ss_branch = 0;
 static thread_local cudaEvent_t g_ss_join2_ev[16 * SS_BRANCHES] = {};   // join of the generation-3 side chain
 static thread_local int g_ss_join2_idx = 0;
-static thread_local cudaEvent_t g_ss_join3_ev[16 * SS_BRANCHES] = {};
-static thread_local int g_ss_join3_idx = 0;
 static thread_local uint32_t *g_ss_heads_out = nullptr;   // set by segsort_want_heads for the NEXT segsort_pairs call
 void segsort_set_branch(int b) { g_ss_branch = b >= 0 && b < SS_BRANCHES ? b : 0; }
 
@@ -1055,7 +1053,6 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     // The tiny / small-segment kernels and the large-segment chain (hist, scan, passes) touch disjoint segments, and
     // neither fills the machine on its own (both wait on latencies): they run as two branches -- a side stream forked
     // here and joined after the last pass; inside a CUDA-graph capture the fork / join become parallel graph branches.
-    // (A third branch for the tiny-segment kernel measured the same as two: 1.277 vs 1.268 ms for the 30X step.)
 #ifndef TDT_SS_FORK
 #define TDT_SS_FORK 1
 #endif
@@ -1077,29 +1074,13 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         TDT_CUDA(cudaStreamWaitEvent(side, fork_ev[dev_id], 0));
     }
 #endif
-    cudaStream_t side3 = st;   // the tiny-segment kernel's own branch (TDT_SS_TINY_BRANCH=1)
+    // (The tiny-segment kernel on a branch of its own: 1.277 vs 1.268 ms for the 30X step in r01, 3.906 vs 3.944 ms on
+    // the tumour set in r02 -- within noise.  Started BEFORE the classify kernel, which it does not need: its 4736 CTAs
+    // fill the SMs first and hold back classify and everything behind it, posB sort 0.274 -> 0.303 ms.)
     if (segid) {
         int64_t blocks = (n_max + 255) / 256;
         if (blocks > 148 * 32) blocks = 148 * 32;
-        cudaStream_t ts = side;
-#if TDT_SS_FORK
-        const char *tb = getenv("TDT_SS_TINY_BRANCH");
-        if (tb && tb[0] == '1' && side != st) {
-            static thread_local cudaStream_t side3_streams[16 * SS_BRANCHES] = {};
-            static thread_local cudaEvent_t fork3_ev[16 * SS_BRANCHES] = {};
-            if (!side3_streams[dev_id]) {
-                TDT_CUDA(cudaStreamCreateWithFlags(&side3_streams[dev_id], cudaStreamNonBlocking));
-                TDT_CUDA(cudaEventCreateWithFlags(&fork3_ev[dev_id], cudaEventDisableTiming));
-                TDT_CUDA(cudaEventCreateWithFlags(&g_ss_join3_ev[dev_id], cudaEventDisableTiming));
-            }
-            side3 = side3_streams[dev_id];
-            TDT_CUDA(cudaEventRecord(fork3_ev[dev_id], st));
-            TDT_CUDA(cudaStreamWaitEvent(side3, fork3_ev[dev_id], 0));
-            g_ss_join3_idx = dev_id;
-            ts = side3;
-        }
-#endif
-        TDT_LAUNCH(segsort_tiny_kernel, (unsigned)blocks, 256, 0, ts, a);
+        TDT_LAUNCH(segsort_tiny_kernel, (unsigned)blocks, 256, 0, side, a);
     }
     int64_t nwin = (n_max + SS_WINDOW - 1) / SS_WINDOW;
     if (nwin > 148 * 4) nwin = 148 * 4;
@@ -1198,10 +1179,6 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
         int32_t *dv = to_out ? vals_out : vals_tmp;
         TDT_LAUNCH(segsort_pass_kernel, tiles, SS_THREADS, SS_PASS_SMEM, st, a, pass, sk, sv, dk, dv);
     }
-    }
-    if (side3 != st) {
-        TDT_CUDA(cudaEventRecord(g_ss_join3_ev[g_ss_join3_idx], side3));
-        TDT_CUDA(cudaStreamWaitEvent(st, g_ss_join3_ev[g_ss_join3_idx], 0));
     }
     if (side2 != st) {
         TDT_CUDA(cudaEventRecord(g_ss_join2_ev[g_ss_join2_idx], side2));

@@ -16,12 +16,9 @@ PY
 run default30 --steps 20 --warmup 3
 run small30 --steps 20 --warmup 3 --signals 2500000
 run tumor --workload tumor60x --steps 10 --warmup 3
-TDT_SS_TINY_BRANCH=1 run tumor_branch --workload tumor60x --steps 10 --warmup 3
-TDT_SS_TINY_BRANCH=1 run default30_branch --steps 20 --warmup 3
 for v in t256 t512; do
   export TDT_B200_LIB=$PWD/tiddit_b200/_variants/libtdt_b200_$v.so
   run tumor_$v --workload tumor60x --steps 10 --warmup 3
-  TDT_SS_TINY_BRANCH=1 run tumor_${v}_branch --workload tumor60x --steps 10 --warmup 3
   run default30_$v --steps 20 --warmup 3
 done
 unset TDT_B200_LIB
