@@ -1,20 +1,16 @@
-"""GPU: the hand-written segmented radix sort (tdt_segsort.cuh) against numpy's stable sort per segment."""
+"""GPU: the hand-written segmented sort (tdt_segsort.cuh, tdt_segsort3.cuh) against numpy's stable sort per segment."""
 import numpy as np
 import pytest
 
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=["auto", "msd", "lsd", "samplesort"], autouse=True)
+@pytest.fixture(params=["auto", "msd", "lsd"], autouse=True)
 def sort_generation(request, monkeypatch):
     """Every test runs on the production dispatch (generation 3 -- MSD rounds + shared-memory finish, tdt_segsort3.cuh --
-    for index-valued sorts, the LSD chain otherwise), on each chain forced for every sort (TDT_SEGSORT=msd / lsd) and on
-    the sample-sort generation (tdt_segsort2.cuh, TDT_SEGSORT_V2=1)."""
-    monkeypatch.delenv("TDT_SEGSORT_V2", raising=False)
+    for index-valued sorts, the LSD chain otherwise) and on each chain forced for every sort (TDT_SEGSORT=msd / lsd)."""
     monkeypatch.delenv("TDT_SEGSORT", raising=False)
-    if request.param == "samplesort":
-        monkeypatch.setenv("TDT_SEGSORT_V2", "1")
-    elif request.param in ("lsd", "msd"):
+    if request.param in ("lsd", "msd"):
         monkeypatch.setenv("TDT_SEGSORT", request.param)
     return request.param
 
@@ -85,8 +81,8 @@ def test_segsort_many_tiny_and_huge_mix():
 
 @pytest.mark.parametrize("kind", ["all_equal", "two_values", "pileup", "hotspot", "narrow", "boundaries", "sorted", "reversed"])
 def test_segsort_skewed_distributions(kind):
-    """What the sample-sort rounds and the interpolation finish must survive: heavy exact duplicates (the buckets cannot be
-    cut: LSD chain), pile-ups inside an otherwise uniform segment, a 2 kb hotspot, segment sizes around the local limit."""
+    """What the partition rounds and the shared-memory finish must survive: heavy exact duplicates, pile-ups inside an
+    otherwise uniform segment, a 2 kb hotspot, segment sizes around the batch capacity."""
     rng = np.random.default_rng(sum(map(ord, kind)))
     if kind == "boundaries":
         sizes = [6143, 6144, 6145, 8191, 8192, 8193, 33, 32, 31, 1, 2, 12288, 12289, 0, 20000]

@@ -24,7 +24,7 @@
 //                        count:~first), distinct-name counts
 //   agg_finalize         the branch logic of :265-330, one 16-int row per candidate
 #include "tdt_common.cuh"
-#include "tdt_segsort2.cuh"
+#include "tdt_segsort.cuh"
 
 namespace tdt {
 

@@ -23,7 +23,7 @@
 //   final_labels                 reference ids scattered back to insertion order
 #include "tdt_common.cuh"
 #define TDT_SEGSORT_IMPL
-#include "tdt_segsort2.cuh"
+#include "tdt_segsort.cuh"
 
 namespace tdt {
 

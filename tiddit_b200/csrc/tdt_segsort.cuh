@@ -137,6 +137,10 @@ static inline size_t m3_temp_bytes(int64_t n) {
            2 * (((size_t)m3_batch_max(n) * sizeof(M3Batch) + 255) / 256 * 256) + 512;
 }
 
+static inline size_t segsort1_temp_bytes(int64_t n, int64_t nseg_max);
+// what callers reserve
+static inline size_t segsort_temp_bytes(int64_t n, int64_t nseg_max) { return segsort1_temp_bytes(n, nseg_max); }
+
 static inline size_t segsort1_temp_bytes(int64_t n, int64_t nseg_max) {
     const int64_t nl = ss_nlarge_max(n, nseg_max);
     const int64_t tiles = ss_tiles_max(n, nl);
@@ -360,18 +364,6 @@ __global__ void segsort_classify_kernel(SSArgs a) {
         uint32_t *h = a.L.ghist + (size_t)i2 * SS_MAX_PASSES * 256;
         for (int i = lane; i < SS_MAX_PASSES * 256; i += 32) h[i] = 0u;
     }
-}
-
-// one CTA per large segment: its tile -> segment entries and its zeroed digit histograms (callers that queue large
-// segments themselves -- the sample sort's leftovers -- still use it)
-__global__ void __launch_bounds__(256) segsort_fill_kernel(SSArgs a) {
-    const int idx = blockIdx.x;
-    if (idx >= a.L.cnt->n_large) return;
-    const SSLarge L = a.L.large[idx];
-    const int32_t nt = (int32_t)((L.size + SS_TILE - 1) / SS_TILE);
-    for (int32_t t = threadIdx.x; t < nt; t += 256) a.L.tile_seg[L.tile_base + t] = idx;
-    uint32_t *h = a.L.ghist + (size_t)idx * SS_MAX_PASSES * 256;
-    for (int i = threadIdx.x; i < SS_MAX_PASSES * 256; i += 256) h[i] = 0u;
 }
 
 #ifndef TDT_SS_TINY_SPLIT
@@ -1192,6 +1184,22 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
 #endif
     return TDT_OK;
 }
+bool segsort_want_heads(uint32_t *heads) {
+    g_ss_heads_out = heads;
+    return true;
+}
+
+// The entry every caller uses.  (r02 also carried a sample-sort generation -- splitter plan, bucket histogram, partition
+// pass, shared-memory interpolation finish; tdt_segsort2.cuh, commit 8a338c8 -- as an opt-in A/B: parity-green, partition
+// round 0.28 ms, finish 1.9 / 4.1 ms for posA / posB.  Generation 3 superseded it and it was removed)
+int segsort_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *keys_out, int32_t *vals_out,
+                  uint32_t *keys_tmp, int32_t *vals_tmp, const int64_t *off, const int64_t *dims, const int32_t *segid,
+                  int64_t n_max, int64_t nseg_max, int key_bits, void *temp, size_t temp_bytes, int *err,
+                  cudaStream_t st) {
+    return segsort1_pairs(keys_in, vals_in, keys_out, vals_out, keys_tmp, vals_tmp, off, dims, segid, n_max, nseg_max,
+                          key_bits, temp, temp_bytes, err, st);
+}
+
 #endif  // TDT_SEGSORT_IMPL
 
 }  // namespace tdt

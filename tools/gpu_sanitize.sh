@@ -37,14 +37,14 @@ for x, y in zip(s[:2000].tolist(), e[:2000].tolist()):
     cq = tiddit_coverage.update_coverage(x, y, 500, cq, eq)
 want = np.zeros(len(cq)); oracle.update_coverage_batch(s[:2000], e[:2000], 500, want, eq)
 assert np.array_equal(np.asarray(cq).view(np.uint64), want.view(np.uint64))
-# one large pair (large-segment chain of the LSD sort), then the same through the sample-sort generation
+# one large pair (large-segment chain: generation 3 for posA, LSD for posB), then everything through the LSD chain
 a2, b2, off2, L2 = synth.config2_signals(40_000, n_clusters=800)
 want2 = oracle.cluster_segments(a2, b2, off2, 500, 3)
 assert np.array_equal(device_ops.cluster_labels(a2, b2, off2, 500, 3, L2), want2)
-os.environ["TDT_SEGSORT_V2"] = "1"
+os.environ["TDT_SEGSORT"] = "lsd"
 assert np.array_equal(device_ops.cluster_labels(a2, b2, off2, 500, 3, L2), want2)
 assert np.array_equal(device_ops.cluster_labels(a, b, off, 500, 3, L), lab)
-del os.environ["TDT_SEGSORT_V2"]
+del os.environ["TDT_SEGSORT"]
 # generation 3 of the segmented sort (tdt_segsort3.cuh): by-value mode (value = element index) and, forced, the stable mode;
 # clustered keys (equi-depth path), pile-ups (later rounds), > 8192 equal keys (compaction path / copy batches), narrow keys
 import torch
