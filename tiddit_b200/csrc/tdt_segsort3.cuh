@@ -442,6 +442,9 @@ __global__ void __launch_bounds__(256) m3_plan_kernel(SSArgs a, int round, int d
 // so an element's place among the tile's equal digits is simply what ONE shared-memory atomicAdd on the digit's counter
 // returns: ~6 instead of ~33 instructions per element for the ranking, no per-warp counter arrays (16 KB less shared
 // memory per CTA).
+// (Measured and dropped: a second instantiation of the tile body for FULL tiles, without the sixteen bound checks of the
+//  load / count / scatter phases -- the unrolled code spills at the 64-register cap that four CTAs per SM need: 95.6 vs
+//  89 us; three CTAs per SM at 85 registers: no better.)
 template <bool STABLE>
 __global__ void __launch_bounds__(SS_THREADS, STABLE ? TDT_SS_PASS_MINBLOCKS : 4) m3_pass_kernel(SSArgs a, int round, int dst_level) {
     extern __shared__ __align__(16) unsigned char ss_smem[];
