@@ -1166,11 +1166,6 @@ static int pos_bits(int32_t max_pos) { return bit_width_u32(max_pos > 0 ? (uint3
 
 // y-pass on the compacted (posB, insertion index, x-run) triples in ykey/yval/gx with offsets goff and
 // sizes dims_y; writes the final ids.  PLAIN: caller ids (stand-alone y-pass).
-static inline bool early_label_fill() {
-    const char *e = getenv("TDT_EARLY_FILL");
-    return e && e[0] == '1';
-}
-
 template <bool PLAIN>
 static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, int key_bits, int P,
                      int32_t plain_cluster_id, int32_t *rank_of, int32_t *labels_out, int32_t *cluster_id_out,
@@ -1238,7 +1233,6 @@ static int run_ypass(const ClusterPlan &pl, Buffers &b, int32_t eps, int32_t m, 
     f.labels_out = labels_out;
     f.cluster_id_out = cluster_id_out;
     ProfScope ps("final_labels", st);
-    if (!PLAIN && !early_label_fill()) TDT_CUDA(cudaMemsetAsync(labels_out, 0xff, (size_t)n * 4, st));
     TDT_LAUNCH(final_labels_kernel<PLAIN>, (unsigned)wr_tiles(n), WR_THREADS, 0, st, f);
     return TDT_OK;
 }
@@ -1252,9 +1246,9 @@ static int cluster_impl(const int32_t *posA, const int32_t *posB, const int64_t 
     if (!b.ok) return fail(TDT_E_WORKSPACE, "workspace of %zu bytes given, %zu needed", ws_bytes, pl.total);
     const int key_bits = pos_bits(max_pos);
 
-    // labels start as -1 (noise).  The fill runs right before the scatter (run_ypass) unless TDT_EARLY_FILL=1: issued here
-    // its 80 MB are long evicted when final_labels stores into them, issued there the stores hit lines that are still in L2
-    if (early_label_fill()) TDT_CUDA(cudaMemsetAsync(labels_out, 0xff, (size_t)n * 4, st));
+    // labels start as -1 (noise).  (Issued right before the scatter instead -- so that final_labels stores into lines
+    // that are still in L2 -- measured the same: 0.9946 vs 0.9906 ms for the 30X step.)
+    TDT_CUDA(cudaMemsetAsync(labels_out, 0xff, (size_t)n * 4, st));
     TDT_CUDA(cudaMemsetAsync(b.headsX, 0, zero_span(pl), st));
     TDT_LAUNCH(set_dims_kernel, 1, 1, 0, st, &b.small->dims_x, n, (int64_t)P, b.small->off2);
 
