@@ -1,4 +1,4 @@
-// tdt_segsort.cuh -- hand-written segmented, stable LSD radix sort of (u32 key, i32 value) pairs (sm_100a).
+// tdt_segsort.cuh -- hand-written segmented, stable sort of (u32 key, i32 value) pairs (sm_100a).
 //
 // The clustering path sorts twice, and both sorts are SEGMENTED: signals by posA inside every
 // (chrA,chrB) pair (tiddit_cluster.pyx:152) and x-cluster members by posB inside every x-cluster
@@ -6,14 +6,16 @@
 // [off[s], off[s+1]) before and after the sort) the keys stay 32 bits -- the coordinate alone -- instead of
 // the 64-bit (segment, coordinate) composites a flat device-wide sort needs.  Three size classes:
 //
-//   tiny   (<= tiny_max elements, only when the caller has a per-element segment id; nearly all x-clusters):
+//   tiny   (<= tiny_max = 128 elements, only when the caller has a per-element segment id; nearly all x-clusters):
 //          one thread per element counts the members of its segment that precede it -- no shared memory;
-//   small  (<= SS_LOCAL_MAX): CTA k gathers the small segments that START in element window [k*W, (k+1)*W)
+//   small  (<= SS_LOCAL_MAX = 2048): CTA k gathers the small segments that START in element window [k*W, (k+1)*W)
 //          into shared memory and sorts them together by (local segment index, key) with 8-bit LSD passes:
 //          one global read and one global write per element;
-//   large  : onesweep-style passes over 4096-element tiles that never straddle a segment: digit histograms
-//          of all passes up front, then per pass a stable in-tile ranking, a per-digit decoupled look-back
-//          over the EARLIER TILES OF THE SAME SEGMENT and a digit-ordered write through shared memory.
+//   large  : two chains.  Generation 3 (tdt_segsort3.cuh, the default for sorts whose value is the element index): one
+//          most-significant-digit partition round + one shared-memory finish per element.  LSD chain (sorts with
+//          explicit values; TDT_SEGSORT=lsd): onesweep-style passes over 4096-element tiles that never straddle a
+//          segment: digit histograms of all passes up front, then per pass a stable in-tile ranking, a per-digit
+//          decoupled look-back over the EARLIER TILES OF THE SAME SEGMENT and a digit-ordered write through shared memory.
 //
 // Stable ranking (small + large): a warp owns a contiguous run of the tile and walks it 32 elements at a time;
 // lanes with equal digits find each other through a shared-memory atomicOr of their lane bits, the lowest
