@@ -959,9 +959,10 @@ namespace tdt {
 
 // Which large-segment chain.  Default: generation 3 (MSD rounds + shared-memory finish, tdt_segsort3.cuh) for sorts
 // whose value is the element index (vals_in == nullptr: the posA sort of all pairs, the aggregation's sub-sorts) --
-// measured on B200 (30X set): 0.61 -> 0.xx ms for posA -- and the four stable LSD passes otherwise: the sorts with
-// explicit values (posB inside x-runs, grouping by candidate) have a few dozen large segments, all of them pile-ups
-// that need the later rounds, and the LSD chain is quicker there (0.335 vs 0.43 ms for posB).
+// measured on B200 (30X set): 0.61 -> 0.39 ms for posA -- and the four stable LSD passes otherwise: generation 3's
+// stable mode pays the warp-private ranking in its pass and scattered stores in its finish, and the sorts with explicit
+// values have few large segments, most of them pile-ups that need the later rounds (forced for every sort, final tree:
+// posB inside x-runs 0.354 vs 0.275 ms, grouping by candidate 0.570 vs 0.342 ms).
 // TDT_SEGSORT=lsd / msd in the environment (read at every call) forces one chain for every sort (A/B runs, tests).
 static inline bool ss_use_msd(bool value_is_index) {
     const char *e = getenv("TDT_SEGSORT");
