@@ -10,6 +10,17 @@ from conftest import GOLDEN
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=["default", "0", "4", "1024"], autouse=True)
+def direct_threshold(request, monkeypatch):
+    """Every test runs with the production threshold of the direct modes / names kernel (candidates of up to 256 members),
+    with the kernel off (every candidate through the three sub-sorts), with a threshold of 4 (most candidates take the
+    compaction + sort path of the big candidates) and at the kernel's limit (tdt_aggregate.cu, TDT_AGG_DIRECT)."""
+    monkeypatch.delenv("TDT_AGG_DIRECT", raising=False)
+    if request.param != "default":
+        monkeypatch.setenv("TDT_AGG_DIRECT", request.param)
+    return request.param
+
+
 def _agg_equal(got, want):
     """(rows, members) equal up to the placement of the member blocks inside member_idx."""
     gr, gm = got
@@ -82,6 +93,36 @@ def test_aggregate_edge_cases(oracle):
     bad[7] = 4000      # pair 1 has 2000 signals
     with pytest.raises(Exception):
         device_ops.cluster_aggregate(bad, posA, posB, span, names, flags, off, same, 20, False, 3)
+
+
+def test_aggregate_ties_small_and_big_candidates(oracle):
+    """Candidates of 1 ... 3000 members side by side, few distinct positions and names per candidate: every mode is
+    decided by the first-inserted tie-break, members of one candidate spread over several warps / CTAs, candidates
+    around every threshold of the direct kernel (4, 128, 1024) and around a warp boundary."""
+    from tiddit_b200 import device_ops
+    rng = np.random.default_rng(11)
+    sizes = [1, 2, 3, 4, 5, 31, 32, 33, 64, 127, 128, 129, 130, 255, 256, 257, 700, 1023, 1024, 1025, 3000] + \
+        rng.integers(1, 40, 400).tolist()
+    per_pair = [sizes[0::3], sizes[1::3], sizes[2::3]]
+    labels, off = [], [0]
+    for ps in per_pair:
+        lab = np.repeat(np.arange(len(ps)), ps)
+        lab = np.concatenate([lab, np.full(50, -1)])          # noise in between
+        rng.shuffle(lab)                                      # members of a candidate are not neighbours in the input
+        labels.append(lab)
+        off.append(off[-1] + len(lab))
+    labels = np.concatenate(labels).astype(np.int32)
+    n = len(labels)
+    posA = rng.integers(100, 104, n).astype(np.int32)         # four values: ties everywhere
+    posB = (posA + rng.integers(0, 3, n)).astype(np.int32)
+    span = np.stack([posA - rng.integers(0, 9, n), posA + 1, posB, posB + rng.integers(1, 9, n)], axis=1).astype(np.int32)
+    names = rng.integers(0, 6, n).astype(np.int32)
+    kinds = rng.integers(0, 3, n).astype(np.uint8)
+    flags = kinds | rng.choice([0x04, 0x08], n).astype(np.uint8) | rng.choice([0x10, 0x20], n).astype(np.uint8)
+    same = np.array([1, 0, 1], dtype=np.uint8)
+    for min_reads in (1, 3, 2000):
+        args = (labels, posA, posB, span, names, flags, np.asarray(off, np.int64), same, 20, False, min_reads)
+        _agg_equal(device_ops.cluster_aggregate(*args), oracle.cluster_aggregate(*args))
 
 
 def test_cluster_packed_roundtrip(tmp_path, oracle):

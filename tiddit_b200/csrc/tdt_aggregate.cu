@@ -19,9 +19,14 @@
 //   agg_rank_scan        chained scan over insertion order: rank of every candidate by first appearance
 //   agg_gather           per member: (kind,posA) (kind,posB) (kind,name) sort keys; min/max/orientation sums by a
 //                        segmented warp reduction, one atomic per (candidate, warp)
-//   segsort #2..#4       inside every candidate by (kind,posA), (kind,posB), (kind,name)   [tiny-segment path]
+//   agg_direct           candidates of <= direct_max members (nearly all; default 256): every member counts its equals
+//                        among the candidate's members directly -- mode with first-inserted tie-break as a warp-
+//                        segmented max of (count : ~position), distinct names as the members without an earlier
+//                        equal; members of LARGER candidates are compacted into the "big" arrays instead
+//   segsort #2..#4       inside every big candidate by (kind,posA), (kind,posB), (kind,name)
 //   agg_runs             runs of equal keys: mode with first-inserted tie-break (64-bit atomicMax of
 //                        count:~first), distinct-name counts
+//                        (TDT_AGG_DIRECT=0: no direct kernel, every candidate goes through the three sorts)
 //   agg_finalize         the branch logic of :265-330, one 16-int row per candidate
 #include "tdt_common.cuh"
 #include "tdt_segsort.cuh"
@@ -34,6 +39,13 @@ constexpr int AG_TILE = AG_THREADS * AG_ITEMS;
 constexpr int AG_ACC = 12;    // int32 accumulators per candidate
 constexpr int AG_MODES = 6;   // u64 (count:~first) per side x kind
 enum { AG_ERR_LABEL = 8, AG_ERR_POS = 9, AG_ERR_NAME = 10 };
+constexpr int AG_DIRECT_RB = 10;                       // bits of the in-candidate position in a packed (count : ~position) word
+constexpr int AG_DIRECT_LIMIT = 1 << AG_DIRECT_RB;     // largest candidate the direct kernel can be given
+#ifndef TDT_AGG_DIRECT_DEFAULT
+#define TDT_AGG_DIRECT_DEFAULT 256   // O(k) work per member.  B200, whole call (tools/agg_direct_ab.py), 30X set / tumour set:
+                                     // 0 (all sorts) 2.23 / 3.60 ms, 32: 2.03 / 3.79, 64: 1.80 / 3.44, 128: 1.79 / 3.00,
+                                     // 256: 1.79 / 2.82, 1024: 1.79 / 2.87
+#endif
 
 struct AggDims {
     int64_t n, nseg;
@@ -45,6 +57,9 @@ struct AggSmall {                // one 256-byte aligned record of device-side s
     u32 ticket[4];
     int err;
     int pad[3];
+    AggDims d3;                  // {members of the big candidates, big candidates}: what the sub-sorts see in direct mode
+    u64 big_ctr;                 // (big candidates << 32) | their members: ONE atomic reserves a slot and a member range
+    u64 pad2;
 };
 
 struct AggParams {
@@ -74,6 +89,13 @@ struct AggParams {
     u64 *modes;          // [G][AG_MODES]
     u32 *ncnt;           // [G][4]
     u64 *status1, *status2, *status3;
+    // direct mode: candidates beyond direct_max members ("big"), compacted for the sub-sorts
+    int direct_max;      // 0: no direct kernel
+    int2 *big;           // [G]   {first position in the big arrays, big slot}; written for big candidates only
+    int64_t *goff_big;   // [B+1] offsets of the big candidates into the big arrays
+    int32_t *bigg;       // [B]   candidate of a big slot
+    u32 *bkA, *bkB, *bkN;           // [M] sub-sort keys of the big candidates' members
+    int32_t *bgrp, *borig;          // [M] big slot / compact position of the same
     // outputs
     int32_t *cand_out, *member_idx;
     int64_t *counts_out;
@@ -337,6 +359,22 @@ __global__ void __launch_bounds__(256) agg_init_kernel(AggParams a) {
     }
     for (int64_t t = t0; t < G * AG_MODES; t += stride) a.modes[t] = 0ull;
     for (int64_t t = t0; t < G; t += stride) ((uint4 *)a.ncnt)[t] = make_uint4(0u, 0u, 0u, 0u);
+    if (a.direct_max > 0) {
+        // big candidates reserve a slot and a member range in the big arrays (any order: the sub-sorts only need the
+        // ranges to tile [0, members)); slot s + 1 starts where slot s ends, so both writers of goff_big[s + 1] agree
+        for (int64_t t = t0; t < G; t += stride) {
+            const int64_t k = a.goff[t + 1] - a.goff[t];
+            if (k > a.direct_max) {
+                const u64 old = atomicAdd(&a.small->big_ctr, (1ull << 32) | (u64)k);
+                const int32_t slot = (int32_t)(old >> 32);
+                const int64_t start = (int64_t)(old & 0xffffffffull);
+                a.big[t] = make_int2((int32_t)start, slot);
+                a.goff_big[slot] = start;
+                a.goff_big[slot + 1] = start + k;
+                a.bigg[slot] = (int32_t)t;
+            }
+        }
+    }
 }
 
 __device__ __forceinline__ int32_t seg_min(int32_t v, int32_t g, int lane) {
@@ -419,23 +457,119 @@ __global__ void __launch_bounds__(256) agg_gather_kernel(AggParams a) {
     }
 }
 
-// ---- runs of equal keys inside every candidate (after the sub-sort) -----------------------------------------------------
-// WHAT 0 / 1: mode of (kind, posA) / (kind, posB); 2: distinct (kind, name)
-template <int WHAT>
-__global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *__restrict__ keys,
-                                                       const int32_t *__restrict__ vals) {
+// ---- direct modes / distinct names of the candidates with <= direct_max members -------------------------------------------
+// One thread per member (compact order: a candidate's members are neighbours, in insertion order).  The member walks its
+// candidate's keys (neighbouring lanes read the same words: broadcasts out of L1) and counts the members with its own
+// (kind, posA) and (kind, posB) and whether an EARLIER member carries its (kind, name).  What the sort + run kernels
+// produce follows without a sort: the mode is the maximum over the members of (count : ~position) -- among the members
+// of the most frequent value the first-inserted one wins, exactly the run head the stable sort would present -- and
+// the distinct names are the members without an earlier equal.  Both are reduced over the warp's lanes of the same
+// candidate first (one hoisted set of segment predicates, 32-bit packed words), then one atomic per (candidate, warp,
+// kind).  Members of big candidates copy their keys into the big arrays for the sorts instead.
+__device__ __forceinline__ u64 direct_mode_word(u32 v, int64_t lo) {
+    const u64 count = (u64)(v >> AG_DIRECT_RB);
+    const u32 first = (u32)lo + ((u32)(AG_DIRECT_LIMIT - 1) - (v & (u32)(AG_DIRECT_LIMIT - 1)));
+    return (count << 32) | (u64)(0xffffffffu - first);
+}
+
+__global__ void __launch_bounds__(256) agg_direct_kernel(AggParams a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t M = a.small->d2.n;
     const int lane = threadIdx.x & 31;
+    if (c == 0) {   // agg_init_kernel has finished: the totals of the big candidates become the sub-sorts' dims
+        const u64 ctr = a.small->big_ctr;
+        a.small->d3.n = (int64_t)(ctr & 0xffffffffull);
+        a.small->d3.nseg = (int64_t)(ctr >> 32);
+    }
     if (c - lane >= M) return;   // whole warp beyond the end
     const bool live = c < M;
-    int32_t g = 0;
+    int32_t g = -1;
+    int64_t lo = 0;
+    u32 vA0 = 0, vA1 = 0, vA2 = 0, vB0 = 0, vB1 = 0, vB2 = 0, one = 0;
+    if (live) {
+        g = a.c_grp[c];
+        lo = a.goff[g];
+        const int64_t hi = a.goff[g + 1];
+        const u32 kA = a.keyA[c], kB = a.keyB[c], kN = a.keyN[c];
+        if (hi - lo > (int64_t)a.direct_max) {
+            const int2 b = a.big[g];
+            const int64_t j = (int64_t)b.x + (c - lo);
+            a.bkA[j] = kA;
+            a.bkB[j] = kB;
+            a.bkN[j] = kN;
+            a.bgrp[j] = b.y;
+            a.borig[j] = (int32_t)c;
+        } else {
+            const int jl = (int)lo, jh = (int)hi, jc = (int)c;
+            const u32 *__restrict__ pA = a.keyA, *__restrict__ pB = a.keyB, *__restrict__ pN = a.keyN;
+            u32 cntA = 0, cntB = 0, dup = 0;
+#pragma unroll 4
+            for (int j = jl; j < jh; j++) {
+                cntA += __ldg(pA + j) == kA ? 1u : 0u;
+                cntB += __ldg(pB + j) == kB ? 1u : 0u;
+                dup |= (__ldg(pN + j) == kN && j < jc) ? 1u : 0u;
+            }
+            const u32 kind = (kA >> a.pos_bits) & 3u;   // 3 is a data error flagged by agg_gather_kernel
+            const u32 rel = (u32)(AG_DIRECT_LIMIT - 1 - (jc - jl));
+            const u32 wa = (cntA << AG_DIRECT_RB) | rel, wb = (cntB << AG_DIRECT_RB) | rel;
+            vA0 = kind == 0u ? wa : 0u; vA1 = kind == 1u ? wa : 0u; vA2 = kind == 2u ? wa : 0u;
+            vB0 = kind == 0u ? wb : 0u; vB1 = kind == 1u ? wb : 0u; vB2 = kind == 2u ? wb : 0u;
+            one = dup ? 0u : (1u << (8u * kind));
+        }
+    }
+    // inclusive segmented scans over the lanes of the same candidate (max of the six mode words, sum of the name counters:
+    // four 8-bit fields, a warp adds at most 32 to each)
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int32_t h = __shfl_up_sync(0xffffffffu, g, o);
+        const bool same = lane >= o && h == g;
+        const u32 a0 = __shfl_up_sync(0xffffffffu, vA0, o), a1 = __shfl_up_sync(0xffffffffu, vA1, o);
+        const u32 a2 = __shfl_up_sync(0xffffffffu, vA2, o), b0 = __shfl_up_sync(0xffffffffu, vB0, o);
+        const u32 b1 = __shfl_up_sync(0xffffffffu, vB1, o), b2 = __shfl_up_sync(0xffffffffu, vB2, o);
+        const u32 w = __shfl_up_sync(0xffffffffu, one, o);
+        if (same) {
+            vA0 = max(vA0, a0); vA1 = max(vA1, a1); vA2 = max(vA2, a2);
+            vB0 = max(vB0, b0); vB1 = max(vB1, b1); vB2 = max(vB2, b2);
+            one += w;
+        }
+    }
+    const int32_t gnext = __shfl_down_sync(0xffffffffu, g, 1);
+    if (live && (lane == 31 || gnext != g)) {   // last lane of the candidate's run inside this warp
+        u64 *md = a.modes + (int64_t)g * AG_MODES;
+        if (vA0) atomicMax(md + 0, direct_mode_word(vA0, lo));
+        if (vA1) atomicMax(md + 1, direct_mode_word(vA1, lo));
+        if (vA2) atomicMax(md + 2, direct_mode_word(vA2, lo));
+        if (vB0) atomicMax(md + 3, direct_mode_word(vB0, lo));
+        if (vB1) atomicMax(md + 4, direct_mode_word(vB1, lo));
+        if (vB2) atomicMax(md + 5, direct_mode_word(vB2, lo));
+#pragma unroll
+        for (int t = 0; t < 4; t++) {
+            const u32 f = (one >> (8 * t)) & 0xffu;
+            if (f) atomicAdd(a.ncnt + (int64_t)g * 4 + t, f);
+        }
+    }
+}
+
+// ---- runs of equal keys inside every candidate (after the sub-sort) -----------------------------------------------------
+// WHAT 0 / 1: mode of (kind, posA) / (kind, posB); 2: distinct (kind, name).  BIG: the sorted arrays hold the members of
+// the big candidates only (direct mode): segment = big slot, positions translated back through bigg / borig.
+template <int WHAT, bool BIG>
+__global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *__restrict__ keys,
+                                                       const int32_t *__restrict__ vals) {
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int64_t M = BIG ? a.small->d3.n : a.small->d2.n;
+    const int lane = threadIdx.x & 31;
+    if (c - lane >= M) return;   // whole warp beyond the end
+    const bool live = c < M;
+    const int64_t *__restrict__ goff = BIG ? a.goff_big : a.goff;
+    int32_t g = 0, gr = 0;       // segment of the sorted arrays / the candidate it is
     int64_t lo = 0;
     u32 key = 0;
     bool head = false;
     if (live) {
-        g = a.c_grp[c];
-        lo = a.goff[g];
+        g = BIG ? a.bgrp[c] : a.c_grp[c];
+        gr = BIG ? a.bigg[g] : g;
+        lo = goff[g];
         key = keys[c];
         head = c == lo || keys[c - 1] != key;   // first element of a run of equal keys
     }
@@ -450,13 +584,13 @@ __global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *_
         if (live && (lane == 31 || nextk != ck)) {
             const int start = 31 - __clz(bnd & lanemask_le());
             const u32 cnt = __popc(heads & lanemask_le() & ~((1u << start) - 1u));
-            if (cnt) atomicAdd(a.ncnt + (int64_t)g * 4 + kind, cnt);
+            if (cnt) atomicAdd(a.ncnt + (int64_t)gr * 4 + kind, cnt);
         }
         return;
     }
     if (!head) return;
     // run end: gallop, then bisect (keys ascend inside the candidate)
-    const int64_t hi = a.goff[g + 1];
+    const int64_t hi = goff[g + 1];
     int64_t left = c, step = 1;            // keys[left] == key
     int64_t right = hi;                    // keys[right] > key (or right == hi)
     while (left + step < hi) {
@@ -473,9 +607,10 @@ __global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *_
         if (keys[mid] == key) left = mid; else right = mid;
     }
     const u64 count = (u64)(right - c);
-    const u32 first = (u32)vals[c];        // compact position of the first occurrence (the sort is stable)
+    // compact position of the first occurrence (the sort is stable)
+    const u32 first = BIG ? (u32)a.borig[vals[c]] : (u32)vals[c];
     const u32 kind = key >> a.pos_bits;
-    atomicMax(a.modes + (int64_t)g * AG_MODES + WHAT * 3 + kind, (count << 32) | (u64)(0xffffffffu - first));
+    atomicMax(a.modes + (int64_t)gr * AG_MODES + WHAT * 3 + kind, (count << 32) | (u64)(0xffffffffu - first));
 }
 
 // ---- one row per candidate (tiddit_cluster.pyx:258-336) ------------------------------------------------------------------
@@ -561,6 +696,7 @@ static AggPlan agg_plan(int64_t n, int32_t P) {
     t += al((size_t)n * AG_ACC * 4) + al((size_t)n * AG_MODES * 8) + al((size_t)n * 16);
     t += 3 * (pl.sort + 256);                          // one sort scratch per parallel sub-sort branch
     t += 2 * 4 * al((size_t)(n + 4) * 4);              // key1s / val1s / tmpK / tmpV of branches 1 and 2
+    t += al((size_t)(n + 4) * 8) + al((size_t)(n + 2) * 8) + 6 * al((size_t)(n + 4) * 4);   // big goff_big | bigg bkA bkB bkN bgrp borig
     pl.total = t;
     return pl;
 }
@@ -598,6 +734,14 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
     a.acc = ar.take<int32_t>((size_t)n * AG_ACC);
     a.modes = ar.take<u64>((size_t)n * AG_MODES);
     a.ncnt = ar.take<u32>((size_t)n * 4);
+    a.big = ar.take<int2>(n + 4);
+    a.goff_big = ar.take<int64_t>(n + 2);
+    a.bigg = ar.take<int32_t>(n + 4);
+    a.bkA = ar.take<u32>(n + 4);
+    a.bkB = ar.take<u32>(n + 4);
+    a.bkN = ar.take<u32>(n + 4);
+    a.bgrp = ar.take<int32_t>(n + 4);
+    a.borig = ar.take<int32_t>(n + 4);
     void *sort_temp = ar.take<char>(pl.sort);
     // the three sub-sorts (by posA, posB, name inside every candidate) are independent: branches 1 and 2 get their own
     // outputs, ping-pong buffers and sort scratch and run next to branch 0
@@ -634,13 +778,17 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
         ProfScope ps("agg_gather", st);
         TDT_LAUNCH(agg_gather_kernel, per_elem, 256, 0, st, a);
     }
-    const int64_t nseg_max = n;
     {
-        // three parallel branches: the main stream and two side streams forked here and joined before agg_finalize
+        // Small candidates: one direct kernel.  What is left for the sorts (all candidates with TDT_AGG_DIRECT=0) runs
+        // as three parallel branches: the main stream and two side streams forked here and joined before agg_finalize
         // (inside a CUDA-graph capture they become parallel graph branches).  Every sort is a chain of small,
         // latency-bound kernels that leaves most of the machine idle; measured one after the other they took
         // 0.43 + 0.43 + 0.36 ms of the 2.46 ms call on the 30X set.
         ProfScope ps("agg_modes_names", st);
+        const bool direct = a.direct_max > 0;
+        if (direct) TDT_LAUNCH(agg_direct_kernel, per_elem, 256, 0, st, a);
+        const int64_t nseg_max = direct ? n / ((int64_t)a.direct_max + 1) + 1 : n;
+        const int64_t *sub_dims = direct ? (const int64_t *)&a.small->d3 : (const int64_t *)&a.small->d2;
         static thread_local cudaStream_t br[16][2] = {};
         static thread_local cudaEvent_t ev_fork[16] = {}, ev_join[16][2] = {};
         int dev = 0;
@@ -657,17 +805,25 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
         for (int what = 0; what < 3; what++) {
             cudaStream_t bs = (par && what > 0) ? br[dev][what - 1] : st;
             if (bs != st) TDT_CUDA(cudaStreamWaitEvent(bs, ev_fork[dev], 0));
-            const u32 *kin = what == 0 ? a.keyA : (what == 1 ? a.keyB : a.keyN);
+            const u32 *kin = direct ? (what == 0 ? a.bkA : (what == 1 ? a.bkB : a.bkN))
+                                    : (what == 0 ? a.keyA : (what == 1 ? a.keyB : a.keyN));
             const int bits = (what == 2 ? a.name_bits : a.pos_bits) + 2;
             segsort_set_branch(what + 1);
-            int rc = segsort_pairs(kin, nullptr, b_keys[what], b_vals[what], b_tmpK[what], b_tmpV[what], a.goff,
-                                   (const int64_t *)&a.small->d2, a.c_grp, n, nseg_max, bits, b_temp[what], pl.sort,
-                                   &a.small->err, bs);
+            // (big candidates exceed the sort's counting path: no per-element segment ids needed)
+            int rc = segsort_pairs(kin, nullptr, b_keys[what], b_vals[what], b_tmpK[what], b_tmpV[what],
+                                   direct ? a.goff_big : a.goff, sub_dims, direct ? nullptr : a.c_grp, n, nseg_max, bits,
+                                   b_temp[what], pl.sort, &a.small->err, bs);
             segsort_set_branch(0);
             if (rc) return rc;
-            if (what == 0) TDT_LAUNCH(agg_runs_kernel<0>, per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
-            else if (what == 1) TDT_LAUNCH(agg_runs_kernel<1>, per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
-            else TDT_LAUNCH(agg_runs_kernel<2>, per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+            if (direct) {
+                if (what == 0) TDT_LAUNCH((agg_runs_kernel<0, true>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else if (what == 1) TDT_LAUNCH((agg_runs_kernel<1, true>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else TDT_LAUNCH((agg_runs_kernel<2, true>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+            } else {
+                if (what == 0) TDT_LAUNCH((agg_runs_kernel<0, false>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else if (what == 1) TDT_LAUNCH((agg_runs_kernel<1, false>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else TDT_LAUNCH((agg_runs_kernel<2, false>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+            }
             if (bs != st) {
                 TDT_CUDA(cudaEventRecord(ev_join[dev][what - 1], bs));
                 TDT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][what - 1], 0));
@@ -724,6 +880,13 @@ int tdt_cluster_aggregate(const int32_t *labels, const int32_t *posA, const int3
     if (a.name_bits < 1) a.name_bits = 1;
     a.sentinel = (1u << bit_width_u32((uint32_t)(2 * n))) - 1u;
     a.cand_out = cand_out; a.member_idx = member_idx_out; a.counts_out = counts_out;
+    // TDT_AGG_DIRECT (read at every call): 0 = every candidate through the sub-sorts; k = direct kernel up to k members
+    a.direct_max = TDT_AGG_DIRECT_DEFAULT;
+    if (const char *e = getenv("TDT_AGG_DIRECT")) {
+        if (e[0] >= '0' && e[0] <= '9') a.direct_max = atoi(e);
+    }
+    if (a.direct_max < 0) a.direct_max = 0;
+    if (a.direct_max > AG_DIRECT_LIMIT) a.direct_max = AG_DIRECT_LIMIT;
     return aggregate_impl(a, ws, ws_bytes, (cudaStream_t)stream);
 }
 
