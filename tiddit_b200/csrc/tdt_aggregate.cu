@@ -22,7 +22,8 @@
 //   agg_direct           candidates of <= direct_max members (nearly all; default 256): every member counts its equals
 //                        among the candidate's members directly -- mode with first-inserted tie-break as a warp-
 //                        segmented max of (count : ~position), distinct names as the members without an earlier
-//                        equal; members of LARGER candidates are compacted into the "big" arrays instead
+//                        equal.  The members of LARGER candidates were compacted into the "big" arrays by agg_gather;
+//                        their sorts run on high-priority side streams NEXT TO this kernel
 //   segsort #2..#4       inside every big candidate by (kind,posA), (kind,posB), (kind,name)
 //   agg_runs             runs of equal keys: mode with first-inserted tie-break (64-bit atomicMax of
 //                        count:~first), distinct-name counts
@@ -409,6 +410,11 @@ __global__ void __launch_bounds__(256) agg_gather_kernel(AggParams a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t M = a.small->d2.n;
     const int lane = threadIdx.x & 31;
+    if (c == 0) {   // agg_init_kernel has finished: the totals of the big candidates become the sub-sorts' dims
+        const u64 ctr = a.small->big_ctr;
+        a.small->d3.n = (int64_t)(ctr & 0xffffffffull);
+        a.small->d3.nseg = (int64_t)(ctr >> 32);
+    }
     if (c - lane >= M) return;   // whole warp beyond the end
     const bool live = c < M;
     int32_t g = -1;
@@ -426,9 +432,22 @@ __global__ void __launch_bounds__(256) agg_gather_kernel(AggParams a) {
         if (x < 0 || y < 0 || (a.pos_bits < 31 && ((x >> a.pos_bits) || (y >> a.pos_bits))))
             atomicMax(&a.small->err, (int)AG_ERR_POS);
         if (nm < 0 || (nm >> a.name_bits)) atomicMax(&a.small->err, (int)AG_ERR_NAME);
-        a.keyA[c] = (kind << a.pos_bits) | (u32)x;
-        a.keyB[c] = (kind << a.pos_bits) | (u32)y;
-        a.keyN[c] = (kind << a.name_bits) | (u32)nm;
+        const u32 kA = (kind << a.pos_bits) | (u32)x, kB = (kind << a.pos_bits) | (u32)y, kN = (kind << a.name_bits) | (u32)nm;
+        a.keyA[c] = kA;
+        a.keyB[c] = kB;
+        a.keyN[c] = kN;
+        if (a.direct_max > 0) {   // members of a big candidate: a second copy, compacted for the sub-sorts
+            const int64_t lo = a.goff[g];
+            if (a.goff[g + 1] - lo > (int64_t)a.direct_max) {
+                const int2 b = a.big[g];
+                const int64_t j = (int64_t)b.x + (c - lo);
+                a.bkA[j] = kA;
+                a.bkB[j] = kB;
+                a.bkN[j] = kN;
+                a.bgrp[j] = b.y;
+                a.borig[j] = (int32_t)c;
+            }
+        }
         sA = sp.x; eA = sp.y; sB = sp.z; eB = sp.w;
         if (kind == 0u) {
             dAmin = dAmax = x;
@@ -465,7 +484,7 @@ __global__ void __launch_bounds__(256) agg_gather_kernel(AggParams a) {
 // of the most frequent value the first-inserted one wins, exactly the run head the stable sort would present -- and
 // the distinct names are the members without an earlier equal.  Both are reduced over the warp's lanes of the same
 // candidate first (one hoisted set of segment predicates, 32-bit packed words), then one atomic per (candidate, warp,
-// kind).  Members of big candidates copy their keys into the big arrays for the sorts instead.
+// kind).  The members of big candidates are left to the sorts.
 __device__ __forceinline__ u64 direct_mode_word(u32 v, int64_t lo) {
     const u64 count = (u64)(v >> AG_DIRECT_RB);
     const u32 first = (u32)lo + ((u32)(AG_DIRECT_LIMIT - 1) - (v & (u32)(AG_DIRECT_LIMIT - 1)));
@@ -476,11 +495,6 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(AggParams a) {
     const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int64_t M = a.small->d2.n;
     const int lane = threadIdx.x & 31;
-    if (c == 0) {   // agg_init_kernel has finished: the totals of the big candidates become the sub-sorts' dims
-        const u64 ctr = a.small->big_ctr;
-        a.small->d3.n = (int64_t)(ctr & 0xffffffffull);
-        a.small->d3.nseg = (int64_t)(ctr >> 32);
-    }
     if (c - lane >= M) return;   // whole warp beyond the end
     const bool live = c < M;
     int32_t g = -1;
@@ -490,16 +504,8 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(AggParams a) {
         g = a.c_grp[c];
         lo = a.goff[g];
         const int64_t hi = a.goff[g + 1];
-        const u32 kA = a.keyA[c], kB = a.keyB[c], kN = a.keyN[c];
-        if (hi - lo > (int64_t)a.direct_max) {
-            const int2 b = a.big[g];
-            const int64_t j = (int64_t)b.x + (c - lo);
-            a.bkA[j] = kA;
-            a.bkB[j] = kB;
-            a.bkN[j] = kN;
-            a.bgrp[j] = b.y;
-            a.borig[j] = (int32_t)c;
-        } else {
+        if (hi - lo <= (int64_t)a.direct_max) {   // (a big candidate's members were compacted for the sorts by agg_gather_kernel)
+            const u32 kA = a.keyA[c], kB = a.keyB[c], kN = a.keyN[c];
             const int jl = (int)lo, jh = (int)hi, jc = (int)c;
             const u32 *__restrict__ pA = a.keyA, *__restrict__ pB = a.keyB, *__restrict__ pN = a.keyN;
             u32 cntA = 0, cntB = 0, dup = 0;
@@ -553,13 +559,10 @@ __global__ void __launch_bounds__(256) agg_direct_kernel(AggParams a) {
 // ---- runs of equal keys inside every candidate (after the sub-sort) -----------------------------------------------------
 // WHAT 0 / 1: mode of (kind, posA) / (kind, posB); 2: distinct (kind, name).  BIG: the sorted arrays hold the members of
 // the big candidates only (direct mode): segment = big slot, positions translated back through bigg / borig.
+// One element of the sorted arrays per thread; called by whole warps (c - lane < M).
 template <int WHAT, bool BIG>
-__global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *__restrict__ keys,
-                                                       const int32_t *__restrict__ vals) {
-    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int64_t M = BIG ? a.small->d3.n : a.small->d2.n;
-    const int lane = threadIdx.x & 31;
-    if (c - lane >= M) return;   // whole warp beyond the end
+__device__ __forceinline__ void agg_runs_element(const AggParams &a, const u32 *__restrict__ keys,
+                                                 const int32_t *__restrict__ vals, int64_t c, int64_t M, int lane) {
     const bool live = c < M;
     const int64_t *__restrict__ goff = BIG ? a.goff_big : a.goff;
     int32_t g = 0, gr = 0;       // segment of the sorted arrays / the candidate it is
@@ -611,6 +614,18 @@ __global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *_
     const u32 first = BIG ? (u32)a.borig[vals[c]] : (u32)vals[c];
     const u32 kind = key >> a.pos_bits;
     atomicMax(a.modes + (int64_t)gr * AG_MODES + WHAT * 3 + kind, (count << 32) | (u64)(0xffffffffu - first));
+}
+
+// Grid-stride over the sorted elements: the BIG launches cover "every member is a big one" with a capped grid (a grid
+// of n / 256 CTAs that only find out that nothing is big would be dispatched ahead of the direct kernel's CTAs).
+template <int WHAT, bool BIG>
+__global__ void __launch_bounds__(256) agg_runs_kernel(AggParams a, const u32 *__restrict__ keys,
+                                                       const int32_t *__restrict__ vals) {
+    const int64_t M = BIG ? a.small->d3.n : a.small->d2.n;
+    const int lane = threadIdx.x & 31;
+    const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; c - lane < M; c += stride)
+        agg_runs_element<WHAT, BIG>(a, keys, vals, c, M, lane);
 }
 
 // ---- one row per candidate (tiddit_cluster.pyx:258-336) ------------------------------------------------------------------
@@ -786,24 +801,35 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
         // 0.43 + 0.43 + 0.36 ms of the 2.46 ms call on the 30X set.
         ProfScope ps("agg_modes_names", st);
         const bool direct = a.direct_max > 0;
-        if (direct) TDT_LAUNCH(agg_direct_kernel, per_elem, 256, 0, st, a);
+        // TDT_AGG_OVERLAP=0: direct kernel first, then the sorts of the big candidates (measurement aid)
+        const char *ov = getenv("TDT_AGG_OVERLAP");
+        const bool overlap = direct && !(ov && ov[0] == '0');
+        if (direct && !overlap) TDT_LAUNCH(agg_direct_kernel, per_elem, 256, 0, st, a);
         const int64_t nseg_max = direct ? n / ((int64_t)a.direct_max + 1) + 1 : n;
         const int64_t *sub_dims = direct ? (const int64_t *)&a.small->d3 : (const int64_t *)&a.small->d2;
-        static thread_local cudaStream_t br[16][2] = {};
-        static thread_local cudaEvent_t ev_fork[16] = {}, ev_join[16][2] = {};
+        // the run kernels of the big candidates: capped grid, grid-stride (usually there is next to nothing to do)
+        const unsigned runs_grid = direct && per_elem > 148u * 8u ? 148u * 8u : per_elem;
+        static thread_local cudaStream_t br[16][3] = {};
+        static thread_local cudaEvent_t ev_fork[16] = {}, ev_join[16][3] = {};
         int dev = 0;
         TDT_CUDA(cudaGetDevice(&dev));
         const bool par = dev >= 0 && dev < 16;
         if (par && !br[dev][0]) {
-            for (int i = 0; i < 2; i++) {
-                TDT_CUDA(cudaStreamCreateWithFlags(&br[dev][i], cudaStreamNonBlocking));
+            // high priority: the chains are short kernels that depend on each other; next to the direct kernel's tens
+            // of thousands of CTAs they must not queue behind them
+            int pr_least = 0, pr_greatest = 0;
+            TDT_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+            for (int i = 0; i < 3; i++) {
+                TDT_CUDA(cudaStreamCreateWithPriority(&br[dev][i], cudaStreamNonBlocking, pr_greatest));
                 TDT_CUDA(cudaEventCreateWithFlags(&ev_join[dev][i], cudaEventDisableTiming));
             }
             TDT_CUDA(cudaEventCreateWithFlags(&ev_fork[dev], cudaEventDisableTiming));
         }
         if (par) TDT_CUDA(cudaEventRecord(ev_fork[dev], st));
         for (int what = 0; what < 3; what++) {
-            cudaStream_t bs = (par && what > 0) ? br[dev][what - 1] : st;
+            // overlap: all three chains on side streams, the caller's stream keeps the direct kernel; otherwise the
+            // first chain stays on the caller's stream
+            cudaStream_t bs = !par ? st : (overlap ? br[dev][what] : (what > 0 ? br[dev][what - 1] : st));
             if (bs != st) TDT_CUDA(cudaStreamWaitEvent(bs, ev_fork[dev], 0));
             const u32 *kin = direct ? (what == 0 ? a.bkA : (what == 1 ? a.bkB : a.bkN))
                                     : (what == 0 ? a.keyA : (what == 1 ? a.keyB : a.keyN));
@@ -816,18 +842,25 @@ static int aggregate_impl(AggParams a, void *ws, size_t ws_bytes, cudaStream_t s
             segsort_set_branch(0);
             if (rc) return rc;
             if (direct) {
-                if (what == 0) TDT_LAUNCH((agg_runs_kernel<0, true>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
-                else if (what == 1) TDT_LAUNCH((agg_runs_kernel<1, true>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
-                else TDT_LAUNCH((agg_runs_kernel<2, true>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                if (what == 0) TDT_LAUNCH((agg_runs_kernel<0, true>), runs_grid, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else if (what == 1) TDT_LAUNCH((agg_runs_kernel<1, true>), runs_grid, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else TDT_LAUNCH((agg_runs_kernel<2, true>), runs_grid, 256, 0, bs, a, b_keys[what], b_vals[what]);
             } else {
-                if (what == 0) TDT_LAUNCH((agg_runs_kernel<0, false>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
-                else if (what == 1) TDT_LAUNCH((agg_runs_kernel<1, false>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
-                else TDT_LAUNCH((agg_runs_kernel<2, false>), per_elem, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                if (what == 0) TDT_LAUNCH((agg_runs_kernel<0, false>), runs_grid, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else if (what == 1) TDT_LAUNCH((agg_runs_kernel<1, false>), runs_grid, 256, 0, bs, a, b_keys[what], b_vals[what]);
+                else TDT_LAUNCH((agg_runs_kernel<2, false>), runs_grid, 256, 0, bs, a, b_keys[what], b_vals[what]);
             }
             if (bs != st) {
-                TDT_CUDA(cudaEventRecord(ev_join[dev][what - 1], bs));
-                TDT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][what - 1], 0));
+                const int bi = overlap ? what : what - 1;
+                TDT_CUDA(cudaEventRecord(ev_join[dev][bi], bs));
+                if (!overlap) TDT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][bi], 0));
             }
+        }
+        if (overlap) {
+            // launched behind the chains: their first kernels are already queued when its CTAs start to fill the SMs
+            TDT_LAUNCH(agg_direct_kernel, per_elem, 256, 0, st, a);
+            if (par)
+                for (int i = 0; i < 3; i++) TDT_CUDA(cudaStreamWaitEvent(st, ev_join[dev][i], 0));
         }
     }
     {

@@ -1061,7 +1061,12 @@ int segsort1_pairs(const uint32_t *keys_in, const int32_t *vals_in, uint32_t *ke
     if (dev_id >= 0 && dev_id < 16) {
         dev_id = dev_id * SS_BRANCHES + g_ss_branch;   // one side stream per (device, branch)
         if (!side_streams[dev_id]) {
-            TDT_CUDA(cudaStreamCreateWithFlags(&side_streams[dev_id], cudaStreamNonBlocking));
+            // branches >= 1 (the aggregation's sub-sorts) run next to a kernel that fills the machine (agg_direct_kernel):
+            // their side streams get the caller's high priority, or the small-segment kernels would queue behind it
+            int pr_least = 0, pr_greatest = 0;
+            TDT_CUDA(cudaDeviceGetStreamPriorityRange(&pr_least, &pr_greatest));
+            TDT_CUDA(cudaStreamCreateWithPriority(&side_streams[dev_id], cudaStreamNonBlocking,
+                                                  g_ss_branch > 0 ? pr_greatest : 0));
             TDT_CUDA(cudaEventCreateWithFlags(&fork_ev[dev_id], cudaEventDisableTiming));
             TDT_CUDA(cudaEventCreateWithFlags(&join_ev[dev_id], cudaEventDisableTiming));
         }

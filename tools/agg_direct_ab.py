@@ -10,7 +10,7 @@ from tiddit_b200 import device_ops, synth, _lib
 n30 = int(sys.argv[1]) if len(sys.argv) > 1 else 20_000_000
 ntu = int(sys.argv[2]) if len(sys.argv) > 2 else 20_000_000
 reps = int(sys.argv[3]) if len(sys.argv) > 3 else 5
-SETTINGS = ["0", "32", "64", "128", "256", "1024"]
+SETTINGS = os.environ.get("TDT_AB_SETTINGS", "0 32 64 128 256 1024").split()   # "k" or "k:overlap" (TDT_AGG_OVERLAP)
 d = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 out = {}
@@ -32,7 +32,10 @@ for name, gen, n, eps, m in (("wgs30x", synth.wgs30x_signals, n30, 500, 3), ("tu
     base = None
     res = {}
     for s in SETTINGS:
-        os.environ["TDT_AGG_DIRECT"] = s
+        os.environ["TDT_AGG_DIRECT"] = s.split(":")[0]
+        os.environ.pop("TDT_AGG_OVERLAP", None)
+        if ":" in s:
+            os.environ["TDT_AGG_OVERLAP"] = s.split(":")[1]
         for _ in range(2):
             run()
         torch.cuda.synchronize()
@@ -58,7 +61,7 @@ for name, gen, n, eps, m in (("wgs30x", synth.wgs30x_signals, n30, 500, 3), ("tu
                 tot[k] = tot.get(k, 0) + ms / reps
         res[s] = {"ms": round(float(np.mean(whole)), 4), "min_ms": round(float(np.min(whole)), 4), "rows_equal_to_sorts": same_rows,
                   "err": err, "stages": {k: round(v, 4) for k, v in tot.items()}}
-        print(name, "TDT_AGG_DIRECT=%s" % s, "candidates", C, "members", Mm, res[s], flush=True)
+        print(name, "TDT_AGG_DIRECT[:OVERLAP]=%s" % s, "candidates", C, "members", Mm, res[s], flush=True)
     out[name] = {"n": n, "candidates": C, "members": Mm, "candidates_larger_than": big, "settings": res}
 os.makedirs("gpurun_out", exist_ok=True)
 json.dump(out, open("gpurun_out/agg_direct_ab.json", "w"), indent=1)

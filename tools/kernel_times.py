@@ -24,7 +24,10 @@ counts = torch.zeros(4, dtype=torch.int64, device="cuda")
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 calls = {"cluster": lambda: device_ops.cluster_labels_device(A, B, O, P, EPS, M, L, labels_out=labels),
          "aggregate": lambda: device_ops.cluster_aggregate_device(labels, A, B, span, name, flags, O, same, P, 5000, False, M, L, n, rows, mem, counts)}
+only = os.environ.get("TDT_KT_ONLY")   # "cluster" / "aggregate": just that call
 for what, fn in calls.items():
+    if only and what != only:
+        continue
     fn(); fn()
     acc, reps = None, 5
     for _ in range(reps):
