@@ -35,7 +35,12 @@
 namespace tdt {
 
 constexpr int AG_THREADS = 256;
-constexpr int AG_ITEMS = 8;
+#ifndef TDT_AG_ITEMS
+#define TDT_AG_ITEMS 8
+#endif
+constexpr int AG_ITEMS = TDT_AG_ITEMS;   // signals per thread of the three chained scans (a multiple of 4 that divides 32).
+                                         // B200, 30X set, whole call: 8 -> 1.655 ms, 16 -> 1.640 (within noise), 32 -> 1.764
+static_assert(AG_ITEMS % 4 == 0 && 32 % AG_ITEMS == 0, "AG_ITEMS: a multiple of 4 that divides 32");
 constexpr int AG_TILE = AG_THREADS * AG_ITEMS;
 constexpr int AG_ACC = 12;    // int32 accumulators per candidate
 constexpr int AG_MODES = 6;   // u64 (count:~first) per side x kind
@@ -282,7 +287,7 @@ __global__ void __launch_bounds__(AG_THREADS) agg_mark_scan_kernel(AggParams a) 
     u32 headm = 0, firstsurv = 0;
     if (j0 < M) {
         u32 prev = j0 > 0 ? a.key1s[j0 - 1] : 0u;
-        u32 hw = a.pair_heads[j0 >> 5] >> (j0 & 31);   // j0 is a multiple of 8: the 8 bits sit in one word
+        u32 hw = a.pair_heads[j0 >> 5] >> (j0 & 31);   // j0 is a multiple of AG_ITEMS, which divides 32: the bits sit in one word
 #pragma unroll
         for (int k = 0; k < AG_ITEMS; k++) {
             const int64_t j = j0 + k;
@@ -333,9 +338,11 @@ __global__ void __launch_bounds__(AG_THREADS) agg_rank_scan_kernel(AggParams a) 
     int32_t g[AG_ITEMS];
     u32 cnt = 0;
     if (i0 + AG_ITEMS <= a.n) {
-        const int4 v0 = *(const int4 *)(a.gfirst + i0), v1 = *(const int4 *)(a.gfirst + i0 + 4);
-        g[0] = v0.x; g[1] = v0.y; g[2] = v0.z; g[3] = v0.w;
-        g[4] = v1.x; g[5] = v1.y; g[6] = v1.z; g[7] = v1.w;
+#pragma unroll
+        for (int k = 0; k < AG_ITEMS; k += 4) {
+            const int4 v = *(const int4 *)(a.gfirst + i0 + k);
+            g[k] = v.x; g[k + 1] = v.y; g[k + 2] = v.z; g[k + 3] = v.w;
+        }
     } else {
 #pragma unroll
         for (int k = 0; k < AG_ITEMS; k++) g[k] = i0 + k < a.n ? a.gfirst[i0 + k] : 0;
