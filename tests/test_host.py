@@ -221,6 +221,63 @@ def test_tab_scanner_irregular_and_errors(tmp_path):
         PackedSignals.from_tab(str(tmp_path / "nothing"), ["c1"], {"c1": 1000}, ["S"], False, 0, True)
 
 
+def test_tab_scanner_parallel_interning(tmp_path):
+    """libtdt_tab.so interns on all threads (per-chunk tables for contigs / orientations merged in file order, a
+    hash-sharded table for the read names): ids must come out in order of FIRST APPEARANCE whatever the thread count --
+    names repeated inside a file, across chunks and across the files of one set; contigs that first appear deep inside
+    a later chunk -- and equal the line reader's (tiddit_cluster.pyx:47-137 restated in signals._part_from_lines)."""
+    from tiddit_b200 import tabio
+    from tiddit_b200.signals import PackedSignals
+    rng = np.random.default_rng(5)
+    contigs = ["chr%d" % i for i in range(1, 30)]
+    clen = {c: 10_000_000 for c in contigs}
+    nd, ns = 120_000, 60_000
+    names_d = rng.integers(0, 40_000, nd)                       # every name about three times
+    names_s = rng.integers(20_000, 70_000, ns)                  # half of them known from the discordants file
+    ca = np.sort(rng.integers(0, 6, nd))                        # few contigs first, the others first appear late
+    ca[-5000:] = rng.integers(6, len(contigs), 5000)
+    cb = rng.integers(0, len(contigs), nd)
+    pos = rng.integers(1, 9_000_000, (nd, 4))
+    ori = np.array(["False", "True", "odd"])
+    os.makedirs(str(tmp_path / "p_tiddit"))
+    with open(str(tmp_path / "p_tiddit" / "discordants_S.tab"), "w") as f:
+        oa, ob = rng.integers(0, 2, nd), rng.integers(0, 3, nd)
+        f.write("".join("read%d\t%s\t%s\t%d\t%d\t%s\t%d\t%d\t%s\n" % (names_d[i], contigs[ca[i]], contigs[cb[i]], pos[i, 0],
+                                                                     pos[i, 0] + 100, ori[oa[i]], pos[i, 1], pos[i, 1] + 100,
+                                                                     ori[ob[i]]) for i in range(nd)))
+    with open(str(tmp_path / "p_tiddit" / "splits_S.tab"), "w") as f:
+        sa, sb = rng.integers(0, len(contigs), ns), rng.integers(0, len(contigs), ns)
+        sp = rng.integers(1, 9_000_000, (ns, 2))
+        f.write("".join("read%d\t%s\t%s\t%d\tTrue\t%d\tFalse\t%d\t%d\t%d\t%d\n" % (names_s[i], contigs[sa[i]], contigs[sb[i]],
+                                                                                  sp[i, 0], sp[i, 1], sp[i, 0] - 5, sp[i, 0],
+                                                                                  sp[i, 1], sp[i, 1] + 5) for i in range(ns)))
+
+    def scan(threads):
+        ts = tabio.TabSet()
+        try:
+            for stem in ("discordants", "splits"):
+                ts.parse(str(tmp_path / "p_tiddit" / ("%s_S.tab" % stem)), stem, threads)
+            return ([ts.col_i32(j) for j in range(5)], [ts.col_i64(j) for j in range(6)], [ts.table(t) for t in range(3)])
+        finally:
+            ts.close()
+
+    one = scan(1)
+    # first appearance: the id column, read in order, introduces 0, 1, 2, ... one at a time
+    for j, t in ((0, 0), (1, 1), (3, 2)):
+        col = one[0][j] if j == 0 else np.stack([one[0][j], one[0][j + 1]], 1).ravel()
+        firsts = col[np.sort(np.unique(col, return_index=True)[1])]
+        assert np.array_equal(firsts, np.arange(len(one[2][t])))
+    assert one[2][0][0] == "read%d" % names_d[0] and len(one[2][0]) == len(set(names_d.tolist()) | set(names_s.tolist()))
+    for threads in (2, 3, 5, 0):
+        got = scan(threads)
+        assert all(np.array_equal(a, b) for a, b in zip(one[0] + one[1], got[0] + got[1])) and one[2] == got[2], threads
+    args = (str(tmp_path / "p"), contigs, clen, ["S"], False, 0, True)
+    a, b = PackedSignals._from_tab_native(*args), PackedSignals.from_tab(*args, fast=False)
+    assert a is not None and list(a.names) == list(b.names) and a.ori_table == b.ori_table and a.pairs == b.pairs
+    for k in PackedSignals.FIELDS:
+        assert np.array_equal(getattr(a, k), getattr(b, k)), k
+
+
 def test_tab_header_symbols_exported():
     import re
     from tiddit_b200 import build, tabio

@@ -1,5 +1,8 @@
 // tdt_tab.cpp -- libtdt_tab.so: the signal tab files of tiddit_signal / tiddit_contig_analysis as columns
 // (include/tdt_tab.h).  Host code only: mmap, a line-aligned split over std::threads, field parsing, string interning.
+// Every phase runs on all threads: the few-valued columns (contigs, orientations) are interned per chunk and the small
+// chunk tables merged in file order; the read names -- one table of millions of strings -- go through a hash-sharded
+// table (NameTable below) in which every thread resolves the names of its own shards.
 #include "../../include/tdt_tab.h"
 
 #include <fcntl.h>
@@ -98,9 +101,101 @@ struct Interner {
 };
 
 struct Chunk {        // what one thread parsed: columns in file order
-    std::vector<Str> name, chrA, chrB, oriA, oriB;
+    std::vector<Str> name;
+    std::vector<int32_t> cA, cB, oA, oB;   // ids in the chunk's OWN small tables (merged into the set's afterwards)
+    Interner contigs, oris;
     std::vector<int64_t> num[6];
     bool irregular = false;
+};
+
+// The read-name table, sharded by the top hash bits so that several threads can intern one file's names at once and
+// still hand out ids in order of first appearance:
+//   A (parallel)   thread t scans all names of the file in order and resolves those of ITS shards: a name already in
+//                  the table keeps its id; otherwise the first occurrence in this file is entered as PENDING (slot value
+//                  = its position g in the file) and later occurrences point at it;
+//   B (sequential) pending first occurrences get consecutive ids in file order, their bytes are appended to the blob;
+//   C (parallel)   later occurrences copy the id of their first occurrence; D: pending slots become id slots.
+struct NameShard {
+    std::vector<uint64_t> slots;   // (hash << 32) | (id + 1), or (hash << 32) | 0x80000000 | g while pending; 0 = empty
+    size_t mask = 0, count = 0;
+
+    void rehash(size_t cap) {
+        std::vector<uint64_t> fresh(cap, 0);
+        mask = cap - 1;
+        for (uint64_t v : slots) {
+            if (!v) continue;
+            size_t s = (size_t)(v >> 32) & mask;
+            while (fresh[s]) s = (s + 1) & mask;
+            fresh[s] = v;
+        }
+        slots.swap(fresh);
+    }
+};
+
+struct NameTable {
+    static constexpr int SHARD_SHIFT = 26, SHARDS = 64;   // shard = top 6 hash bits, slot = low bits
+    NameShard shard[SHARDS];
+    std::vector<int64_t> offsets{0};
+    std::string blob;
+    size_t count = 0;
+
+    // phase A for the shards of thread t (of T): res[g] >= 0: id of a name already in the table; -2 - g0: same string
+    // as position g0 <= g of this file (g0 == g: first occurrence).  -> bytes of the first occurrences found
+    size_t resolve(const std::vector<Str> &flat, std::vector<int32_t> &res, int t, int T) {
+        const size_t N = flat.size();
+        size_t bytes = 0;
+        for (int sh = t; sh < SHARDS; sh += T) {   // room for an even share of the file plus slack; grows on demand
+            NameShard &S = shard[sh];
+            size_t want = (S.count + N / SHARDS + N / SHARDS / 4 + 16) * 2, cap = S.slots.empty() ? 64 : S.slots.size();
+            while (cap < want) cap *= 2;
+            if (cap != S.slots.size()) S.rehash(cap);
+        }
+        for (size_t g = 0; g < N; g++) {
+            const Str &f = flat[g];
+            const int sh = (int)(f.hash >> SHARD_SHIFT);
+            if (sh % T != t) continue;
+            NameShard &S = shard[sh];
+            if ((S.count + 1) * 2 > S.slots.size()) S.rehash(S.slots.size() * 2);
+            size_t s = f.hash & S.mask;
+            while (true) {
+                const uint64_t v = S.slots[s];
+                if (!v) {
+                    S.slots[s] = ((uint64_t)f.hash << 32) | 0x80000000ull | (uint64_t)g;
+                    S.count++;
+                    res[g] = -2 - (int32_t)g;
+                    bytes += f.len;
+                    break;
+                }
+                if ((uint32_t)(v >> 32) == f.hash) {
+                    const uint32_t low = (uint32_t)v;
+                    if (low & 0x80000000u) {
+                        const Str &h = flat[low & 0x7fffffffu];
+                        if (h.len == f.len && memcmp(h.p, f.p, f.len) == 0) {
+                            res[g] = -2 - (int32_t)(low & 0x7fffffffu);
+                            break;
+                        }
+                    } else {
+                        const int32_t id = (int32_t)low - 1;
+                        const int64_t o = offsets[id], l = offsets[id + 1] - o;
+                        if ((uint32_t)l == f.len && memcmp(blob.data() + o, f.p, f.len) == 0) {
+                            res[g] = id;
+                            break;
+                        }
+                    }
+                }
+                s = (s + 1) & S.mask;
+            }
+        }
+        return bytes;
+    }
+
+    // phase D for the shards of thread t: pending slots -> id slots
+    void settle(const std::vector<int32_t> &res, int t, int T) {
+        for (int sh = t; sh < SHARDS; sh += T)
+            for (uint64_t &v : shard[sh].slots)
+                if ((uint32_t)v & 0x80000000u)
+                    v = (v & 0xffffffff00000000ull) | (uint64_t)(uint32_t)(res[(uint32_t)v & 0x7fffffffu] + 1);
+    }
 };
 
 inline bool is_space(char c) { return c == ' ' || c == '\t' || c == '\r' || c == '\n' || c == '\v' || c == '\f'; }
@@ -144,10 +239,10 @@ void parse_range(const char *lo, const char *hi, int kind, Chunk &c) {
             q = nl + 1;
         }
         c.name.reserve(lines);
-        c.chrA.reserve(lines);
-        c.chrB.reserve(lines);
-        c.oriA.reserve(lines);
-        c.oriB.reserve(lines);
+        c.cA.reserve(lines);
+        c.cB.reserve(lines);
+        c.oA.reserve(lines);
+        c.oB.reserve(lines);
         for (int i = 0; i < 6; i++) c.num[i].reserve(lines);
     }
     while (p < hi) {
@@ -188,10 +283,11 @@ void parse_range(const char *lo, const char *hi, int kind, Chunk &c) {
             return;
         }
         c.name.push_back(name);
-        c.chrA.push_back(ca);
-        c.chrB.push_back(cb);
-        c.oriA.push_back(oa);
-        c.oriB.push_back(ob);
+        // in the order the reader meets them per record: chrA, chrB / oriA, oriB (the first of each mostly repeats)
+        c.cA.push_back(c.contigs.intern_cached(ca));
+        c.cB.push_back(c.contigs.intern(cb));
+        c.oA.push_back(c.oris.intern_cached(oa));
+        c.oB.push_back(c.oris.intern(ob));
         for (int i = 0; i < 6; i++) c.num[i].push_back(v[i]);
         p = eol < hi ? eol + 1 : hi;
     }
@@ -200,7 +296,8 @@ void parse_range(const char *lo, const char *hi, int kind, Chunk &c) {
 }  // namespace
 
 struct tdt_tab_set {
-    Interner names, contigs, oris;
+    NameTable names;
+    Interner contigs, oris;
     std::vector<int32_t> i32[5];
     std::vector<int64_t> i64[6];
 };
@@ -259,27 +356,78 @@ int64_t tdt_tab_parse(tdt_tab_set *set, const char *path, int kind, int threads)
     for (auto &c : chunks) irregular = irregular || c.irregular;
     if (!irregular) {
         size_t total = 0;
-        for (auto &c : chunks) total += c.name.size();
-        set->names.reserve(total);
+        std::vector<size_t> first(T + 1, 0);          // chunk t holds records [first[t], first[t + 1]) of the file
+        for (int t = 0; t < T; t++) first[t + 1] = first[t] + chunks[t].name.size();
+        total = first[T];
+        if (total >= (size_t)1 << 31 || set->names.count + total >= (size_t)1 << 31) {
+            munmap((void *)data, size);
+            return fail(TDT_TAB_E_ARG, "%s: more than 2^31 records / names", path);
+        }
         const size_t base = set->i32[0].size();
         for (int j = 0; j < 5; j++) set->i32[j].resize(base + total);
-        for (int j = 0; j < 6; j++) set->i64[j].reserve(base + total);
-        // the few-valued columns are interned first (sequential, cached), in the order the reader meets them per
-        // record: chrA, chrB / oriA, oriB; then the names, the only large table
-        size_t at = base;
-        for (auto &c : chunks) {
-            const size_t k = c.name.size();
-            for (size_t i = 0; i < k; i++, at++) {
-                set->i32[1][at] = set->contigs.intern_cached(c.chrA[i]);
-                set->i32[2][at] = set->contigs.intern(c.chrB[i]);
-                set->i32[3][at] = set->oris.intern_cached(c.oriA[i]);
-                set->i32[4][at] = set->oris.intern(c.oriB[i]);
-                set->i32[0][at] = set->names.intern(c.name[i]);
+        for (int j = 0; j < 6; j++) set->i64[j].resize(base + total);
+        // the chunks' small tables merged in file order: a string keeps the id of its first appearance in the set
+        std::vector<std::vector<int32_t>> cmap(T), omap(T);
+        for (int t = 0; t < T; t++) {
+            for (int which = 0; which < 2; which++) {
+                const Interner &loc = which == 0 ? chunks[t].contigs : chunks[t].oris;
+                Interner &glob = which == 0 ? set->contigs : set->oris;
+                std::vector<int32_t> &map = which == 0 ? cmap[t] : omap[t];
+                map.resize(loc.count);
+                for (size_t k = 0; k < loc.count; k++) {
+                    Str f;
+                    f.p = loc.blob.data() + loc.offsets[k];
+                    f.len = (uint32_t)(loc.offsets[k + 1] - loc.offsets[k]);
+                    f.hash = hash_bytes(f.p, f.len);
+                    map[k] = glob.intern(f);
+                }
             }
-            for (int j = 0; j < 6; j++) set->i64[j].insert(set->i64[j].end(), c.num[j].begin(), c.num[j].end());
-            added += (int64_t)k;
         }
-        set->contigs.last_id = set->oris.last_id = -1;   // the cached pointers die with the mapping
+        // names: flat view of the file, then the phases of NameTable
+        std::vector<Str> flat(total);
+        std::vector<int32_t> res(total);
+        std::vector<size_t> new_bytes(T, 0);
+        auto run = [&](auto fn) {
+            std::vector<std::thread> pool;
+            for (int t = 1; t < T; t++) pool.emplace_back(fn, t);
+            fn(0);
+            for (auto &th : pool) th.join();
+        };
+        run([&](int t) {   // columns of chunk t into place
+            const Chunk &c = chunks[t];
+            const size_t k = c.name.size(), at = base + first[t];
+            if (k) memcpy(&flat[first[t]], c.name.data(), k * sizeof(Str));
+            for (size_t i = 0; i < k; i++) {
+                set->i32[1][at + i] = cmap[t][c.cA[i]];
+                set->i32[2][at + i] = cmap[t][c.cB[i]];
+                set->i32[3][at + i] = omap[t][c.oA[i]];
+                set->i32[4][at + i] = omap[t][c.oB[i]];
+            }
+            for (int j = 0; j < 6; j++)
+                if (k) memcpy(&set->i64[j][at], c.num[j].data(), k * sizeof(int64_t));
+        });
+        run([&](int t) { new_bytes[t] = set->names.resolve(flat, res, t, T); });
+        {   // first occurrences in file order: ids, bytes
+            NameTable &nt = set->names;
+            size_t add = 0;
+            for (size_t b : new_bytes) add += b;
+            nt.blob.reserve(nt.blob.size() + add);
+            for (size_t g = 0; g < total; g++) {
+                if (res[g] == -2 - (int32_t)g) {
+                    res[g] = (int32_t)nt.count++;
+                    nt.blob.append(flat[g].p, flat[g].len);
+                    nt.offsets.push_back((int64_t)nt.blob.size());
+                }
+            }
+        }
+        run([&](int t) {   // later occurrences, the name column of chunk t, the pending slots of thread t's shards
+            for (size_t g = first[t]; g < first[t + 1]; g++) {
+                if (res[g] < 0) res[g] = res[(size_t)(-2 - res[g])];
+                set->i32[0][base + g] = res[g];
+            }
+        });
+        run([&](int t) { set->names.settle(res, t, T); });
+        added = (int64_t)total;
     }
     munmap((void *)data, size);
     if (timing) fprintf(stderr, "tdt_tab_parse %s: %d threads, parse %.3f s, intern %.3f s\n", path, T, t_parsed - t_begin, now() - t_parsed);
@@ -299,7 +447,12 @@ const int64_t *tdt_tab_col_i64(const tdt_tab_set *set, int which) {
 
 int64_t tdt_tab_table(const tdt_tab_set *set, int table, const char **blob, const int64_t **offsets) {
     if (!set || table < 0 || table > 2) return fail(TDT_TAB_E_ARG, "bad argument");
-    const Interner &t = table == 0 ? set->names : (table == 1 ? set->contigs : set->oris);
+    if (table == 0) {
+        if (blob) *blob = set->names.blob.data();
+        if (offsets) *offsets = set->names.offsets.data();
+        return (int64_t)set->names.count;
+    }
+    const Interner &t = table == 1 ? set->contigs : set->oris;
     if (blob) *blob = t.blob.data();
     if (offsets) *offsets = t.offsets.data();
     return (int64_t)t.count;

@@ -264,12 +264,13 @@ class PackedSignals:
                     posA[sl], posB[sl] = np.minimum(num[0][sl], la[sl]), np.minimum(num[1][sl], lb[sl])
                     span[sl] = np.stack([num[j][sl] for j in range(2, 6)], 1)
             keep = (la >= min_contig) & (lb >= min_contig)
-            for arr in (posA[keep], posB[keep], span[keep]):
+            all_kept = bool(keep.all())
+            sel = (lambda arr: arr) if all_kept else (lambda arr: arr[keep])   # (no copies when nothing is dropped)
+            for arr in (sel(posA), sel(posB), sel(span)):
                 if arr.size and (arr.min() < -2 ** 31 or arr.max() >= 2 ** 31 - 1):
                     raise OverflowError("signal coordinates must fit int32")
             name_id = ts.col_i32(0)
             names = ts.table(0, lazy=True)
-            all_kept = bool(keep.all())
             if not all_kept:
                 # ids in order of first appearance among the KEPT records, like the line reader interns them
                 name_id, names = _reintern(name_id[keep], names)
@@ -281,27 +282,47 @@ class PackedSignals:
                 is_false = np.array([o == "False" for o in ori_tab] or [False])
             else:
                 oA_k, oB_k = oA, oB
-            flags = kind_col[keep].copy()
+            flags = sel(kind_col).copy()
             flags |= np.where(is_true[oA_k], SIG_A_TRUE, np.where(is_false[oA_k], SIG_A_FALSE, 0)).astype(np.uint8)
             flags |= np.where(is_true[oB_k], SIG_B_TRUE, np.where(is_false[oB_k], SIG_B_FALSE, 0)).astype(np.uint8)
             # pairs in the reference's visiting order (:140-150)
             chrom_rank = {c: i for i, c in reversed(list(enumerate(chromosomes)))}       # first listing wins
             rank_of = np.array([chrom_rank.get(c, -1) for c in contig_tab] or [-1], dtype=np.int64)
             C = max(len(chromosomes), 1)
-            ra, rb = rank_of[cA[keep]], rank_of[cB[keep]]
-            visited = (ra >= 0) & (rb >= 0)
-            key = np.where(visited, ra * C + rb, -1)
-            present = np.unique(key[visited])
+            cA_k, cB_k = sel(cA), sel(cB)
+            T = max(len(contig_tab), 1)
+            if T * T <= 1 << 22:
+                # the contig pairs that occur, found on the (contig id, contig id) grid instead of on the records
+                grid = (np.bincount(cA_k.astype(np.int64) * T + cB_k, minlength=T * T) if len(cA_k)
+                        else np.zeros(T * T, np.int64)).reshape(T, T)
+                ia, ib = np.nonzero(grid)
+                listed = (rank_of[ia] >= 0) & (rank_of[ib] >= 0)
+                ia, ib = ia[listed], ib[listed]
+                keys = rank_of[ia] * C + rank_of[ib]
+                by_key = np.argsort(keys)                                  # visiting order: chrA rank, then chrB rank
+                present = keys[by_key]
+                rank_grid = np.full((T, T), len(present), dtype=np.int64)  # never-visited pairs sort behind the others
+                rank_grid[ia[by_key], ib[by_key]] = np.arange(len(present))
+                pair_rank = rank_grid[cA_k, cB_k]
+                counts = grid[ia[by_key], ib[by_key]]
+                seen_a = np.flatnonzero(grid.sum(axis=1)).tolist()
+            else:                                                          # very many contigs: on the records
+                ra, rb = rank_of[cA_k], rank_of[cB_k]
+                visited = (ra >= 0) & (rb >= 0)
+                key = np.where(visited, ra * C + rb, -1)
+                present = np.unique(key[visited])
+                pair_rank = np.where(visited, np.searchsorted(present, key), len(present))
+                counts = np.bincount(pair_rank, minlength=len(present) + 1)[:len(present)]
+                seen_a = np.unique(cA_k).tolist()
             pairs = [(chromosomes[int(kk) // C], chromosomes[int(kk) % C]) for kk in present]
-            pair_rank = np.where(visited, np.searchsorted(present, key), -1)
-            order = np.argsort(pair_rank, kind="stable")
-            order = order[pair_rank[order] >= 0]
-            counts = np.bincount(pair_rank[order], minlength=len(pairs)) if len(pairs) else np.zeros(0, dtype=np.int64)
             seg_off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int64)
-            seen_a = set(np.unique(cA[keep]).tolist())
+            # stable sort of small integers: numpy's radix sort takes 16-bit keys
+            order = np.argsort(pair_rank.astype(np.uint16) if len(pairs) < 65535 else pair_rank, kind="stable")
+            order = order[:int(seg_off[-1])]
             chrA_all = {contig_tab[i] for i in seen_a}
-            return cls(pairs, seg_off, posA[keep][order], posB[keep][order], span[keep][order], name_id[order], flags[order],
-                       sample_col[keep][order], oA_k[order], oB_k[order], names, samples, list(ori_tab),
+            pick = (lambda arr: arr[order]) if all_kept else (lambda arr: arr[keep][order])
+            return cls(pairs, seg_off, pick(posA), pick(posB), pick(span), name_id[order], flags[order],
+                       pick(sample_col), oA_k[order], oB_k[order], names, samples, list(ori_tab),
                        chrA_present=[a for a in dict.fromkeys(chromosomes) if a in chrA_all])
         finally:
             ts.close()
