@@ -653,7 +653,7 @@ def cluster_main_leg(torch, args):
     dt = time.perf_counter() - t0
     n_cand = sum(len(got[a][b]) for a in got for b in got[a])
     out = {"lines": n, "candidates": n_cand, "s_per_call": dt, "lines_per_sec": n / dt,
-           "path": "tiddit_cluster.main(prefix, ...): pandas C parser -> packed arrays -> 2 GPU calls -> candidates dict (Python)"}
+           "path": "tiddit_cluster.main(prefix, ...): native tab scanner (libtdt_tab.so, all host cores) -> packed arrays -> 2 GPU calls -> candidates dict (Python)"}
     # where the time goes
     from tiddit_b200.signals import PackedSignals
     t0 = time.perf_counter()
