@@ -64,6 +64,12 @@ TDT_BAM_API int64_t tdt_bam_read_columns(tdt_bam_reader *r, int64_t max_reads, i
                                          uint8_t *has_sa, int64_t *rec_off);
 TDT_BAM_API const uint8_t *tdt_bam_batch_data(const tdt_bam_reader *r, int64_t *len);
 
+/* The block decoder on its own (tests, diagnosis): in[0, in_len) = one complete raw DEFLATE stream (the payload of a BGZF
+ * block, what pysam / htslib hand to zlib's inflate), out[0, out_len) = exactly its inflated bytes.  -> 1 decoded,
+ * 0 refused (not a clean stream of exactly out_len bytes: the reader then lets zlib decide), < 0 bad argument.
+ * The reader checks every block's CRC32 whichever decoder produced it. */
+TDT_BAM_API int tdt_bam_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,7 +29,7 @@ def _stale():
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f not in ("tdt_bam.cpp", "tdt_tab.cpp")] + [os.path.join(HERE, "..", "include", "tdt_b200.h")]
+    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f not in ("tdt_bam.cpp", "tdt_tab.cpp", "tdt_inflate.h")] + [os.path.join(HERE, "..", "include", "tdt_b200.h")]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -37,7 +37,8 @@ def build_bam(force=False):
     """g++ -O3 -shared: the BGZF/BAM column scanner (host code only, links zlib)."""
     src = os.path.join(CSRC, "tdt_bam.cpp")
     hdr = os.path.join(HERE, "..", "include", "tdt_bam.h")
-    if not force and os.path.exists(BAM_LIB) and os.path.getmtime(BAM_LIB) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    inflate = os.path.join(CSRC, "tdt_inflate.h")          # the block decoder the scanner includes
+    if not force and os.path.exists(BAM_LIB) and os.path.getmtime(BAM_LIB) > max(map(os.path.getmtime, (src, hdr, inflate))):
         return BAM_LIB
     subprocess.check_call([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden",
                            "-Wall", "-o", BAM_LIB, src, "-lz", "-lpthread"])
