@@ -477,8 +477,9 @@ def bam_leg(torch, args):
     dt = float(np.median(times))
     out = {"reads": n, "file_bytes": os.path.getsize(path), "bin_size": z, "min_q": q, "s_per_pass": dt,
            "reads_per_sec": n / dt, "file_MB_per_sec": os.path.getsize(path) / dt / 1e6, "host_threads": os.cpu_count(),
-           "path": "coverage_from_bam: BGZF inflate (zlib, all host cores) -> columns -> H2D -> coverage kernel per 1M-read batch -> bins D2H",
-           "bound": "host: zlib inflate of the BGZF blocks"}
+           "path": "coverage_from_bam: BGZF inflate (csrc/tdt_inflate.h block decoder + zlib CRC32, all host cores, 16 MiB "
+                   "windows) -> columns -> H2D -> coverage kernel per window batch -> bins D2H",
+           "bound": "host: inflate of the BGZF blocks + the sequential record walk"}
     from oracle import oracle
     keep = ((flag & 0x400) == 0) & (mapq >= q)
     ok = True
