@@ -2,7 +2,8 @@
 // Host code only (g++ + zlib).  The file is mapped, BGZF block boundaries are found by hopping over the BSIZE
 // fields, a window of blocks is inflated on a pool of threads straight into one contiguous buffer (every block
 // states its inflated size in its trailer, so the destinations are known up front), and records are decoded
-// from that buffer without copying.  Blocks go through the whole-buffer decoder of tdt_inflate.h (r02 v6); zlib
+// from that buffer without copying (record boundaries by a sequential walk over the block_size words, the fields of
+// the records on a second small pool).  Blocks go through the whole-buffer decoder of tdt_inflate.h (r02 v6); zlib
 // computes the CRC of every block and inflates the ones that decoder refuses or gets wrong (TDT_BAM_ZLIB=1: all).
 #include "../../include/tdt_bam.h"
 #include "tdt_inflate.h"
@@ -15,6 +16,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -36,6 +42,7 @@ int fail(int code, const char *fmt, ...) {
     return code;
 }
 
+inline double now_s() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 inline uint32_t le32(const uint8_t *p) { uint32_t v; memcpy(&v, p, 4); return v; }
 inline uint16_t le16(const uint8_t *p) { uint16_t v; memcpy(&v, p, 2); return v; }
 
@@ -48,6 +55,68 @@ struct Block {
     uint32_t isize;          // inflated size
     uint32_t crc;
     size_t dst;              // offset in the window buffer
+};
+
+// A fixed set of threads that run one job at a time: run(f) calls f(worker) on every worker (the caller is worker 0) and
+// returns when all are done.  The reader owns two: the background thread inflates the next window on one while the
+// caller's thread decodes the records of the current window on the other.
+class Pool {
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable start_, done_;
+    std::function<void(int)> job_;
+    int generation_ = 0, pending_ = 0;
+    bool stop_ = false;
+
+    void worker(int idx) {
+        int seen = 0;
+        for (;;) {
+            std::unique_lock<std::mutex> lk(m_);
+            start_.wait(lk, [&] { return stop_ || generation_ != seen; });
+            if (stop_) return;
+            seen = generation_;
+            std::function<void(int)> f = job_;
+            lk.unlock();
+            f(idx);
+            lk.lock();
+            if (--pending_ == 0) done_.notify_one();
+        }
+    }
+
+public:
+    explicit Pool(int n) {
+        for (int i = 1; i < n; ++i) th_.emplace_back([this, i] { worker(i); });
+    }
+    ~Pool() {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        start_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    int size() const { return (int)th_.size() + 1; }
+    void run(const std::function<void(int)> &f) {   // f must not throw
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            job_ = f;
+            pending_ = (int)th_.size();
+            ++generation_;
+        }
+        start_.notify_all();
+        f(0);
+        std::unique_lock<std::mutex> lk(m_);
+        done_.wait(lk, [&] { return pending_ == 0; });
+    }
+};
+
+struct InflateWorker {       // per inflate-pool worker, kept between windows
+    z_stream zs;
+    bool zs_ready = false;
+    tdtz::Inflater fast;
+    ~InflateWorker() {
+        if (zs_ready) inflateEnd(&zs);
+    }
 };
 
 }  // namespace
@@ -71,6 +140,10 @@ struct tdt_bam_reader {
     int bg_rc = 0;                // 1 = bytes ready, 0 = end of file, < 0 error
     size_t bg_bytes = 0;
     char bg_err[512] = "";
+    std::unique_ptr<Pool> inflate_pool, parse_pool;
+    std::vector<std::unique_ptr<InflateWorker>> inflate_workers;
+    std::vector<int64_t> rec_at;  // offsets of the records of the batch being decoded
+    double t_wait = 0, t_walk = 0, t_decode = 0;   // TDT_BAM_TIMING=1: seconds waiting for the inflater / walking / decoding
     std::string text;
     std::vector<std::string> ref_names;
     std::vector<int32_t> ref_lens;
@@ -129,41 +202,34 @@ int inflate_window(tdt_bam_reader *r, std::vector<uint8_t> &dst, size_t *nbytes,
     uint8_t *base = dst.data();
     const char *zenv = getenv("TDT_BAM_ZLIB");
     const bool zlib_only = zenv && zenv[0] == '1';
-    auto work = [&]() {
-        z_stream zs;
-        memset(&zs, 0, sizeof zs);
-        if (inflateInit2(&zs, -15) != Z_OK) { bad = 1; return; }
-        tdtz::Inflater *fast = zlib_only ? nullptr : new (std::nothrow) tdtz::Inflater;
+    auto work = [&](int w) {
+        InflateWorker &ws = *r->inflate_workers[(size_t)w];
         for (;;) {
             size_t i = next.fetch_add(1);
             if (i >= blocks.size()) break;
             const Block &b = blocks[i];
             uint8_t *out = base + b.dst;
             // the trailer's CRC decides whether the fast decoder's bytes stand; zlib inflates whatever it does not
-            if (fast && tdtz::inflate_raw(*fast, b.payload, b.clen, out, b.isize) &&
+            if (!zlib_only && tdtz::inflate_raw(ws.fast, b.payload, b.clen, out, b.isize) &&
                 (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, b.isize) == b.crc)
                 continue;
-            zs.next_in = const_cast<Bytef *>(b.payload);
-            zs.avail_in = b.clen;
-            zs.next_out = out;
-            zs.avail_out = b.isize;
-            int rc = inflate(&zs, Z_FINISH);
-            if (rc != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, b.isize) != b.crc)
+            if (!ws.zs_ready) {
+                memset(&ws.zs, 0, sizeof ws.zs);
+                if (inflateInit2(&ws.zs, -15) != Z_OK) { bad = 1; continue; }
+                ws.zs_ready = true;
+            }
+            ws.zs.next_in = const_cast<Bytef *>(b.payload);
+            ws.zs.avail_in = b.clen;
+            ws.zs.next_out = out;
+            ws.zs.avail_out = b.isize;
+            int rc = inflate(&ws.zs, Z_FINISH);
+            if (rc != Z_STREAM_END || ws.zs.avail_out != 0 || (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, b.isize) != b.crc)
                 bad = 1;
-            inflateReset(&zs);
+            inflateReset(&ws.zs);
         }
-        delete fast;
-        inflateEnd(&zs);
     };
-    int nt = (int)std::min<size_t>((size_t)r->threads, blocks.size());
-    if (nt <= 1) {
-        work();
-    } else {
-        std::vector<std::thread> pool;
-        for (int t = 1; t < nt; ++t) pool.emplace_back(work);
-        work();
-        for (auto &t : pool) t.join();
-    }
+    if (blocks.size() < 4) work(0);
+    else r->inflate_pool->run(work);
     if (bad) {
         snprintf(err, err_len, "%s: a BGZF block failed to inflate (corrupt data or CRC mismatch)", r->path.c_str());
         return TDT_BAM_E_FORMAT;
@@ -318,7 +384,16 @@ static int open_impl(const char *path, int threads, tdt_bam_reader **out) {
     r->path = path;
     if (threads <= 0) threads = (int)std::thread::hardware_concurrency();
     r->threads = std::max(1, threads);
-    int rc = read_header(r);
+    int rc;
+    try {
+        r->inflate_pool.reset(new Pool(r->threads));
+        r->parse_pool.reset(new Pool(std::min(r->threads, 8)));   // decoding record fields is latency-bound: a few threads cover it
+        for (int i = 0; i < r->threads; ++i) r->inflate_workers.emplace_back(new InflateWorker);
+        rc = read_header(r);
+    } catch (...) {   // thread creation, bad_alloc: the reader must not leak
+        tdt_bam_close(r);
+        throw;
+    }
     if (rc < 0) {
         tdt_bam_close(r);
         return rc;
@@ -330,6 +405,9 @@ static int open_impl(const char *path, int threads, tdt_bam_reader **out) {
 void tdt_bam_close(tdt_bam_reader *r) {
     if (!r) return;
     if (r->bg_running) r->bg.join();
+    if (getenv("TDT_BAM_TIMING"))
+        fprintf(stderr, "tdt_bam %s: waited %.3f s for inflated windows, boundary walk %.3f s, field decode %.3f s\n",
+                r->path.c_str(), r->t_wait, r->t_walk, r->t_decode);
     if (r->map) munmap(const_cast<uint8_t *>(r->map), r->map_len);
     if (r->fd >= 0) close(r->fd);
     delete r;
@@ -373,7 +451,9 @@ static int64_t read_columns_impl(tdt_bam_reader *r, int64_t max_reads, int32_t *
         size_t have = r->bend - r->bpos;
         bool complete = have >= 4 && have >= 4 + (size_t)le32(r->buf.data() + r->bpos);
         if (!complete) {
+            const double t0 = now_s();
             int rc = refill(r);
+            r->t_wait += now_s() - t0;
             if (rc < 0) return rc;
             if (rc == 0) {
                 if (r->bend - r->bpos != 0)
@@ -381,50 +461,86 @@ static int64_t read_columns_impl(tdt_bam_reader *r, int64_t max_reads, int32_t *
                 return 0;
             }
         }
+        // 1. the record boundaries of this batch: a walk over the block_size words (sequential by nature)
+        const double t_a = now_s();
         const uint8_t *base = r->buf.data();
-        while (n < max_reads) {
-            size_t avail = r->bend - r->bpos;
+        r->rec_at.clear();
+        size_t at = r->bpos;
+        while ((int64_t)r->rec_at.size() < max_reads) {
+            size_t avail = r->bend - at;
             if (avail < 4) break;
-            const uint8_t *rec = base + r->bpos;
-            uint32_t bs = le32(rec);
+            uint32_t bs = le32(base + at);
             if (bs < 32) return fail(TDT_BAM_E_FORMAT, "%s: record of %u bytes", r->path.c_str(), bs);
             if (avail < 4 + (size_t)bs) break;
-            const uint8_t *c = rec + 4;
-            int32_t rid = (int32_t)le32(c), p0 = (int32_t)le32(c + 4);
-            uint32_t l_name = c[8];
-            uint32_t n_cig = le16(c + 12);
-            uint16_t fl = le16(c + 14);
-            uint32_t l_seq = le32(c + 16);
-            size_t fixed = 32 + (size_t)l_name + 4 * (size_t)n_cig;
-            size_t aux_at = fixed + ((size_t)l_seq + 1) / 2 + l_seq;
-            if (aux_at > bs) return fail(TDT_BAM_E_FORMAT, "%s: record fields exceed its size", r->path.c_str());
-            const uint8_t *cg = c + 32 + l_name;
-            if (ref_id) ref_id[n] = rid;
-            if (pos) pos[n] = p0;
-            if (end) {
-                if ((fl & 4) || n_cig == 0) {
-                    end[n] = -1;
-                } else {
-                    int64_t e = p0;
-                    for (uint32_t k = 0; k < n_cig; ++k) {
-                        uint32_t w = le32(cg + 4 * k);
-                        if (kConsumesRef[w & 15]) e += w >> 4;
+            r->rec_at.push_back((int64_t)at);
+            at += 4 + (size_t)bs;
+            // the walk is a chain of dependent loads into memory other cores have just written (~70 ns each): short reads
+            // have records of nearly one size, so the lines around "eight records ahead" are requested now
+            const uint8_t *ahead = base + at + 8 * (4 + (size_t)bs);
+            if (ahead + 128 < base + r->bend) {
+                __builtin_prefetch(ahead - 64);
+                __builtin_prefetch(ahead);
+                __builtin_prefetch(ahead + 64);
+            }
+        }
+        n = (int64_t)r->rec_at.size();
+        const double t_b = now_s();
+        r->t_walk += t_b - t_a;
+        // 2. the fields of every record into the columns, on the parse pool when the batch is worth it
+        std::atomic<int64_t> next(0);
+        std::atomic<int> bad(0);
+        const int64_t *rec_at = r->rec_at.data();
+        auto decode = [&](int) {
+            for (;;) {
+                const int64_t lo = next.fetch_add(4096), hi = std::min<int64_t>(lo + 4096, n);
+                if (lo >= n) break;
+                for (int64_t k = lo; k < hi; ++k) {
+                    const uint8_t *rec = base + rec_at[k];
+                    const uint32_t bs = le32(rec);
+                    const uint8_t *c = rec + 4;
+                    int32_t rid = (int32_t)le32(c), p0 = (int32_t)le32(c + 4);
+                    uint32_t l_name = c[8];
+                    uint32_t n_cig = le16(c + 12);
+                    uint16_t fl = le16(c + 14);
+                    uint32_t l_seq = le32(c + 16);
+                    size_t fixed = 32 + (size_t)l_name + 4 * (size_t)n_cig;
+                    size_t aux_at = fixed + ((size_t)l_seq + 1) / 2 + l_seq;
+                    if (aux_at > bs) {
+                        bad = 1;
+                        return;
                     }
-                    end[n] = (int32_t)e;
+                    const uint8_t *cg = c + 32 + l_name;
+                    if (ref_id) ref_id[k] = rid;
+                    if (pos) pos[k] = p0;
+                    if (end) {
+                        if ((fl & 4) || n_cig == 0) {
+                            end[k] = -1;
+                        } else {
+                            int64_t e = p0;
+                            for (uint32_t q = 0; q < n_cig; ++q) {
+                                uint32_t w = le32(cg + 4 * q);
+                                if (kConsumesRef[w & 15]) e += w >> 4;
+                            }
+                            end[k] = (int32_t)e;
+                        }
+                    }
+                    if (mate_ref) mate_ref[k] = (int32_t)le32(c + 20);
+                    if (mate_pos) mate_pos[k] = (int32_t)le32(c + 24);
+                    if (tlen) tlen[k] = (int32_t)le32(c + 28);
+                    if (flag) flag[k] = fl;
+                    if (mapq) mapq[k] = c[9];
+                    if (cig_first) cig_first[k] = n_cig ? le32(cg) : 0;
+                    if (cig_last) cig_last[k] = n_cig ? le32(cg + 4 * (n_cig - 1)) : 0;
+                    if (has_sa) has_sa[k] = aux_has_sa(c + aux_at, c + bs) ? 1 : 0;
+                    if (rec_off) rec_off[k] = rec_at[k];
                 }
             }
-            if (mate_ref) mate_ref[n] = (int32_t)le32(c + 20);
-            if (mate_pos) mate_pos[n] = (int32_t)le32(c + 24);
-            if (tlen) tlen[n] = (int32_t)le32(c + 28);
-            if (flag) flag[n] = fl;
-            if (mapq) mapq[n] = c[9];
-            if (cig_first) cig_first[n] = n_cig ? le32(cg) : 0;
-            if (cig_last) cig_last[n] = n_cig ? le32(cg + 4 * (n_cig - 1)) : 0;
-            if (has_sa) has_sa[n] = aux_has_sa(c + aux_at, c + bs) ? 1 : 0;
-            if (rec_off) rec_off[n] = (int64_t)r->bpos;
-            r->bpos += 4 + (size_t)bs;
-            ++n;
-        }
+        };
+        if (n >= 16384 && r->parse_pool && r->parse_pool->size() > 1) r->parse_pool->run(decode);
+        else decode(0);
+        r->t_decode += now_s() - t_b;
+        if (bad) return fail(TDT_BAM_E_FORMAT, "%s: record fields exceed its size", r->path.c_str());
+        r->bpos = at;
     }
     return n;
 }
