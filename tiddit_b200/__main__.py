@@ -16,7 +16,8 @@ def coverage_from_bam(path, bin_size, min_q, threads=0, batch_reads=1 << 20):
     kernel contig by contig.  -> ({contig: float64 bins}, header)"""
     import numpy as np
     from . import bamio, tiddit_coverage
-    with bamio.ColumnReader(path, threads=threads, batch_reads=batch_reads) as reader:
+    with bamio.ColumnReader(path, threads=threads, batch_reads=batch_reads,
+                            columns=("ref_id", "pos", "end", "flag", "mapq")) as reader:
         bam_header = reader.header
         cov = tiddit_coverage.DeviceCoverage(bam_header, bin_size)
         for b in reader.batches():

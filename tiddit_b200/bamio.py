@@ -286,7 +286,7 @@ class ColumnBatch:
     def __init__(self, n, cols, data, references):
         self.n = n
         for (name, _), col in zip(self.COLUMNS, cols):
-            setattr(self, name, col[:n])
+            setattr(self, name, None if col is None else col[:n])    # None: a column the reader was told to skip
         self._data, self._refs = data, references
 
     def __len__(self):
@@ -302,7 +302,9 @@ class ColumnBatch:
 class ColumnReader:
     """`pysam.AlignmentFile(path).fetch(until_eof=True)` as batches of columns (libtdt_bam.so)."""
 
-    def __init__(self, path, threads=0, batch_reads=1 << 20):
+    def __init__(self, path, threads=0, batch_reads=1 << 20, columns=None):
+        """columns: names of the ColumnBatch.COLUMNS to fill (default: all).  The scanner skips the work of the others --
+        `has_sa` walks the aux fields at the far end of every record -- and the batch carries None for them."""
         L = bam_lib()
         h = _vp()
         rc = L.tdt_bam_open(os.fsencode(path), int(threads), ctypes.byref(h))
@@ -317,11 +319,15 @@ class ColumnReader:
         self.lengths = [L.tdt_bam_ref_len(h, i) for i in range(len(self.references))]
         self.header = _parse_header_text(self.text, self.references, self.lengths)
         self.batch_reads = int(batch_reads)
-        self._cols = [np.empty(self.batch_reads, dtype=dt) for _, dt in ColumnBatch.COLUMNS]
+        known = [name for name, _ in ColumnBatch.COLUMNS]
+        if columns is not None and any(c not in known for c in columns):
+            raise ValueError("unknown column in %r (known: %s)" % (columns, ", ".join(known)))
+        self._cols = [np.empty(self.batch_reads, dtype=dt) if columns is None or name in columns else None
+                      for name, dt in ColumnBatch.COLUMNS]
 
     def batches(self):
         L, h = self._L, self._h
-        ptrs = [c.ctypes.data_as(_vp) for c in self._cols]
+        ptrs = [None if c is None else c.ctypes.data_as(_vp) for c in self._cols]
         while True:
             n = L.tdt_bam_read_columns(h, self.batch_reads, *ptrs)
             if n < 0:
