@@ -244,7 +244,7 @@ class PackedSignals:
             is_false = np.array([o == "False" for o in ori_tab] or [False])
             num = [ts.col_i64(j) for j in range(6)]
             posA, posB = np.zeros(n, np.int64), np.zeros(n, np.int64)
-            span = np.zeros((n, 4), np.int64)
+            span = [np.zeros(n, np.int64) for _ in range(4)]          # rec[8..11] as four columns until the very end
             kind_col, sample_col = np.zeros(n, np.uint8), np.zeros(n, np.int32)
             for kind, k, lo, hi in ranges:
                 sl = slice(lo, hi)
@@ -259,16 +259,21 @@ class PackedSignals:
                         pa, pb = np.where(ft | ff, eA, sA), np.where(ft | tt, sB, eB)
                     posA[sl] = np.where(pa > la[sl], np.where(pb > lb[sl], lb[sl], la[sl]), pa)   # :67-70 nested test
                     posB[sl] = pb
-                    span[sl] = np.stack([sA, eA, sB, eB], 1)
+                    for j, col in enumerate((sA, eA, sB, eB)):
+                        span[j][sl] = col
                 else:
                     posA[sl], posB[sl] = np.minimum(num[0][sl], la[sl]), np.minimum(num[1][sl], lb[sl])
-                    span[sl] = np.stack([num[j][sl] for j in range(2, 6)], 1)
+                    for j in range(4):
+                        span[j][sl] = num[j + 2][sl]
             keep = (la >= min_contig) & (lb >= min_contig)
             all_kept = bool(keep.all())
             sel = (lambda arr: arr) if all_kept else (lambda arr: arr[keep])   # (no copies when nothing is dropped)
-            for arr in (sel(posA), sel(posB), sel(span)):
+            for arr in [sel(posA), sel(posB)] + [sel(c) for c in span]:
                 if arr.size and (arr.min() < -2 ** 31 or arr.max() >= 2 ** 31 - 1):
                     raise OverflowError("signal coordinates must fit int32")
+            # (checked on the kept records: dropped ones may hold anything) -- from here on 32 bits per coordinate
+            with np.errstate(over="ignore"):
+                posA, posB, span = posA.astype(np.int32), posB.astype(np.int32), [c.astype(np.int32) for c in span]
             name_id = ts.col_i32(0)
             names = ts.table(0, lazy=True)
             if not all_kept:
@@ -283,8 +288,8 @@ class PackedSignals:
             else:
                 oA_k, oB_k = oA, oB
             flags = sel(kind_col).copy()
-            flags |= np.where(is_true[oA_k], SIG_A_TRUE, np.where(is_false[oA_k], SIG_A_FALSE, 0)).astype(np.uint8)
-            flags |= np.where(is_true[oB_k], SIG_B_TRUE, np.where(is_false[oB_k], SIG_B_FALSE, 0)).astype(np.uint8)
+            flags |= np.where(is_true, SIG_A_TRUE, np.where(is_false, SIG_A_FALSE, 0)).astype(np.uint8)[oA_k]   # per table entry,
+            flags |= np.where(is_true, SIG_B_TRUE, np.where(is_false, SIG_B_FALSE, 0)).astype(np.uint8)[oB_k]   # then one gather
             # pairs in the reference's visiting order (:140-150)
             chrom_rank = {c: i for i, c in reversed(list(enumerate(chromosomes)))}       # first listing wins
             rank_of = np.array([chrom_rank.get(c, -1) for c in contig_tab] or [-1], dtype=np.int64)
@@ -321,7 +326,10 @@ class PackedSignals:
             order = order[:int(seg_off[-1])]
             chrA_all = {contig_tab[i] for i in seen_a}
             pick = (lambda arr: arr[order]) if all_kept else (lambda arr: arr[keep][order])
-            return cls(pairs, seg_off, pick(posA), pick(posB), pick(span), name_id[order], flags[order],
+            span_out = np.empty((len(order), 4), dtype=np.int32)
+            for j in range(4):
+                span_out[:, j] = pick(span[j])
+            return cls(pairs, seg_off, pick(posA), pick(posB), span_out, name_id[order], flags[order],
                        pick(sample_col), oA_k[order], oB_k[order], names, samples, list(ori_tab),
                        chrA_present=[a for a in dict.fromkeys(chromosomes) if a in chrA_all])
         finally:
