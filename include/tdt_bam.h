@@ -69,6 +69,9 @@ TDT_BAM_API const uint8_t *tdt_bam_batch_data(const tdt_bam_reader *r, int64_t *
  * 0 refused (not a clean stream of exactly out_len bytes: the reader then lets zlib decide), < 0 bad argument.
  * The reader checks every block's CRC32 whichever decoder produced it. */
 TDT_BAM_API int tdt_bam_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t out_len);
+/* The CRC-32 the reader compares with a block's trailer (zlib's crc32(0, data, len); carry-less multiplication where the
+ * host has it). */
+TDT_BAM_API uint32_t tdt_bam_crc32(const uint8_t *data, int64_t len);
 
 #ifdef __cplusplus
 }

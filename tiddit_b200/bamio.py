@@ -260,6 +260,7 @@ BAM_SIGNATURES = {
     "tdt_bam_read_columns": (_i64, [_vp, _i64] + [_vp] * 12),
     "tdt_bam_batch_data": (_vp, [_vp, ctypes.POINTER(_i64)]),
     "tdt_bam_inflate_raw": (ctypes.c_int, [ctypes.c_char_p, _i64, _vp, _i64]),
+    "tdt_bam_crc32": (ctypes.c_uint32, [ctypes.c_char_p, _i64]),
 }
 _bam_lib = None
 

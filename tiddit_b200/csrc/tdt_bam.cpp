@@ -4,7 +4,7 @@
 // states its inflated size in its trailer, so the destinations are known up front), and records are decoded
 // from that buffer without copying (record boundaries by a sequential walk over the block_size words, the fields of
 // the records on a second small pool).  Blocks go through the whole-buffer decoder of tdt_inflate.h (r02 v6); zlib
-// computes the CRC of every block and inflates the ones that decoder refuses or gets wrong (TDT_BAM_ZLIB=1: all).
+// computes the CRC of every block and inflates the ones that decoder refuses or gets wrong (TDT_BAM_ZLIB=1: all, with zlib's CRC).
 #include "../../include/tdt_bam.h"
 #include "tdt_inflate.h"
 
@@ -210,8 +210,7 @@ int inflate_window(tdt_bam_reader *r, std::vector<uint8_t> &dst, size_t *nbytes,
             const Block &b = blocks[i];
             uint8_t *out = base + b.dst;
             // the trailer's CRC decides whether the fast decoder's bytes stand; zlib inflates whatever it does not
-            if (!zlib_only && tdtz::inflate_raw(ws.fast, b.payload, b.clen, out, b.isize) &&
-                (uint32_t)crc32(crc32(0L, Z_NULL, 0), out, b.isize) == b.crc)
+            if (!zlib_only && tdtz::inflate_raw(ws.fast, b.payload, b.clen, out, b.isize) && tdtz::crc32_of(out, b.isize) == b.crc)
                 continue;
             if (!ws.zs_ready) {
                 memset(&ws.zs, 0, sizeof ws.zs);
@@ -553,6 +552,8 @@ int tdt_bam_inflate_raw(const uint8_t *in, int64_t in_len, uint8_t *out, int64_t
     delete st;
     return ok ? 1 : 0;
 }
+
+uint32_t tdt_bam_crc32(const uint8_t *data, int64_t len) { return (data && len > 0) ? tdtz::crc32_of(data, (size_t)len) : 0u; }
 
 const uint8_t *tdt_bam_batch_data(const tdt_bam_reader *r, int64_t *len) {
     if (len) *len = (int64_t)r->bend;
